@@ -1,0 +1,133 @@
+// Kernel launch interface between the host runtime (context.cu / vec.cu / api.cu) and the CUDA kernels.
+// Every launcher is asynchronous on the given stream and returns the cudaError_t of the launch.
+#pragma once
+#include "modarith.cuh"
+
+namespace cnhe {
+
+// NTT tables of one modulus in HBM (N words each); the kernels index an array of these by modulus id:
+//   0..k-1 coefficient primes q_i, k..2k the BEHZ base Bsk (aux primes then m_sk), 2k+1.. plain moduli.
+struct NttTab {
+    const u64 *w, *ws;   // psi^bitrev(i) and floor(w 2^64 / p)        (forward, Cooley-Tukey order)
+    const u64 *iw, *iws; // psi^-bitrev(i) and its Shoup quotient       (inverse, Gentleman-Sande order)
+    u64 inv_n, inv_n_s;  // N^-1 mod p and its Shoup quotient
+    DMod mod;
+};
+
+// Base-2^w digit decomposition used by relinearisation / Galois key switching: digit d comes from residue
+// src[d] of the target polynomial, bits [shift[d], shift[d]+w).
+struct DigitMap {
+    unsigned char src[64];
+    unsigned char shift[64];
+    int D;
+    u64 mask;
+};
+
+enum NttLoad { NTT_LOAD_PLAIN = 0, NTT_LOAD_DIGIT = 1 };
+enum NttStore { NTT_STORE_PLAIN = 0, NTT_STORE_ADD = 1 };
+
+// In-place / out-of-place batched negacyclic NTT.  Polynomial b (0 <= b < n_polys) uses modulus
+// mod_base + (b % mod_count).  src == dst allowed.
+cudaError_t launch_ntt_forward(const u64 *src, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base, int mod_count,
+                               cudaStream_t s);
+cudaError_t launch_ntt_inverse(const u64 *src, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base, int mod_count,
+                               cudaStream_t s);
+// dst[((c*D + d)*k + l)] = NTT_l( digit d of target[c] )   target: [n_ct][k][N] coefficient form
+cudaError_t launch_ntt_forward_digits(const u64 *target, u64 *dst, int n_ct, int k, const DigitMap &dm, int logn, const NttTab *tabs,
+                                      cudaStream_t s);
+// dst[b] = INTT(src[b]) + base[b]  (mod p)
+cudaError_t launch_ntt_inverse_add(const u64 *src, const u64 *base, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base,
+                                   int mod_count, cudaStream_t s);
+int ntt_kernel_smem_bytes(int logn);
+
+} // namespace cnhe
+
+// ---------------------------------------------------------------------------------------------------------------
+namespace cnhe {
+
+constexpr int KMAX = 9; // up to 9 coefficient primes (N = 16384 default table)
+
+// Everything the BEHZ kernels need that depends only on (q, Bsk, m~): SEAL 3.2 util::BaseConverter::generate.
+struct BehzConst {
+    int k, centered_mtilde;
+    DMod q[KMAX], bsk[KMAX + 1];
+    u64 inv_qhat_mod_q[KMAX];        // (q/q_i)^-1 mod q_i
+    u64 mtilde_inv_qhat_mod_q[KMAX]; // m~ (q/q_i)^-1 mod q_i
+    u64 qhat_mod_mtilde[KMAX];       // (q/q_i) mod 2^32
+    u64 inv_q_mod_mtilde;            // q^-1 mod 2^32
+    u64 qhat_mod_bsk[KMAX + 1][KMAX];
+    u64 q_mod_bsk[KMAX + 1], inv_q_mod_bsk[KMAX + 1], inv_mtilde_mod_bsk[KMAX + 1];
+    u64 inv_bhat_mod_b[KMAX];        // (B/b_j)^-1 mod b_j
+    u64 bhat_mod_q[KMAX][KMAX];      // (B/b_j) mod q_i
+    u64 bhat_mod_msk[KMAX];
+    u64 inv_B_mod_msk, B_mod_q[KMAX];
+};
+// Per plaintext modulus t.
+struct PlainConst {
+    u64 t, threshold;                 // (t+1)/2
+    u64 delta[KMAX], q_mod_t[KMAX];   // floor(q/t) mod q_i, (q mod t) mod q_i
+    // decryption (Decryptor::decrypt, gamma base)
+    DMod tmod, gmod;
+    u64 tgamma_mod_q[KMAX], qhat_mod_t[KMAX], qhat_mod_gamma[KMAX];
+    u64 neg_inv_q_mod_t, neg_inv_q_mod_gamma, inv_gamma_mod_t, gamma;
+};
+
+// ---- elementwise over ciphertext words (words = n * size * k * N; residue of word w is (w / N) % k)
+cudaError_t launch_ct_add(const u64 *a, const u64 *b, u64 *out, size_t words, int k, int logn, const BehzConst *bc, int sub, cudaStream_t s);
+cudaError_t launch_ct_negate(const u64 *a, u64 *out, size_t words, int k, int logn, const BehzConst *bc, cudaStream_t s);
+// out = sum_j in_ptrs[j]  (AddMany)
+cudaError_t launch_ct_add_many(const u64 *const *in_ptrs, int n_in, u64 *out, size_t words, int k, int logn, const BehzConst *bc, cudaStream_t s);
+// ct (size polys) (+/-)= Delta*plain on c0; plain has `coeffs` coefficients mod t.  n cts, plain shared (plain_stride 0) or per ct.
+cudaError_t launch_ct_add_plain(const u64 *ct, u64 *out, int n, int size, const u64 *plain, size_t plain_stride, int coeffs, int k,
+                                int logn, const BehzConst *bc, PlainConst pc, int sub, cudaStream_t s);
+// out[n] = in[n] * scalar (constant plaintext, lifted per residue)      (multiply_plain monomial path, exponent 0)
+cudaError_t launch_ct_scale(const u64 *in, u64 *out, int n, int size, const u64 *scalars /*n values mod t, device*/, int k, int logn,
+                            const BehzConst *bc, PlainConst pc, cudaStream_t s);
+// lifted[l][x] = plain[x] (+ q_l - t if in the upper half)   (multiply_plain generic path)
+cudaError_t launch_plain_lift(const u64 *plain, u64 *lifted, int n, int coeffs, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
+// out[c][part][l][x] = a[c or 0][part][l][x] * b[c or 0][l][x]
+cudaError_t launch_dyadic_bcast(const u64 *a, const u64 *b, u64 *out, int n, int size, int a_per_ct, int b_per_ct, int k, int logn,
+                                const BehzConst *bc, cudaStream_t s);
+// Galois: out[c] = (perm(c0), 0), perm1[c] = perm(c1)   (util::apply_galois)
+cudaError_t launch_galois(const u64 *in, u64 *out_base, u64 *perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *bc, cudaStream_t s);
+
+// ---- K4: out[m] = sum_k w[m][k] * in[gather[m][k]] (+ Delta*bias[m] on coefficient 0 of c0)
+struct MacTile {
+    int n_out;       // outputs in this tile (<= 8) sharing one gather row
+    int gather_row;  // row index into gather[] (K entries)
+    int out_index[8];
+};
+// w_ptrs[m]: K weights mod t (device); bias[m] mod t or null
+cudaError_t launch_mac_layer(const u64 *const *in_ptrs, const int *gather, const MacTile *tiles, int n_tiles, const u64 *const *w_ptrs,
+                             const u64 *bias, int K, u64 *const *out_ptrs, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
+
+// ---- K5: BEHZ multiply pieces
+// in: ct pointers (each [2][k][N]); out together layout [n][2][2k+1][N] (q residues copied, then Bsk residues)
+cudaError_t launch_behz_lift(const u64 *const *ct_ptrs, u64 *out, int n, int logn, const BehzConst *bc, cudaStream_t s);
+// d[n][3][2k+1][N] from NTT-form a,b [n][2][2k+1][N]
+cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *d, int n, int k, int logn, const BehzConst *bc, cudaStream_t s);
+// d (coefficient form) -> times t, fast_floor, fastbconv_sk -> out3[n][3][k][N]
+cudaError_t launch_behz_floor(const u64 *d, u64 *out3, int n, u64 t, int logn, const BehzConst *bc, cudaStream_t s);
+// ---- K6: key-switch inner product. digits [n][D][k][N] (NTT), key [D][2][k][N] (NTT) -> acc [n][2][k][N] (NTT)
+cudaError_t launch_ks_mac(const u64 *digits, const u64 *key, u64 *acc, int n, int D, int k, int logn, const BehzConst *bc, cudaStream_t s);
+// split a size-3 array [n][3][k][N] view: base[n][2][k][N] = (c0,c1), c2[n][k][N]
+cudaError_t launch_split3(const u64 *ct3, u64 *base, u64 *c2, int n, int k, int logn, cudaStream_t s);
+
+// ---- sampling / encode / encrypt / decrypt
+enum SampleKind { SAMPLE_TERNARY = 0, SAMPLE_NOISE = 1, SAMPLE_UNIFORM = 2 };
+// out[i][l][x] for i<n: stream ids stream0 + i*stream_step (+ l for UNIFORM); lifted into each residue
+cudaError_t launch_sample(u64 *out, int n, int kind, u64 seed, u64 stream0, u64 stream_step, int k, int logn, const BehzConst *bc, cudaStream_t s);
+// plain[i][index_map[j]] = values[i][j]  (j < count), zero elsewhere
+cudaError_t launch_encode_scatter(const u64 *values, u64 *plain, int n, int count, const u32 *index_map, int logn, cudaStream_t s);
+cudaError_t launch_decode_gather(const u64 *plain_ntt, u64 *values, int n, const u32 *index_map, int logn, cudaStream_t s);
+// ct[i] (already u*pk, coefficient form) += (e0 + Delta*m_i, e1)
+cudaError_t launch_encrypt_finish(u64 *ct, const u64 *plain, size_t plain_stride, int n, int coeffs, u64 seed, u64 nonce0, int k, int logn,
+                                  const BehzConst *bc, PlainConst pc, cudaStream_t s);
+// x[n][k][N] = c0 + c1*s (coefficient form) -> plain[n][N]
+cudaError_t launch_decrypt_round(const u64 *x, u64 *plain, int n, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
+cudaError_t launch_fill_zero(u64 *p, size_t words, cudaStream_t s);
+// keys[d][0][src[d]][x] += factors[d] * target[src[d]][x]   (KeyGenerator: the 2^{jw} s' term of key-switching key d)
+cudaError_t launch_key_add_scaled(u64 *keys, const u64 *target, const u64 *factors, const DigitMap &dm, int k, int logn, const BehzConst *bc,
+                                  cudaStream_t s);
+
+} // namespace cnhe

@@ -1,0 +1,677 @@
+// Host runtime of libcnhe (see runtime.h).  Product code: builds every table with hostmath.h, never touches oracle/.
+#include "runtime.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "hostmath.h"
+
+namespace cnhe {
+
+void cuda_check(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) throw Error(-2, std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+
+DevBuf::DevBuf(size_t w, cudaStream_t s) : words(w), stream(s) {
+    if (w) CNHE_CUDA(cudaMallocAsync((void **)&p, w * sizeof(u64), s));
+}
+DevBuf::~DevBuf() {
+    if (p) cudaFreeAsync(p, stream);
+}
+
+static std::vector<BufRef> &temps_of(Context &c);
+struct TempStore {
+    std::map<Context *, std::vector<BufRef>> m;
+};
+static TempStore g_temps;
+static std::vector<BufRef> &temps_of(Context &c) { return g_temps.m[&c]; }
+
+u64 *Context::ws_alloc(size_t words) {
+    BufRef b = alloc(words ? words : 1);
+    temps_of(*this).push_back(b);
+    ws_used += words;
+    return b->p;
+}
+void Context::ws_reserve(size_t) {}
+void Context::sync() { CNHE_CUDA(cudaStreamSynchronize(stream)); }
+Context::~Context() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    g_temps.m.erase(this);
+    ch.clear();
+    if (d_bc) cudaFree(d_bc);
+    if (d_tabs) cudaFree(d_tabs);
+    if (d_table_mem) cudaFree(d_table_mem);
+    if (d_index_map) cudaFree(d_index_map);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+}
+// free the temporaries of the previous operation (stream ordered, so kernels still in flight keep their memory)
+void ws_release_all(Context &c) {
+    temps_of(c).clear();
+    c.ws_used = 0;
+}
+WsScope::WsScope(Context &ctx) : c(ctx), mark(temps_of(ctx).size()) {}
+WsScope::~WsScope() { temps_of(c).resize(mark); }
+
+std::vector<u64> default_coeff_modulus(uint32_t N) {
+    // DefaultParams.CoeffModulus128(N) of SEAL 3.2 ("HE Wrapper/AtomicSealBfvVector.cs:146"); values = the largest primes
+    // congruent to 1 mod 2N with bit sizes 54 | 36,36,37 | 43,43,44,44,44 | 48x3,49x6 (checked by tests/test_tables.py)
+    switch (N) {
+    case 2048: return {0x3fffffff000001ULL};
+    case 4096: return {0xffffee001ULL, 0xffffc4001ULL, 0x1ffffe0001ULL};
+    case 8192: return {0x7fffffd8001ULL, 0x7fffffc8001ULL, 0xfffffffc001ULL, 0xffffff6c001ULL, 0xfffffebc001ULL};
+    case 16384:
+        return {0xfffffffd8001ULL,  0xfffffffa0001ULL,  0xfffffff00001ULL,  0x1fffffff68001ULL, 0x1fffffff50001ULL,
+                0x1ffffffee8001ULL, 0x1ffffffea0001ULL, 0x1ffffffe88001ULL, 0x1ffffffe48001ULL};
+    default: return {};
+    }
+}
+
+static DMod make_dmod(u64 p) {
+    DMod m;
+    m.p = p;
+    hm::barrett_ratio(p, m.r0, m.r1);
+    return m;
+}
+static DigitMap make_digit_map(const std::vector<u64> &q, int w) {
+    DigitMap dm;
+    memset(&dm, 0, sizeof(dm));
+    int d = 0;
+    for (int i = 0; i < (int)q.size(); i++) {
+        int bits = hm::bit_length(q[i]);
+        for (int shift = 0; shift < bits; shift += w) {
+            if (d >= 64) throw Error(-1, "decomposition bit count too small: more than 64 digits");
+            dm.src[d] = (unsigned char)i;
+            dm.shift[d] = (unsigned char)shift;
+            d++;
+        }
+    }
+    dm.D = d;
+    dm.mask = w >= 64 ? ~0ULL : ((1ULL << w) - 1);
+    return dm;
+}
+
+Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *coeff, int k, int dbc_relin, int dbc_galois, int device) {
+    if (P < 1 || P > 16) throw Error(-1, "need 1..16 plaintext primes");
+    int logN = 0;
+    while ((1u << logN) < N) logN++;
+    if ((1u << logN) != N || logN < 10 || logN > 14) throw Error(-1, "PolyModulusDegree must be a power of two in [1024, 16384]");
+    if (k < 1 || k > KMAX) throw Error(-1, "need 1..9 coefficient primes");
+    if (dbc_relin < 1 || dbc_relin > 60 || dbc_galois < 1 || dbc_galois > 60) throw Error(-1, "decomposition bit count must be in [1,60]");
+    int ndev = 0;
+    cudaError_t de = cudaGetDeviceCount(&ndev);
+    if (de != cudaSuccess || ndev == 0) throw Error(-2, "libcnhe needs a CUDA device (B200); none is visible -- there is no CPU fallback");
+    if (device < 0 || device >= ndev) throw Error(-1, "bad device ordinal");
+    std::unique_ptr<Context> cp(new Context());
+    Context &c = *cp;
+    c.device = device;
+    CNHE_CUDA(cudaSetDevice(device));
+    c.N = N; c.logN = logN; c.k = k; c.P = P; c.dbc_relin = dbc_relin; c.dbc_galois = dbc_galois;
+    c.q.assign(coeff, coeff + k);
+    c.t.assign(plain_primes, plain_primes + P);
+    for (u64 p : c.q)
+        if (!hm::is_prime(p) || (p - 1) % (2ULL * N) || hm::bit_length(p) > 61) throw Error(-1, "coefficient moduli must be primes = 1 mod 2N below 2^61");
+    for (u64 p : c.t) {
+        if (!hm::is_prime(p) || (p - 1) % (2ULL * N)) throw Error(-1, "plaintext moduli must be primes = 1 mod 2N (batching)");
+        for (u64 qq : c.q)
+            if (p >= qq) throw Error(-1, "plaintext modulus must be smaller than every coefficient prime");
+    }
+    // Bsk = k auxiliary 61-bit primes (= 1 mod 2^18, descending, after m_sk and gamma) then m_sk   (SEAL small_mods)
+    const u64 M_SK = 0x1fffffffffe00001ULL, GAMMA = 0x1fffffffffc80001ULL;
+    {
+        u64 cand = (1ULL << 61) + 1;
+        int skipped = 0;
+        while ((int)c.bsk.size() < k) {
+            cand -= 1ULL << 18;
+            if (!hm::is_prime(cand)) continue;
+            if (skipped < 2) { skipped++; continue; }
+            c.bsk.push_back(cand);
+        }
+        c.bsk.push_back(M_SK);
+    }
+    CNHE_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CNHE_CUDA(cudaEventCreate(&c.ev0));
+    CNHE_CUDA(cudaEventCreate(&c.ev1));
+    {
+        cudaMemPool_t pool;
+        CNHE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thr = ~0ULL;
+        CNHE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    }
+    // ---- NTT tables: ids 0..k-1 q, k..2k Bsk, 2k+1+c plain modulus c
+    const int n_mod = 2 * k + 1 + P;
+    std::vector<u64> moduli;
+    for (u64 p : c.q) moduli.push_back(p);
+    for (u64 p : c.bsk) moduli.push_back(p);
+    for (u64 p : c.t) moduli.push_back(p);
+    std::vector<u64> host((size_t)n_mod * 4 * N);
+    CNHE_CUDA(cudaMalloc((void **)&c.d_table_mem, host.size() * sizeof(u64)));
+    c.h_tabs.resize(n_mod);
+    for (int m = 0; m < n_mod; m++) {
+        const u64 p = moduli[m];
+        const u64 psi = hm::minimal_primitive_root(2ULL * N, p), ipsi = hm::inv(psi, p);
+        u64 *w = &host[((size_t)m * 4 + 0) * N], *ws = w + N, *iw = ws + N, *iws = iw + N;
+        u64 a = 1, b = 1;
+        for (u64 i = 0; i < N; i++) {
+            const u64 r = hm::bit_reverse(i, logN);
+            w[r] = a; ws[r] = hm::shoup(a, p);
+            iw[r] = b; iws[r] = hm::shoup(b, p);
+            a = hm::mul(a, psi, p);
+            b = hm::mul(b, ipsi, p);
+        }
+        NttTab &tb = c.h_tabs[m];
+        u64 *base = c.d_table_mem + (size_t)m * 4 * N;
+        tb.w = base; tb.ws = base + N; tb.iw = base + 2 * (size_t)N; tb.iws = base + 3 * (size_t)N;
+        tb.inv_n = hm::inv(N % p, p);
+        tb.inv_n_s = hm::shoup(tb.inv_n, p);
+        tb.mod = make_dmod(p);
+    }
+    CNHE_CUDA(cudaMemcpy(c.d_table_mem, host.data(), host.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    CNHE_CUDA(cudaMalloc((void **)&c.d_tabs, n_mod * sizeof(NttTab)));
+    CNHE_CUDA(cudaMemcpy(c.d_tabs, c.h_tabs.data(), n_mod * sizeof(NttTab), cudaMemcpyHostToDevice));
+    // ---- BatchEncoder index map (BatchEncoder::populate_matrix_reps_index_map)
+    c.h_index_map.resize(N);
+    {
+        const u64 row = N >> 1, m2 = 2ULL * N;
+        u64 pos = 1;
+        for (u64 i = 0; i < row; i++) {
+            c.h_index_map[i] = (u32)hm::bit_reverse((pos - 1) >> 1, logN);
+            c.h_index_map[row | i] = (u32)hm::bit_reverse((m2 - pos - 1) >> 1, logN);
+            pos = (pos * 3) & (m2 - 1);
+        }
+    }
+    CNHE_CUDA(cudaMalloc((void **)&c.d_index_map, N * sizeof(u32)));
+    CNHE_CUDA(cudaMemcpy(c.d_index_map, c.h_index_map.data(), N * sizeof(u32), cudaMemcpyHostToDevice));
+    // ---- BEHZ constants (BaseConverter::generate)
+    BehzConst &bc = c.h_bc;
+    memset(&bc, 0, sizeof(bc));
+    bc.k = k;
+    bc.centered_mtilde = 0;
+    std::vector<u64> B(c.bsk.begin(), c.bsk.begin() + k);
+    for (int i = 0; i < k; i++) bc.q[i] = make_dmod(c.q[i]);
+    for (int j = 0; j <= k; j++) bc.bsk[j] = make_dmod(c.bsk[j]);
+    const u64 MT = 1ULL << 32;
+    u64 q_mod_mt = 1;
+    for (int i = 0; i < k; i++) q_mod_mt = (q_mod_mt * (c.q[i] & 0xffffffffULL)) & 0xffffffffULL;
+    {
+        u64 x = q_mod_mt; // Newton iteration for the inverse modulo 2^32 (q is odd)
+        for (int it = 0; it < 6; it++) x *= 2 - q_mod_mt * x;
+        bc.inv_q_mod_mtilde = x & 0xffffffffULL;
+    }
+    for (int i = 0; i < k; i++) {
+        const u64 qi = c.q[i];
+        const u64 inv = hm::inv(hm::product_mod(c.q, i, qi), qi);
+        bc.inv_qhat_mod_q[i] = inv;
+        bc.mtilde_inv_qhat_mod_q[i] = hm::mul(inv, MT % qi, qi);
+        u64 pm = 1;
+        for (int l = 0; l < k; l++)
+            if (l != i) pm = (pm * (c.q[l] & 0xffffffffULL)) & 0xffffffffULL;
+        bc.qhat_mod_mtilde[i] = pm;
+        bc.B_mod_q[i] = hm::product_mod(B, -1, qi);
+        for (int j = 0; j < k; j++) bc.bhat_mod_q[i][j] = hm::product_mod(B, j, qi);
+    }
+    for (int j = 0; j <= k; j++) {
+        const u64 bj = c.bsk[j];
+        for (int i = 0; i < k; i++) bc.qhat_mod_bsk[j][i] = hm::product_mod(c.q, i, bj);
+        bc.q_mod_bsk[j] = hm::product_mod(c.q, -1, bj);
+        bc.inv_q_mod_bsk[j] = hm::inv(bc.q_mod_bsk[j], bj);
+        bc.inv_mtilde_mod_bsk[j] = hm::inv(MT % bj, bj);
+    }
+    for (int j = 0; j < k; j++) {
+        bc.inv_bhat_mod_b[j] = hm::inv(hm::product_mod(B, j, B[j]), B[j]);
+        bc.bhat_mod_msk[j] = hm::product_mod(B, j, M_SK);
+    }
+    bc.inv_B_mod_msk = hm::inv(hm::product_mod(B, -1, M_SK), M_SK);
+    CNHE_CUDA(cudaMalloc((void **)&c.d_bc, sizeof(BehzConst)));
+    CNHE_CUDA(cudaMemcpy(c.d_bc, &bc, sizeof(BehzConst), cudaMemcpyHostToDevice));
+    // ---- per plaintext modulus
+    c.ch.resize(P);
+    for (int ci = 0; ci < P; ci++) {
+        Channel &ch = c.ch[ci];
+        const u64 t = c.t[ci];
+        ch.t = t;
+        ch.mod_id = 2 * k + 1 + ci;
+        PlainConst &pc = ch.pc;
+        memset(&pc, 0, sizeof(pc));
+        pc.t = t;
+        pc.threshold = (t + 1) >> 1;
+        pc.gamma = GAMMA;
+        pc.tmod = make_dmod(t);
+        pc.gmod = make_dmod(GAMMA);
+        std::vector<u64> quot;
+        u64 rem;
+        hm::div_product(c.q, t, quot, rem);
+        for (int i = 0; i < k; i++) {
+            pc.delta[i] = hm::limbs_mod(quot, c.q[i]);
+            pc.q_mod_t[i] = rem % c.q[i];
+            pc.tgamma_mod_q[i] = hm::mul(t % c.q[i], GAMMA % c.q[i], c.q[i]);
+            pc.qhat_mod_t[i] = hm::product_mod(c.q, i, t);
+            pc.qhat_mod_gamma[i] = hm::product_mod(c.q, i, GAMMA);
+        }
+        pc.neg_inv_q_mod_t = hm::neg(hm::inv(hm::product_mod(c.q, -1, t), t), t);
+        pc.neg_inv_q_mod_gamma = hm::neg(hm::inv(hm::product_mod(c.q, -1, GAMMA), GAMMA), GAMMA);
+        pc.inv_gamma_mod_t = hm::inv(GAMMA % t, t);
+    }
+    c.dm_relin = make_digit_map(c.q, dbc_relin);
+    c.dm_galois = make_digit_map(c.q, dbc_galois);
+    // Galois elements of KeyGenerator::galois_keys(dbc): 2N-1, then 3^(2^i), 3^-(2^i) for i < logN-1
+    {
+        const u64 m2 = 2ULL * N;
+        c.galois_elts.push_back(m2 - 1);
+        u64 p3 = 3, n3 = 0;
+        for (u64 x = 1; x < m2; x += 2)
+            if (((x * 3) & (m2 - 1)) == 1) { n3 = x; break; }
+        for (int i = 0; i < logN - 1; i++) {
+            c.galois_elts.push_back(p3);
+            p3 = (p3 * p3) & (m2 - 1);
+            c.galois_elts.push_back(n3);
+            n3 = (n3 * n3) & (m2 - 1);
+        }
+    }
+    // ---- wrapper CRT data (EncryptedSealBfvEnvironment.PreCompute, "EncryptedSealBfvVector.cs:79-90")
+    {
+        unsigned __int128 big = 1;
+        int bits = 0;
+        for (u64 t : c.t) bits += hm::bit_length(t);
+        if (bits > 126) throw Error(-1, "product of the plaintext moduli must stay below 2^126");
+        for (u64 t : c.t) big *= t;
+        c.big_factor = big;
+        for (int i = 0; i < P; i++) {
+            unsigned __int128 minor = big / c.t[i];
+            u64 y = hm::inv((u64)(minor % c.t[i]), c.t[i]);
+            c.crt_coeff.push_back(minor * y);
+        }
+    }
+    CNHE_CUDA(cudaDeviceSynchronize());
+    return cp.release();
+}
+
+// ---------------------------------------------------------------- pointer tables
+const u64 *const *upload_ptrs(Context &c, const std::vector<const u64 *> &ptrs) {
+    u64 *d = c.ws_alloc(ptrs.size());
+    CNHE_CUDA(cudaMemcpyAsync(d, ptrs.data(), ptrs.size() * sizeof(u64 *), cudaMemcpyHostToDevice, c.stream));
+    return reinterpret_cast<const u64 *const *>(d);
+}
+u64 *const *upload_ptrs_mut(Context &c, const std::vector<u64 *> &ptrs) {
+    u64 *d = c.ws_alloc(ptrs.size());
+    CNHE_CUDA(cudaMemcpyAsync(d, ptrs.data(), ptrs.size() * sizeof(u64 *), cudaMemcpyHostToDevice, c.stream));
+    return reinterpret_cast<u64 *const *>(d);
+}
+
+// ---------------------------------------------------------------- core operations
+void op_ntt(Context &c, const u64 *src, u64 *dst, int n_polys, int mod_base, int mod_count, bool inverse) {
+    c.check(inverse ? launch_ntt_inverse(src, dst, n_polys, c.logN, c.d_tabs, mod_base, mod_count, c.stream)
+                    : launch_ntt_forward(src, dst, n_polys, c.logN, c.d_tabs, mod_base, mod_count, c.stream),
+            "ntt");
+}
+
+void op_key_switch(Context &c, const u64 *target, int n, const u64 *key, const DigitMap &dm, const u64 *base, u64 *out) {
+    const int k = c.k;
+    const size_t N = c.N;
+    for (int c0 = 0; c0 < n; c0 += c.chunk) {
+        WsScope scope(c);
+        const int m = std::min(c.chunk, n - c0);
+        u64 *digits = c.ws_alloc((size_t)m * dm.D * k * N);
+        u64 *acc = c.ws_alloc((size_t)m * 2 * k * N);
+        c.check(launch_ntt_forward_digits(target + (size_t)c0 * k * N, digits, m, k, dm, c.logN, c.d_tabs, c.stream), "ntt_forward_digits");
+        c.check(launch_ks_mac(digits, key, acc, m, dm.D, k, c.logN, c.d_bc, c.stream), "ks_mac");
+        c.check(launch_ntt_inverse_add(acc, base + (size_t)c0 * 2 * k * N, out + (size_t)c0 * 2 * k * N, m * 2 * k, c.logN, c.d_tabs, 0, k, c.stream),
+                "ntt_inverse_add");
+    }
+}
+
+static void multiply_chunk(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, int c0, int m, u64 *out3) {
+    const int k = c.k, kt = 2 * k + 1;
+    const size_t N = c.N;
+    bool square = true;
+    for (int i = 0; i < m; i++) square = square && a[c0 + i] == b[c0 + i];
+    std::vector<const u64 *> pa(a.begin() + c0, a.begin() + c0 + m);
+    u64 *A = c.ws_alloc((size_t)m * 2 * kt * N);
+    c.check(launch_behz_lift(upload_ptrs(c, pa), A, m, c.logN, c.d_bc, c.stream), "behz_lift");
+    c.check(launch_ntt_forward(A, A, m * 2 * kt, c.logN, c.d_tabs, 0, kt, c.stream), "ntt_forward");
+    u64 *B = A;
+    if (!square) {
+        std::vector<const u64 *> pb(b.begin() + c0, b.begin() + c0 + m);
+        B = c.ws_alloc((size_t)m * 2 * kt * N);
+        c.check(launch_behz_lift(upload_ptrs(c, pb), B, m, c.logN, c.d_bc, c.stream), "behz_lift");
+        c.check(launch_ntt_forward(B, B, m * 2 * kt, c.logN, c.d_tabs, 0, kt, c.stream), "ntt_forward");
+    }
+    u64 *D = c.ws_alloc((size_t)m * 3 * kt * N);
+    c.check(launch_behz_tensor(A, B, D, m, k, c.logN, c.d_bc, c.stream), "behz_tensor");
+    c.check(launch_ntt_inverse(D, D, m * 3 * kt, c.logN, c.d_tabs, 0, kt, c.stream), "ntt_inverse");
+    c.check(launch_behz_floor(D, out3, m, c.ch[ch].t, c.logN, c.d_bc, c.stream), "behz_floor");
+}
+void op_multiply(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out3) {
+    const int n = (int)a.size();
+    for (int c0 = 0; c0 < n; c0 += c.chunk) {
+        WsScope scope(c);
+        const int m = std::min(c.chunk, n - c0);
+        multiply_chunk(c, ch, a, b, c0, m, out3 + (size_t)c0 * 3 * c.k * c.N);
+    }
+}
+void op_relinearize(Context &c, int ch, const u64 *in3, int n, u64 *out2) {
+    if (!c.ch[ch].have_rlk) throw Error(-3, "relinearization keys are missing");
+    const int k = c.k;
+    const size_t N = c.N;
+    for (int c0 = 0; c0 < n; c0 += c.chunk) {
+        const int m = std::min(c.chunk, n - c0);
+        u64 *base = c.ws_alloc((size_t)m * 2 * k * N), *c2 = c.ws_alloc((size_t)m * k * N);
+        c.check(launch_split3(in3 + (size_t)c0 * 3 * k * N, base, c2, m, k, c.logN, c.stream), "split3");
+        op_key_switch(c, c2, m, c.ch[ch].rlk->p, c.dm_relin, base, out2 + (size_t)c0 * 2 * k * N);
+    }
+}
+void op_multiply_relin(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out2) {
+    if (!c.ch[ch].have_rlk) throw Error(-3, "relinearization keys are missing");
+    const int n = (int)a.size(), k = c.k;
+    const size_t N = c.N;
+    for (int c0 = 0; c0 < n; c0 += c.chunk) {
+        WsScope scope(c); // stream-ordered frees: the next chunk reuses the pool memory once these kernels are done
+        const int m = std::min(c.chunk, n - c0);
+        u64 *ct3 = c.ws_alloc((size_t)m * 3 * k * N);
+        multiply_chunk(c, ch, a, b, c0, m, ct3);
+        u64 *base = c.ws_alloc((size_t)m * 2 * k * N), *c2 = c.ws_alloc((size_t)m * k * N);
+        c.check(launch_split3(ct3, base, c2, m, k, c.logN, c.stream), "split3");
+        op_key_switch(c, c2, m, c.ch[ch].rlk->p, c.dm_relin, base, out2 + (size_t)c0 * 2 * k * N);
+    }
+}
+
+u64 galois_elt_from_step(const Context &c, int steps) { // Evaluator::galois_elt_from_step: positive = rotate left
+    const u64 n = c.N, m = 2 * n;
+    if (steps == 0) return m - 1;
+    const bool neg = steps < 0;
+    const u64 pos = neg ? (u64)(-(long long)steps) : (u64)steps;
+    if (pos >= (n >> 1)) throw Error(-1, "step count too large");
+    const u64 s = neg ? (n >> 1) - pos : pos;
+    u64 e = 1;
+    for (u64 i = 0; i < s; i++) e = (e * 3) & (m - 1);
+    return e;
+}
+void op_apply_galois(Context &c, int ch, const u64 *in, int n, u64 elt, u64 *out) {
+    auto it = c.ch[ch].glk.find(elt);
+    if (it == c.ch[ch].glk.end()) throw Error(-3, "Galois key not present");
+    const int k = c.k;
+    const size_t N = c.N;
+    const u64 m2 = 2ULL * N;
+    u64 einv = 0;
+    for (u64 x = 1; x < m2; x += 2)
+        if (((x * elt) & (m2 - 1)) == 1) { einv = x; break; }
+    for (int c0 = 0; c0 < n; c0 += c.chunk) {
+        const int m = std::min(c.chunk, n - c0);
+        u64 *base = c.ws_alloc((size_t)m * 2 * k * N), *p1 = c.ws_alloc((size_t)m * k * N);
+        c.check(launch_galois(in + (size_t)c0 * 2 * k * N, base, p1, m, einv, k, c.logN, c.d_bc, c.stream), "galois");
+        op_key_switch(c, p1, m, it->second->p, c.dm_galois, base, out + (size_t)c0 * 2 * k * N);
+    }
+}
+static std::vector<int> naf(int value) { // non-adjacent form, least significant term first (SEAL util::naf)
+    std::vector<int> res;
+    const bool sign = value < 0;
+    int v = sign ? -value : value;
+    for (int i = 0; v; i++) {
+        const int zi = (v & 1) ? 2 - (v & 3) : 0;
+        v = (v - zi) >> 1;
+        if (zi) res.push_back((sign ? -zi : zi) * (1 << i));
+    }
+    return res;
+}
+void op_rotate_rows(Context &c, int ch, const u64 *in, int n, int steps, u64 *out) { // Evaluator::rotate_internal
+    const size_t words = (size_t)n * c.ct_words();
+    if (steps == 0) {
+        if (in != out) CNHE_CUDA(cudaMemcpyAsync(out, in, words * 8, cudaMemcpyDeviceToDevice, c.stream));
+        return;
+    }
+    const u64 elt = galois_elt_from_step(c, steps);
+    if (c.ch[ch].glk.count(elt)) { op_apply_galois(c, ch, in, n, elt, out); return; }
+    std::vector<int> hops = naf(steps);
+    if (hops.size() == 1) throw Error(-3, "Galois key not present");
+    const u64 *cur = in;
+    for (size_t h = 0; h < hops.size(); h++) {
+        if ((size_t)std::abs(hops[h]) == (c.N >> 1)) continue;
+        u64 *nxt = (h + 1 == hops.size()) ? out : c.ws_alloc(words);
+        op_rotate_rows(c, ch, cur, n, hops[h], nxt);
+        cur = nxt;
+    }
+    if (cur != out) CNHE_CUDA(cudaMemcpyAsync(out, cur, words * 8, cudaMemcpyDeviceToDevice, c.stream));
+}
+void op_rotate_columns(Context &c, int ch, const u64 *in, int n, u64 *out) { op_apply_galois(c, ch, in, n, 2ULL * c.N - 1, out); }
+
+void op_multiply_plain_dense(Context &c, int ch, const u64 *ct, int n, const u64 *plain, bool plain_per_ct, u64 *out) {
+    const int k = c.k;
+    const size_t N = c.N;
+    const int np = plain_per_ct ? n : 1;
+    u64 *lifted = c.ws_alloc((size_t)np * k * N);
+    c.check(launch_plain_lift(plain, lifted, np, (int)N, k, c.logN, c.d_bc, c.ch[ch].pc, c.stream), "plain_lift");
+    c.check(launch_ntt_forward(lifted, lifted, np * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+    u64 *tmp = c.ws_alloc((size_t)n * 2 * k * N);
+    c.check(launch_ntt_forward(ct, tmp, n * 2 * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+    c.check(launch_dyadic_bcast(tmp, lifted, tmp, n, 2, 1, plain_per_ct ? 1 : 0, k, c.logN, c.d_bc, c.stream), "dyadic");
+    c.check(launch_ntt_inverse(tmp, out, n * 2 * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_inverse");
+}
+void op_encode(Context &c, int ch, const u64 *values, int n, int count, u64 *plain) {
+    c.check(launch_encode_scatter(values, plain, n, count, c.d_index_map, c.logN, c.stream), "encode_scatter");
+    c.check(launch_ntt_inverse(plain, plain, n, c.logN, c.d_tabs, c.ch[ch].mod_id, 1, c.stream), "ntt_inverse(t)");
+}
+void op_decode(Context &c, int ch, const u64 *plain, int n, u64 *values) {
+    u64 *tmp = c.ws_alloc((size_t)n * c.N);
+    c.check(launch_ntt_forward(plain, tmp, n, c.logN, c.d_tabs, c.ch[ch].mod_id, 1, c.stream), "ntt_forward(t)");
+    c.check(launch_decode_gather(tmp, values, n, c.d_index_map, c.logN, c.stream), "decode_gather");
+}
+void op_encrypt(Context &c, int chi, const u64 *plain, size_t plain_stride, int n, int coeffs, u64 nonce0, u64 *ct) {
+    Channel &ch = c.ch[chi];
+    if (!ch.have_pk) throw Error(-3, "public key is missing");
+    const int k = c.k;
+    const size_t N = c.N;
+    for (int c0 = 0; c0 < n; c0 += 4 * c.chunk) {
+        const int m = std::min(4 * c.chunk, n - c0);
+        u64 *u = c.ws_alloc((size_t)m * k * N);
+        c.check(launch_sample(u, m, SAMPLE_TERNARY, ch.seed, stream_id(8, nonce0 + c0, 0), 1ULL << 16, k, c.logN, c.d_bc, c.stream), "sample");
+        c.check(launch_ntt_forward(u, u, m * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+        u64 *dst = ct + (size_t)c0 * 2 * k * N;
+        c.check(launch_dyadic_bcast(ch.pk->p, u, dst, m, 2, 0, 1, k, c.logN, c.d_bc, c.stream), "dyadic");
+        c.check(launch_ntt_inverse(dst, dst, m * 2 * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_inverse");
+        c.check(launch_encrypt_finish(dst, plain ? plain + (size_t)c0 * plain_stride : nullptr, plain_stride, m, plain ? coeffs : 0, ch.seed,
+                                      nonce0 + c0, k, c.logN, c.d_bc, ch.pc, c.stream),
+                "encrypt_finish");
+    }
+}
+static void dot_with_secret(Context &c, int chi, const u64 *ct, int n, u64 *x) {
+    Channel &ch = c.ch[chi];
+    if (!ch.have_sk) throw Error(-3, "secret key is missing");
+    const int k = c.k;
+    const size_t N = c.N, kN = (size_t)k * N;
+    u64 *c0 = c.ws_alloc((size_t)n * kN), *c1 = c.ws_alloc((size_t)n * kN);
+    CNHE_CUDA(cudaMemcpy2DAsync(c0, kN * 8, ct, 2 * kN * 8, kN * 8, n, cudaMemcpyDeviceToDevice, c.stream));
+    CNHE_CUDA(cudaMemcpy2DAsync(c1, kN * 8, ct + kN, 2 * kN * 8, kN * 8, n, cudaMemcpyDeviceToDevice, c.stream));
+    c.check(launch_ntt_forward(c1, c1, n * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+    c.check(launch_dyadic_bcast(c1, ch.sk->p, c1, n, 1, 1, 0, k, c.logN, c.d_bc, c.stream), "dyadic");
+    c.check(launch_ntt_inverse_add(c1, c0, x, n * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_inverse_add");
+}
+void op_decrypt(Context &c, int chi, const u64 *ct, int n, u64 *plain) {
+    u64 *x = c.ws_alloc((size_t)n * c.k * c.N);
+    dot_with_secret(c, chi, ct, n, x);
+    c.check(launch_decrypt_round(x, plain, n, c.k, c.logN, c.d_bc, c.ch[chi].pc, c.stream), "decrypt_round");
+}
+// Decryptor::invariant_noise_budget: bits(q) - bits(|t * (c0 + c1 s) mod q|_centred) - 1, composed on the host
+int op_noise_budget(Context &c, int chi, const u64 *ct) {
+    const int k = c.k;
+    const size_t N = c.N;
+    u64 *x = c.ws_alloc((size_t)k * N);
+    dot_with_secret(c, chi, ct, 1, x);
+    std::vector<u64> h((size_t)k * N);
+    CNHE_CUDA(cudaMemcpyAsync(h.data(), x, h.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    typedef std::vector<u64> Big;
+    auto mul_small = [](const Big &a, u64 b) {
+        Big r(a.size() + 1, 0);
+        u64 carry = 0;
+        for (size_t i = 0; i < a.size(); i++) {
+            unsigned __int128 v = (unsigned __int128)a[i] * b + carry;
+            r[i] = (u64)v;
+            carry = (u64)(v >> 64);
+        }
+        r[a.size()] = carry;
+        return r;
+    };
+    auto add_to = [](Big &a, const Big &b) {
+        if (a.size() < b.size() + 1) a.resize(b.size() + 1, 0);
+        u64 carry = 0;
+        for (size_t i = 0; i < a.size(); i++) {
+            unsigned __int128 v = (unsigned __int128)a[i] + (i < b.size() ? b[i] : 0) + carry;
+            a[i] = (u64)v;
+            carry = (u64)(v >> 64);
+        }
+    };
+    auto cmp = [](const Big &a, const Big &b) {
+        size_t n = std::max(a.size(), b.size());
+        for (size_t i = n; i-- > 0;) {
+            u64 x = i < a.size() ? a[i] : 0, y = i < b.size() ? b[i] : 0;
+            if (x != y) return x < y ? -1 : 1;
+        }
+        return 0;
+    };
+    auto sub_from = [](Big &a, const Big &b) {
+        u64 borrow = 0;
+        for (size_t i = 0; i < a.size(); i++) {
+            u64 y = i < b.size() ? b[i] : 0;
+            unsigned __int128 v = (unsigned __int128)a[i] - y - borrow;
+            a[i] = (u64)v;
+            borrow = (u64)(v >> 64) ? 1 : 0;
+        }
+    };
+    auto bits = [](const Big &a) {
+        for (size_t i = a.size(); i-- > 0;)
+            if (a[i]) return (int)(i * 64 + 64 - __builtin_clzll(a[i]));
+        return 0;
+    };
+    Big Q{1};
+    for (u64 p : c.q) Q = mul_small(Q, p);
+    std::vector<Big> qhat(k, Big{1});
+    for (int i = 0; i < k; i++)
+        for (int l = 0; l < k; l++)
+            if (l != i) qhat[i] = mul_small(qhat[i], c.q[l]);
+    Big half = Q;
+    {
+        unsigned __int128 r = 0;
+        for (size_t i = half.size(); i-- > 0;) {
+            unsigned __int128 cur = (r << 64) | half[i];
+            half[i] = (u64)(cur / 2);
+            r = cur % 2;
+        }
+    }
+    int maxbits = 0;
+    const u64 t = c.ch[chi].t;
+    for (size_t n = 0; n < N; n++) {
+        Big acc{0};
+        for (int i = 0; i < k; i++) {
+            u64 v = hm::mul(hm::mul(h[i * N + n], t % c.q[i], c.q[i]), c.h_bc.inv_qhat_mod_q[i], c.q[i]);
+            add_to(acc, mul_small(qhat[i], v));
+        }
+        while (cmp(acc, Q) >= 0) sub_from(acc, Q);
+        if (cmp(acc, half) > 0) {
+            Big tmp = Q;
+            tmp.resize(std::max(tmp.size(), acc.size()), 0);
+            sub_from(tmp, acc);
+            acc = tmp;
+        }
+        maxbits = std::max(maxbits, bits(acc));
+    }
+    int b = bits(Q) - maxbits - 1;
+    return b < 0 ? 0 : b;
+}
+
+// ---------------------------------------------------------------- keys (KeyGenerator of SEAL 3.2, sampled on the device)
+BufRef &key_slot(Context &c, int channel, int what, u64 arg, size_t &words, bool create) {
+    if (channel < 0 || channel >= c.P) throw Error(-1, "bad channel");
+    Channel &ch = c.ch[channel];
+    const size_t kN = (size_t)c.k * c.N;
+    BufRef *slot = nullptr;
+    switch (what) {
+    case 0: words = kN; slot = &ch.sk; break;
+    case 1: words = 2 * kN; slot = &ch.pk; break;
+    case 2: words = (size_t)c.dm_relin.D * 2 * kN; slot = &ch.rlk; break;
+    case 3:
+        words = (size_t)c.dm_galois.D * 2 * kN;
+        if (!create && !ch.glk.count(arg)) throw Error(-3, "Galois key not present");
+        slot = &ch.glk[arg];
+        break;
+    default: throw Error(-1, "bad key kind");
+    }
+    if (create && !*slot) *slot = c.alloc(words);
+    if (!*slot) throw Error(-3, "key is missing");
+    return *slot;
+}
+// key-switching keys for `target` (k*N, NTT form): key (i,j) = (-(a s + e) + [residue i] 2^{jw} target, a)
+static void make_kskeys(Context &c, Channel &ch, const u64 *target_ntt, const DigitMap &dm, int w, u64 purpose_a, u64 purpose_e, u64 key_tag, u64 *out) {
+    const int k = c.k, D = dm.D;
+    const size_t N = c.N, kN = (size_t)k * N;
+    // c1 = a (uniform), written in place: key d part 1
+    u64 *e = c.ws_alloc((size_t)D * kN), *as = c.ws_alloc((size_t)D * kN), *a = c.ws_alloc((size_t)D * kN);
+    c.check(launch_sample(a, D, SAMPLE_UNIFORM, ch.seed, stream_id(purpose_a, key_tag * 256, 0), 1ULL << 16, k, c.logN, c.d_bc, c.stream), "sample");
+    c.check(launch_sample(e, D, SAMPLE_NOISE, ch.seed, stream_id(purpose_e, key_tag * 256, 0), 1ULL << 16, k, c.logN, c.d_bc, c.stream), "sample");
+    c.check(launch_ntt_forward(e, e, D * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+    c.check(launch_dyadic_bcast(a, ch.sk->p, as, D, 1, 1, 0, k, c.logN, c.d_bc, c.stream), "dyadic");
+    c.check(launch_ct_add(as, e, as, (size_t)D * kN, k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+    c.check(launch_ct_negate(as, as, (size_t)D * kN, k, c.logN, c.d_bc, c.stream), "ct_negate");
+    // interleave into [D][2][k][N]
+    CNHE_CUDA(cudaMemcpy2DAsync(out, 2 * kN * 8, as, kN * 8, kN * 8, D, cudaMemcpyDeviceToDevice, c.stream));
+    CNHE_CUDA(cudaMemcpy2DAsync(out + kN, 2 * kN * 8, a, kN * 8, kN * 8, D, cudaMemcpyDeviceToDevice, c.stream));
+    // add 2^{jw} * target on residue src[d] of c0 of key d
+    std::vector<u64> factors(D);
+    for (int d = 0; d < D; d++) factors[d] = hm::pw(2, (u64)dm.shift[d], c.q[dm.src[d]]);
+    (void)w;
+    u64 *dfac = c.ws_alloc(D);
+    CNHE_CUDA(cudaMemcpyAsync(dfac, factors.data(), D * 8, cudaMemcpyHostToDevice, c.stream));
+    c.check(launch_key_add_scaled(out, target_ntt, dfac, dm, k, c.logN, c.d_bc, c.stream), "key_add_scaled");
+}
+void keys_generate(Context &c, u64 seed) {
+    const int k = c.k;
+    const size_t N = c.N, kN = (size_t)k * N;
+    for (int ci = 0; ci < c.P; ci++) {
+        Channel &ch = c.ch[ci];
+        ch.seed = seed + (u64)ci;
+        ch.nonce = 1;
+        size_t words;
+        // secret key: ternary, kept in NTT form (and a coefficient-form copy for the Galois keys)
+        BufRef &sk = key_slot(c, ci, 0, 0, words, true);
+        u64 *sk_coeff = c.ws_alloc(kN);
+        c.check(launch_sample(sk_coeff, 1, SAMPLE_TERNARY, ch.seed, stream_id(1, 0, 0), 0, k, c.logN, c.d_bc, c.stream), "sample");
+        c.check(launch_ntt_forward(sk_coeff, sk->p, k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+        ch.have_sk = true;
+        // public key (-(a s + e), a)
+        BufRef &pk = key_slot(c, ci, 1, 0, words, true);
+        u64 *e = c.ws_alloc(kN), *as = c.ws_alloc(kN);
+        c.check(launch_sample(pk->p + kN, 1, SAMPLE_UNIFORM, ch.seed, stream_id(2, 0, 0), 0, k, c.logN, c.d_bc, c.stream), "sample");
+        c.check(launch_sample(e, 1, SAMPLE_NOISE, ch.seed, stream_id(3, 0, 0), 0, k, c.logN, c.d_bc, c.stream), "sample");
+        c.check(launch_ntt_forward(e, e, k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+        c.check(launch_dyadic_bcast(pk->p + kN, sk->p, as, 1, 1, 1, 0, k, c.logN, c.d_bc, c.stream), "dyadic");
+        c.check(launch_ct_add(as, e, as, kN, k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+        c.check(launch_ct_negate(as, pk->p, kN, k, c.logN, c.d_bc, c.stream), "ct_negate");
+        ch.have_pk = true;
+        // relinearization keys for s^2
+        BufRef &rlk = key_slot(c, ci, 2, 0, words, true);
+        u64 *s2 = c.ws_alloc(kN);
+        c.check(launch_dyadic_bcast(sk->p, sk->p, s2, 1, 1, 1, 0, k, c.logN, c.d_bc, c.stream), "dyadic");
+        make_kskeys(c, ch, s2, c.dm_relin, c.dbc_relin, 4, 5, 0, rlk->p);
+        ch.have_rlk = true;
+        // Galois keys: s(x^elt) in NTT form
+        for (size_t gi = 0; gi < c.galois_elts.size(); gi++) {
+            const u64 elt = c.galois_elts[gi], m2 = 2ULL * N;
+            u64 einv = 0;
+            for (u64 x = 1; x < m2; x += 2)
+                if (((x * elt) & (m2 - 1)) == 1) { einv = x; break; }
+            // reuse the ciphertext Galois kernel on (sk_coeff, sk_coeff): perm_c1 receives the permuted second part
+            u64 *pair = c.ws_alloc(2 * kN), *base = c.ws_alloc(2 * kN), *rs = c.ws_alloc(kN);
+            CNHE_CUDA(cudaMemcpyAsync(pair, sk_coeff, kN * 8, cudaMemcpyDeviceToDevice, c.stream));
+            CNHE_CUDA(cudaMemcpyAsync(pair + kN, sk_coeff, kN * 8, cudaMemcpyDeviceToDevice, c.stream));
+            c.check(launch_galois(pair, base, rs, 1, einv, k, c.logN, c.d_bc, c.stream), "galois");
+            c.check(launch_ntt_forward(rs, rs, k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+            BufRef &gk = key_slot(c, ci, 3, elt, words, true);
+            make_kskeys(c, ch, rs, c.dm_galois, c.dbc_galois, 6, 7, gi + 1, gk->p);
+        }
+        c.sync();
+        ws_release_all(c);
+    }
+}
+
+} // namespace cnhe

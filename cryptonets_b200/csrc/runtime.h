@@ -1,0 +1,124 @@
+// Host runtime of libcnhe: context (device tables, keys, workspace) and the ciphertext-array operations the vector
+// layer (vec.cu) is built from.  Mirrors AtomicSealBfvEncryptedEnvironment ("HE Wrapper/AtomicSealBfvVector.cs:19-206")
+// plus the SEAL objects it owns (SEALContext, KeyGenerator, Evaluator, Encryptor, Decryptor, BatchEncoder).
+#pragma once
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace cnhe {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+void cuda_check(cudaError_t e, const char *what);
+#define CNHE_CUDA(x) ::cnhe::cuda_check((x), #x)
+
+// Reference-counted device allocation (stream-ordered pool).
+struct DevBuf {
+    u64 *p = nullptr;
+    size_t words = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf(size_t w, cudaStream_t s);
+    ~DevBuf();
+    DevBuf(const DevBuf &) = delete;
+};
+typedef std::shared_ptr<DevBuf> BufRef;
+
+struct Channel { // one plaintext modulus (one AtomicSealBfvEncryptedEnvironment)
+    u64 t = 0;
+    PlainConst pc;
+    int mod_id = 0; // NTT table id of t
+    bool have_sk = false, have_pk = false, have_rlk = false;
+    BufRef sk, pk, rlk;
+    std::map<u64, BufRef> glk;
+    u64 seed = 0;
+    u64 nonce = 1; // running encryption counter
+};
+
+struct Context {
+    int device = 0;
+    uint32_t N = 0;
+    int logN = 0, k = 0, P = 0, dbc_relin = 0, dbc_galois = 0;
+    std::vector<u64> q, bsk, t;
+    BehzConst h_bc;
+    BehzConst *d_bc = nullptr;
+    std::vector<NttTab> h_tabs;
+    NttTab *d_tabs = nullptr;
+    u64 *d_table_mem = nullptr;
+    std::vector<u32> h_index_map;
+    u32 *d_index_map = nullptr;
+    DigitMap dm_relin, dm_galois;
+    std::vector<u64> galois_elts;
+    std::vector<Channel> ch;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::recursive_mutex mu;
+    int chunk = 128;
+    uint64_t launches = 0;
+    // workspace arena (grown on demand, reused by every op)
+    u64 *ws = nullptr;
+    size_t ws_words = 0, ws_used = 0;
+    // host CRT data of the wrapper ("HE Wrapper/EncryptedSealBfvVector.cs:79-90")
+    unsigned __int128 big_factor = 0;
+    std::vector<unsigned __int128> crt_coeff;
+
+    ~Context();
+    size_t ct_words() const { return (size_t)2 * k * N; }
+    void ws_reset() { ws_used = 0; }
+    u64 *ws_alloc(size_t words);   // valid until the next ws_reset(); may synchronise when growing
+    void ws_reserve(size_t words); // grow before taking pointers
+    BufRef alloc(size_t words) { return std::make_shared<DevBuf>(words, stream); }
+    void launched(int n = 1) { launches += n; }
+    void check(cudaError_t e, const char *what) { cuda_check(e, what); launched(); }
+    void sync();
+};
+
+void ws_release_all(Context &c); // drop every workspace temporary (call at the start of a public operation)
+struct WsScope {                  // temporaries allocated inside the scope are released when it ends
+    Context &c;
+    size_t mark;
+    explicit WsScope(Context &ctx);
+    ~WsScope();
+};
+
+Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *coeff, int k, int dbc_relin, int dbc_galois, int device);
+std::vector<u64> default_coeff_modulus(uint32_t N);
+
+// ---- keys
+void keys_generate(Context &c, u64 seed);
+BufRef &key_slot(Context &c, int channel, int what, u64 arg, size_t &words, bool create);
+
+// ---- ciphertext-array operations (all asynchronous on c.stream; device pointers)
+// upload a host array of device pointers into workspace memory
+const u64 *const *upload_ptrs(Context &c, const std::vector<const u64 *> &ptrs);
+u64 *const *upload_ptrs_mut(Context &c, const std::vector<u64 *> &ptrs);
+
+void op_ntt(Context &c, const u64 *src, u64 *dst, int n_polys, int mod_base, int mod_count, bool inverse);
+// out3[n][3][k][N] = a[i] * b[i]  (BEHZ).  a_ptrs/b_ptrs: host vectors of device ciphertext pointers.
+void op_multiply(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out3);
+void op_relinearize(Context &c, int ch, const u64 *in3, int n, u64 *out2);
+void op_multiply_relin(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out2);
+void op_key_switch(Context &c, const u64 *target, int n, const u64 *key, const DigitMap &dm, const u64 *base, u64 *out);
+void op_apply_galois(Context &c, int ch, const u64 *in, int n, u64 elt, u64 *out);
+void op_rotate_rows(Context &c, int ch, const u64 *in, int n, int steps, u64 *out); // steps == 0 copies
+void op_rotate_columns(Context &c, int ch, const u64 *in, int n, u64 *out);
+u64 galois_elt_from_step(const Context &c, int steps);
+// dense plaintext (coefficient form mod t, [n or 1][N]) times ciphertexts [n][2kN]
+void op_multiply_plain_dense(Context &c, int ch, const u64 *ct, int n, const u64 *plain, bool plain_per_ct, u64 *out);
+// values [n][count] (mod t, device) -> plain [n][N] coefficient form
+void op_encode(Context &c, int ch, const u64 *values, int n, int count, u64 *plain);
+void op_decode(Context &c, int ch, const u64 *plain, int n, u64 *values);
+// plain [n][plain_stride] (first `coeffs` coefficients used) -> ct [n][2kN]; nonces nonce0..nonce0+n-1
+void op_encrypt(Context &c, int ch, const u64 *plain, size_t plain_stride, int n, int coeffs, u64 nonce0, u64 *ct);
+void op_decrypt(Context &c, int ch, const u64 *ct, int n, u64 *plain);
+int op_noise_budget(Context &c, int ch, const u64 *ct);
+
+} // namespace cnhe

@@ -1,0 +1,1081 @@
+// C ABI of libcnhe (include/cnhe.h) and the vector layer behind it.
+//
+// One cnhe_vec is the reference's EncryptedSealBfvVector ("HE Wrapper/EncryptedSealBfvVector.cs:150-573"): P channels,
+// one per plaintext modulus, each carrying what AtomicSealBfvEncryptedVector ("HE Wrapper/AtomicSealBfvVector.cs:303-326")
+// keeps in `Ciphertext[] encData` / `Plaintext[] plainData` -- here blocks of HBM.  The functions below restate that
+// class method by method (cited inline); the arithmetic itself is in the CUDA kernels.
+#include <cmath>
+#include <cstring>
+#include <unordered_map>
+
+#include "../../include/cnhe.h"
+#include "hostmath.h"
+#include "runtime.h"
+
+using namespace cnhe;
+typedef unsigned __int128 u128;
+
+struct cnhe_ctx {
+    Context *c;
+};
+
+struct cnhe_vec {
+    Context *ctx = nullptr;
+    uint64_t dim = 0;
+    double scale = 1.0;
+    int format = CNHE_DENSE;
+    bool enc = false;
+    int blocks = 0; // ciphertexts / plaintexts per channel
+    std::vector<BufRef> buf; // per channel: enc -> blocks*2kN words, plain dense -> blocks*N words, plain sparse -> `blocks` scalars
+    std::vector<size_t> off;
+    std::vector<std::vector<u64>> scalars; // plain sparse: host copy of the constants (mod t)
+    bool is_const = false;                 // plain dense whose every plaintext is a constant polynomial
+    std::vector<u64> const_val;            // per channel constant (mod t) when is_const
+
+    u64 *ptr(int ch) const { return buf[ch]->p + off[ch]; }
+    size_t unit() const { return enc ? ctx->ct_words() : (format == CNHE_DENSE ? (size_t)ctx->N : 1); }
+    u64 *block(int ch, int b) const { return ptr(ch) + (size_t)b * unit(); }
+};
+
+static thread_local std::string g_err;
+static int set_err(int code, const std::string &m) {
+    g_err = m;
+    return code;
+}
+extern "C" const char *cnhe_last_error(void) { return g_err.c_str(); }
+extern "C" const char *cnhe_version(void) { return "cnhe-b200 0.1 (sm_100a)"; }
+
+#define API_BEGIN(CTX)                                                                                                 \
+    if (!(CTX)) return set_err(CNHE_ERR_INVALID, "null context");                                                      \
+    Context &c = *(CTX)->c;                                                                                            \
+    try {                                                                                                              \
+        std::lock_guard<std::recursive_mutex> lock(c.mu);                                                              \
+        CNHE_CUDA(cudaSetDevice(c.device));                                                                            \
+        ws_release_all(c);
+#define API_END                                                                                                        \
+    }                                                                                                                  \
+    catch (const Error &e) { return set_err(e.code, e.what()); }                                                      \
+    catch (const std::exception &e) { return set_err(CNHE_ERR_INVALID, e.what()); }                                   \
+    return CNHE_OK;
+static void fail(const char *m) { throw Error(CNHE_ERR_INVALID, m); }
+
+// ---------------------------------------------------------------------------------------------------- context & keys
+extern "C" int cnhe_context_create_custom(const uint64_t *plain_primes, int P, uint32_t N, const uint64_t *coeff, int k, int dbc_relin,
+                                          int dbc_galois, int device, cnhe_ctx **out) {
+    try {
+        if (!plain_primes || !coeff || !out) fail("null argument");
+        std::vector<u64> pp(plain_primes, plain_primes + P), cc(coeff, coeff + k);
+        Context *c = context_create(pp.data(), P, N, cc.data(), k, dbc_relin, dbc_galois, device);
+        *out = new cnhe_ctx{c};
+    } catch (const Error &e) { return set_err(e.code, e.what()); } catch (const std::exception &e) { return set_err(CNHE_ERR_INVALID, e.what()); }
+    return CNHE_OK;
+}
+extern "C" int cnhe_context_create(const uint64_t *plain_primes, int P, uint32_t N, int dbc_relin, int dbc_galois, int small_modulus_count,
+                                   int device, cnhe_ctx **out) {
+    std::vector<u64> q = default_coeff_modulus(N);
+    if (q.empty()) return set_err(CNHE_ERR_INVALID, "no default coefficient modulus for this PolyModulusDegree");
+    if (small_modulus_count > 0 && small_modulus_count < (int)q.size()) q.resize(small_modulus_count); // AtomicSealBfvVector.cs:148-149
+    std::vector<uint64_t> qq(q.begin(), q.end());
+    return cnhe_context_create_custom(plain_primes, P, N, qq.data(), (int)qq.size(), dbc_relin, dbc_galois, device, out);
+}
+extern "C" int cnhe_context_destroy(cnhe_ctx *h) {
+    if (!h) return CNHE_OK;
+    delete h->c;
+    delete h;
+    return CNHE_OK;
+}
+extern "C" int cnhe_context_info(const cnhe_ctx *h, uint32_t *N, int *k, int *P, int *relin_digits, int *galois_digits, int *galois_elts) {
+    if (!h) return set_err(CNHE_ERR_INVALID, "null context");
+    const Context &c = *h->c;
+    if (N) *N = c.N;
+    if (k) *k = c.k;
+    if (P) *P = c.P;
+    if (relin_digits) *relin_digits = c.dm_relin.D;
+    if (galois_digits) *galois_digits = c.dm_galois.D;
+    if (galois_elts) *galois_elts = (int)c.galois_elts.size();
+    return CNHE_OK;
+}
+extern "C" int cnhe_context_coeff_moduli(const cnhe_ctx *h, uint64_t *out) {
+    if (!h || !out) return set_err(CNHE_ERR_INVALID, "null argument");
+    for (int i = 0; i < h->c->k; i++) out[i] = h->c->q[i];
+    return CNHE_OK;
+}
+extern "C" int cnhe_context_plain_moduli(const cnhe_ctx *h, uint64_t *out) {
+    if (!h || !out) return set_err(CNHE_ERR_INVALID, "null argument");
+    for (int i = 0; i < h->c->P; i++) out[i] = h->c->t[i];
+    return CNHE_OK;
+}
+extern "C" int cnhe_context_galois_elts(const cnhe_ctx *h, uint64_t *out) {
+    if (!h || !out) return set_err(CNHE_ERR_INVALID, "null argument");
+    for (size_t i = 0; i < h->c->galois_elts.size(); i++) out[i] = h->c->galois_elts[i];
+    return CNHE_OK;
+}
+extern "C" int cnhe_context_set_option(cnhe_ctx *h, const char *name, int64_t value) {
+    API_BEGIN(h)
+    std::string n(name ? name : "");
+    if (n == "behz_centered_mtilde") {
+        c.h_bc.centered_mtilde = value ? 1 : 0;
+        CNHE_CUDA(cudaMemcpyAsync(c.d_bc, &c.h_bc, sizeof(BehzConst), cudaMemcpyHostToDevice, c.stream));
+        c.sync();
+    } else if (n == "chunk") {
+        if (value < 1 || value > 4096) fail("chunk must be in [1,4096]");
+        c.chunk = (int)value;
+    } else fail("unknown option");
+    API_END
+}
+extern "C" int cnhe_context_sync(cnhe_ctx *h) {
+    API_BEGIN(h)
+    c.sync();
+    API_END
+}
+extern "C" uint64_t cnhe_kernel_launch_count(const cnhe_ctx *h) { return h ? h->c->launches : 0; }
+extern "C" int cnhe_keys_generate(cnhe_ctx *h, uint64_t seed) {
+    API_BEGIN(h)
+    keys_generate(c, seed);
+    API_END
+}
+extern "C" int cnhe_keys_set_seed(cnhe_ctx *h, int channel, uint64_t seed) {
+    API_BEGIN(h)
+    if (channel < 0 || channel >= c.P) fail("bad channel");
+    c.ch[channel].seed = seed;
+    API_END
+}
+extern "C" int cnhe_keys_export(cnhe_ctx *h, int channel, int what, uint64_t arg, uint64_t *dst, size_t cap) {
+    API_BEGIN(h)
+    size_t words;
+    BufRef &b = key_slot(c, channel, what, arg, words, false);
+    if (cap < words) fail("destination too small");
+    CNHE_CUDA(cudaMemcpyAsync(dst, b->p, words * 8, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    API_END
+}
+extern "C" int cnhe_keys_import(cnhe_ctx *h, int channel, int what, uint64_t arg, const uint64_t *src, size_t nwords) {
+    API_BEGIN(h)
+    size_t words;
+    BufRef &b = key_slot(c, channel, what, arg, words, true);
+    if (nwords != words) fail("wrong key size");
+    CNHE_CUDA(cudaMemcpyAsync(b->p, src, words * 8, cudaMemcpyHostToDevice, c.stream));
+    c.sync();
+    Channel &ch = c.ch[channel];
+    if (what == 0) ch.have_sk = true;
+    if (what == 1) ch.have_pk = true;
+    if (what == 2) ch.have_rlk = true;
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------------- raw / microbench
+extern "C" int cnhe_dev_alloc(cnhe_ctx *h, size_t words, uint64_t *dptr) {
+    API_BEGIN(h)
+    void *p = nullptr;
+    CNHE_CUDA(cudaMalloc(&p, words * 8));
+    *dptr = (uint64_t)p;
+    API_END
+}
+extern "C" int cnhe_dev_free(cnhe_ctx *h, uint64_t dptr) {
+    API_BEGIN(h)
+    c.sync();
+    CNHE_CUDA(cudaFree((void *)dptr));
+    API_END
+}
+extern "C" int cnhe_dev_upload(cnhe_ctx *h, uint64_t dptr, const uint64_t *src, size_t words) {
+    API_BEGIN(h)
+    CNHE_CUDA(cudaMemcpyAsync((void *)dptr, src, words * 8, cudaMemcpyHostToDevice, c.stream));
+    c.sync();
+    API_END
+}
+extern "C" int cnhe_dev_download(cnhe_ctx *h, uint64_t *dst, uint64_t dptr, size_t words) {
+    API_BEGIN(h)
+    CNHE_CUDA(cudaMemcpyAsync(dst, (void *)dptr, words * 8, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    API_END
+}
+extern "C" int cnhe_raw_ntt(cnhe_ctx *h, uint64_t src, uint64_t dst, int n_polys, int mod_base, int mod_count, int inverse) {
+    API_BEGIN(h)
+    if (mod_base < 0 || mod_count < 1 || mod_base + mod_count > 2 * c.k + 1 + c.P) fail("bad modulus range");
+    op_ntt(c, (const u64 *)src, (u64 *)dst, n_polys, mod_base, mod_count, inverse != 0);
+    API_END
+}
+static std::vector<const u64 *> strided(uint64_t base, int n, size_t words) {
+    std::vector<const u64 *> v(n);
+    for (int i = 0; i < n; i++) v[i] = (const u64 *)base + (size_t)i * words;
+    return v;
+}
+extern "C" int cnhe_raw_multiply(cnhe_ctx *h, int channel, uint64_t a, uint64_t b, int n, uint64_t out3) {
+    API_BEGIN(h)
+    op_multiply(c, channel, strided(a, n, c.ct_words()), strided(b, n, c.ct_words()), (u64 *)out3);
+    API_END
+}
+extern "C" int cnhe_raw_relinearize(cnhe_ctx *h, int channel, uint64_t in3, int n, uint64_t out2) {
+    API_BEGIN(h)
+    op_relinearize(c, channel, (const u64 *)in3, n, (u64 *)out2);
+    API_END
+}
+extern "C" int cnhe_raw_multiply_relin(cnhe_ctx *h, int channel, uint64_t a, uint64_t b, int n, uint64_t out2) {
+    API_BEGIN(h)
+    op_multiply_relin(c, channel, strided(a, n, c.ct_words()), strided(b, n, c.ct_words()), (u64 *)out2);
+    API_END
+}
+extern "C" int cnhe_raw_apply_galois(cnhe_ctx *h, int channel, uint64_t in, int n, uint64_t elt, uint64_t out) {
+    API_BEGIN(h)
+    op_apply_galois(c, channel, (const u64 *)in, n, elt, (u64 *)out);
+    API_END
+}
+extern "C" int cnhe_raw_rotate_rows(cnhe_ctx *h, int channel, uint64_t in, int n, int steps, uint64_t out) {
+    API_BEGIN(h)
+    op_rotate_rows(c, channel, (const u64 *)in, n, steps, (u64 *)out);
+    API_END
+}
+extern "C" int cnhe_raw_behz_lift(cnhe_ctx *h, uint64_t in_cts, int n, uint64_t out) {
+    API_BEGIN(h)
+    c.check(launch_behz_lift(upload_ptrs(c, strided(in_cts, n, c.ct_words())), (u64 *)out, n, c.logN, c.d_bc, c.stream), "behz_lift");
+    API_END
+}
+extern "C" int cnhe_raw_behz_floor(cnhe_ctx *h, int channel, uint64_t d, int n, uint64_t out3) {
+    API_BEGIN(h)
+    c.check(launch_behz_floor((const u64 *)d, (u64 *)out3, n, c.ch[channel].t, c.logN, c.d_bc, c.stream), "behz_floor");
+    API_END
+}
+extern "C" int cnhe_raw_event_timing(cnhe_ctx *h, int start) {
+    API_BEGIN(h)
+    CNHE_CUDA(cudaEventRecord(start ? c.ev0 : c.ev1, c.stream));
+    API_END
+}
+extern "C" int cnhe_raw_elapsed_ms(cnhe_ctx *h, float *ms) {
+    API_BEGIN(h)
+    CNHE_CUDA(cudaEventSynchronize(c.ev1));
+    CNHE_CUDA(cudaEventElapsedTime(ms, c.ev0, c.ev1));
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------------- vector helpers
+static cnhe_vec *new_vec(Context &c, uint64_t dim, double scale, int format, bool enc, int blocks) {
+    cnhe_vec *v = new cnhe_vec();
+    v->ctx = &c;
+    v->dim = dim;
+    v->scale = scale;
+    v->format = format;
+    v->enc = enc;
+    v->blocks = blocks;
+    v->buf.resize(c.P);
+    v->off.assign(c.P, 0);
+    return v;
+}
+static void alloc_channels(cnhe_vec *v) {
+    for (int ch = 0; ch < v->ctx->P; ch++) v->buf[ch] = v->ctx->alloc((size_t)v->blocks * v->unit());
+}
+static cnhe_vec *alias_of(const cnhe_vec *a) { return new cnhe_vec(*a); } // shares the reference-counted buffers
+static void same_ctx(Context &c, const cnhe_vec *v) {
+    if (!v) fail("null vector");
+    if (v->ctx != &c) fail("vector belongs to another context");
+}
+// SplitBigNumbers ("EncryptedSealBfvVector.cs:352-365"): round(v*scale) -> +bigFactor if negative -> residues
+static void split_values(Context &c, const double *v, uint64_t n, double scale, std::vector<std::vector<u64>> &res) {
+    res.assign(c.P, std::vector<u64>(n));
+    for (uint64_t j = 0; j < n; j++) {
+        const double w = std::nearbyint(v[j] * scale); // Math.Round: to nearest, ties to even
+        if (!(std::fabs(w) < 1.5e38)) fail("value out of range");
+        const bool neg = w < 0;
+        u128 mag = (u128)(neg ? -w : w);
+        if (mag >= c.big_factor) mag %= c.big_factor;
+        const u128 z = (neg && mag) ? c.big_factor - mag : mag;
+        for (int i = 0; i < c.P; i++) res[i][j] = (u64)(z % c.t[i]);
+    }
+}
+static u128 mulmod_u128(u128 a, u64 b, u128 m) { // a < m < 2^126
+    u128 r = 0;
+    while (b) {
+        if (b & 1) { r += a; if (r >= m) r -= m; }
+        a += a; if (a >= m) a -= m;
+        b >>= 1;
+    }
+    return r;
+}
+// JoinSplitNumbers ("EncryptedSealBfvVector.cs:381-395")
+static void join_values(Context &c, const std::vector<std::vector<u64>> &split, uint64_t n, double scale, double *out) {
+    for (uint64_t j = 0; j < n; j++) {
+        u128 acc = 0;
+        for (int i = 0; i < c.P; i++) {
+            acc += mulmod_u128(c.crt_coeff[i] % c.big_factor, split[i][j], c.big_factor);
+            if (acc >= c.big_factor) acc -= c.big_factor;
+        }
+        double val;
+        if (acc * 2 > c.big_factor) val = -(double)(c.big_factor - acc);
+        else val = (double)acc;
+        out[j] = val / scale;
+    }
+}
+
+static cnhe_vec *make_vector(Context &c, const double *v, uint64_t dim, double scale, int format, bool encrypt) {
+    if (!v && dim) fail("null values");
+    if (format != CNHE_DENSE && format != CNHE_SPARSE) fail("bad format");
+    if (scale == 0) scale = 1; // AtomicSealBfvVector.cs:1120
+    const size_t N = c.N;
+    std::vector<std::vector<u64>> split;
+    split_values(c, v, dim, scale, split);
+    const int blocks = format == CNHE_DENSE ? (int)((dim + N - 1) / N) : (int)dim;
+    if (blocks < 1) fail("empty vector");
+    cnhe_vec *out = new_vec(c, dim, scale, format, encrypt, blocks);
+    std::unique_ptr<cnhe_vec> guard(out);
+    if (format == CNHE_SPARSE && !encrypt) {
+        out->scalars = split;
+        for (int ch = 0; ch < c.P; ch++) {
+            out->buf[ch] = c.alloc(dim);
+            CNHE_CUDA(cudaMemcpyAsync(out->buf[ch]->p, split[ch].data(), dim * 8, cudaMemcpyHostToDevice, c.stream));
+        }
+        c.sync();
+        return guard.release();
+    }
+    alloc_channels(out);
+    for (int ch = 0; ch < c.P; ch++) {
+        if (format == CNHE_DENSE) {
+            // BatchEncoder.Encode per N-slot chunk (AtomicSealBfvVector.cs:1123-1133); a short last chunk is zero padded
+            std::vector<u64> padded((size_t)blocks * N, 0);
+            memcpy(padded.data(), split[ch].data(), dim * 8);
+            u64 *dvals = c.ws_alloc((size_t)blocks * N);
+            CNHE_CUDA(cudaMemcpyAsync(dvals, padded.data(), padded.size() * 8, cudaMemcpyHostToDevice, c.stream));
+            u64 *plain = encrypt ? c.ws_alloc((size_t)blocks * N) : out->ptr(ch);
+            op_encode(c, ch, dvals, blocks, (int)N, plain);
+            if (encrypt) {
+                op_encrypt(c, ch, plain, N, blocks, (int)N, c.ch[ch].nonce, out->ptr(ch));
+                c.ch[ch].nonce += blocks;
+            }
+        } else { // sparse encrypted: one constant-polynomial plaintext per element (AtomicSealBfvVector.cs:1135-1138)
+            u64 *dvals = c.ws_alloc(dim);
+            CNHE_CUDA(cudaMemcpyAsync(dvals, split[ch].data(), dim * 8, cudaMemcpyHostToDevice, c.stream));
+            op_encrypt(c, ch, dvals, 1, blocks, 1, c.ch[ch].nonce, out->ptr(ch));
+            c.ch[ch].nonce += blocks;
+        }
+        c.sync(); // host staging buffers go out of scope
+    }
+    if (!encrypt && format == CNHE_DENSE && dim % N == 0) { // every slot equal => every plaintext is the constant polynomial
+        bool all_eq = true;
+        for (uint64_t j = 1; j < dim && all_eq; j++) all_eq = v[j] == v[0];
+        if (all_eq) {
+            out->is_const = true;
+            for (int ch = 0; ch < c.P; ch++) out->const_val.push_back(split[ch][0]);
+        }
+    }
+    return guard.release();
+}
+
+extern "C" int cnhe_vec_encrypt(cnhe_ctx *h, const double *v, uint64_t dim, double scale, int format, cnhe_vec **out) {
+    API_BEGIN(h)
+    *out = make_vector(c, v, dim, scale, format, true);
+    API_END
+}
+extern "C" int cnhe_vec_plain(cnhe_ctx *h, const double *v, uint64_t dim, double scale, int format, cnhe_vec **out) {
+    API_BEGIN(h)
+    *out = make_vector(c, v, dim, scale, format, false);
+    API_END
+}
+// n dense single-block-or-more vectors encrypted in one wave per channel (GetEncryptedMatrix, IFactory.cs:353-380)
+extern "C" int cnhe_vecs_encrypt(cnhe_ctx *h, const double *v, int n, uint64_t dim, double scale, cnhe_vec **out) {
+    API_BEGIN(h)
+    if (n < 1 || !v || !out) fail("bad arguments");
+    if (scale == 0) scale = 1;
+    const size_t N = c.N;
+    const int bl = (int)((dim + N - 1) / N);
+    std::vector<std::vector<u64>> split;
+    split_values(c, v, (uint64_t)n * dim, scale, split);
+    std::vector<BufRef> big(c.P);
+    for (int ch = 0; ch < c.P; ch++) {
+        std::vector<u64> padded((size_t)n * bl * N, 0);
+        for (int i = 0; i < n; i++) memcpy(&padded[(size_t)i * bl * N], &split[ch][(size_t)i * dim], dim * 8);
+        u64 *dvals = c.ws_alloc(padded.size()), *plain = c.ws_alloc(padded.size());
+        CNHE_CUDA(cudaMemcpyAsync(dvals, padded.data(), padded.size() * 8, cudaMemcpyHostToDevice, c.stream));
+        op_encode(c, ch, dvals, n * bl, (int)N, plain);
+        big[ch] = c.alloc((size_t)n * bl * c.ct_words());
+        op_encrypt(c, ch, plain, N, n * bl, (int)N, c.ch[ch].nonce, big[ch]->p);
+        c.ch[ch].nonce += (u64)n * bl;
+        c.sync();
+    }
+    for (int i = 0; i < n; i++) {
+        cnhe_vec *o = new_vec(c, dim, scale, CNHE_DENSE, true, bl);
+        for (int ch = 0; ch < c.P; ch++) {
+            o->buf[ch] = big[ch];
+            o->off[ch] = (size_t)i * bl * c.ct_words();
+        }
+        out[i] = o;
+    }
+    API_END
+}
+
+// Decrypt of the blocks of one channel into residues (dense: first `dim` slots; sparse: constant coefficients)
+static void decrypt_channel(Context &c, const cnhe_vec *v, int ch, std::vector<u64> &res) {
+    const size_t N = c.N;
+    res.assign(v->dim, 0);
+    if (!v->enc && v->format == CNHE_SPARSE) { res = v->scalars[ch]; return; }
+    u64 *plain;
+    if (v->enc) {
+        plain = c.ws_alloc((size_t)v->blocks * N);
+        op_decrypt(c, ch, v->ptr(ch), v->blocks, plain);
+    } else plain = v->ptr(ch);
+    if (v->format == CNHE_DENSE) {
+        u64 *vals = c.ws_alloc((size_t)v->blocks * N);
+        op_decode(c, ch, plain, v->blocks, vals);
+        std::vector<u64> hostv((size_t)v->blocks * N);
+        CNHE_CUDA(cudaMemcpyAsync(hostv.data(), vals, hostv.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+        const uint64_t take = std::min<uint64_t>(v->dim, hostv.size());
+        memcpy(res.data(), hostv.data(), take * 8);
+    } else {
+        std::vector<u64> hostv(v->blocks);
+        CNHE_CUDA(cudaMemcpy2DAsync(hostv.data(), 8, plain, N * 8, 8, v->blocks, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+        const uint64_t take = std::min<uint64_t>(v->dim, hostv.size());
+        memcpy(res.data(), hostv.data(), take * 8);
+    }
+}
+extern "C" int cnhe_vec_decrypt(cnhe_ctx *h, const cnhe_vec *v, double *out, uint64_t cap) {
+    API_BEGIN(h)
+    same_ctx(c, v);
+    if (cap < v->dim) fail("destination too small");
+    std::vector<std::vector<u64>> split(c.P);
+    for (int ch = 0; ch < c.P; ch++) decrypt_channel(c, v, ch, split[ch]);
+    join_values(c, split, v->dim, v->scale, out);
+    API_END
+}
+extern "C" int cnhe_vecs_decrypt(cnhe_ctx *h, const cnhe_vec *const *vecs, int n, double *out, uint64_t dim) {
+    API_BEGIN(h)
+    for (int i = 0; i < n; i++) {
+        same_ctx(c, vecs[i]);
+        if (vecs[i]->dim != dim) fail("all vectors must have the same dimension");
+        std::vector<std::vector<u64>> split(c.P);
+        for (int ch = 0; ch < c.P; ch++) decrypt_channel(c, vecs[i], ch, split[ch]);
+        join_values(c, split, dim, vecs[i]->scale, out + (size_t)i * dim);
+    }
+    API_END
+}
+extern "C" int cnhe_vec_copy(cnhe_ctx *h, const cnhe_vec *v, cnhe_vec **out) {
+    API_BEGIN(h)
+    same_ctx(c, v);
+    cnhe_vec *o = new cnhe_vec(*v);
+    for (int ch = 0; ch < c.P; ch++) {
+        const size_t words = (size_t)v->blocks * v->unit();
+        o->buf[ch] = c.alloc(words);
+        o->off[ch] = 0;
+        CNHE_CUDA(cudaMemcpyAsync(o->buf[ch]->p, v->ptr(ch), words * 8, cudaMemcpyDeviceToDevice, c.stream));
+    }
+    *out = o;
+    API_END
+}
+extern "C" int cnhe_vec_destroy(cnhe_vec *v) {
+    if (!v) return CNHE_OK;
+    try {
+        std::lock_guard<std::recursive_mutex> lock(v->ctx->mu);
+        cudaSetDevice(v->ctx->device);
+        delete v;
+    } catch (...) { return set_err(CNHE_ERR_INVALID, "destroy failed"); }
+    return CNHE_OK;
+}
+extern "C" int cnhe_vec_meta(const cnhe_vec *v, uint64_t *dim, double *scale, int *format, int *is_encrypted, int *blocks, uint64_t *block_size) {
+    if (!v) return set_err(CNHE_ERR_INVALID, "null vector");
+    if (dim) *dim = v->dim;
+    if (scale) *scale = v->scale;
+    if (format) *format = v->format;
+    if (is_encrypted) *is_encrypted = v->enc ? 1 : 0;
+    if (blocks) *blocks = v->blocks;
+    if (block_size) *block_size = v->ctx->N;
+    return CNHE_OK;
+}
+extern "C" int cnhe_vec_register_scale(cnhe_vec *v, double scale) {
+    if (!v) return set_err(CNHE_ERR_INVALID, "null vector");
+    v->scale = scale;
+    return CNHE_OK;
+}
+extern "C" int cnhe_vec_register_dim(cnhe_vec *v, uint64_t dim) {
+    if (!v) return set_err(CNHE_ERR_INVALID, "null vector");
+    v->dim = dim;
+    return CNHE_OK;
+}
+extern "C" int cnhe_vec_export_raw(cnhe_ctx *h, const cnhe_vec *v, int channel, int block, uint64_t *dst, size_t cap) {
+    API_BEGIN(h)
+    same_ctx(c, v);
+    if (!v->enc) fail("vector is not encrypted");
+    if (channel < 0 || channel >= c.P || block < 0 || block >= v->blocks) fail("bad channel/block");
+    if (cap < c.ct_words()) fail("destination too small");
+    CNHE_CUDA(cudaMemcpyAsync(dst, v->block(channel, block), c.ct_words() * 8, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    API_END
+}
+extern "C" int cnhe_vec_import_raw(cnhe_ctx *h, const uint64_t *src, int blocks, uint64_t dim, double scale, int format, cnhe_vec **out) {
+    API_BEGIN(h)
+    if (!src || blocks < 1) fail("bad arguments");
+    cnhe_vec *o = new_vec(c, dim, scale, format, true, blocks);
+    alloc_channels(o);
+    const size_t words = (size_t)blocks * c.ct_words();
+    for (int ch = 0; ch < c.P; ch++)
+        CNHE_CUDA(cudaMemcpyAsync(o->ptr(ch), src + (size_t)ch * words, words * 8, cudaMemcpyHostToDevice, c.stream));
+    c.sync();
+    *out = o;
+    API_END
+}
+extern "C" int cnhe_vec_device_ptr(const cnhe_vec *v, int channel, uint64_t *dptr, size_t *words) {
+    if (!v || channel < 0 || channel >= v->ctx->P) return set_err(CNHE_ERR_INVALID, "bad arguments");
+    *dptr = (uint64_t)v->ptr(channel);
+    if (words) *words = (size_t)v->blocks * v->unit();
+    return CNHE_OK;
+}
+extern "C" int cnhe_noise_budget(cnhe_ctx *h, const cnhe_vec *v, int channel, int block, int *bits) {
+    API_BEGIN(h)
+    same_ctx(c, v);
+    if (!v->enc || channel < 0 || channel >= c.P || block < 0 || block >= v->blocks) fail("bad arguments");
+    *bits = op_noise_budget(c, channel, v->block(channel, block));
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------------- IVector operations
+static void check_pair(const cnhe_vec *a, const cnhe_vec *b) {
+    if (a->dim != b->dim) fail("Dimensions do not match");
+    if (a->format != b->format) fail("Format mismatch");
+}
+// Add / Subtract (AtomicSealBfvVector.cs:983-1024, 1238-1271; wrapper EncryptedSealBfvVector.cs:271-282, 457-471)
+static cnhe_vec *addsub(Context &c, const cnhe_vec *a, const cnhe_vec *b, bool sub) {
+    if (!sub && a->scale == 0) return alias_of(b);
+    if (b->scale == 0) return alias_of(a);
+    if (a->scale != b->scale) fail("Scales do not match.");
+    check_pair(a, b);
+    if (!a->enc && !b->enc) fail("adding two plaintexts is not supported");
+    if (sub && !a->enc) fail("the first argument for subtraction must be encrypted");
+    const cnhe_vec *e = a->enc ? a : b, *p = a->enc ? b : a;
+    if (e->blocks != p->blocks) fail("Dimensions do not match");
+    cnhe_vec *o = new_vec(c, a->dim, a->scale, a->format, true, e->blocks);
+    alloc_channels(o);
+    for (int ch = 0; ch < c.P; ch++) {
+        if (p->enc) {
+            c.check(launch_ct_add(a->ptr(ch), b->ptr(ch), o->ptr(ch), (size_t)e->blocks * c.ct_words(), c.k, c.logN, c.d_bc, sub, c.stream), "ct_add");
+        } else {
+            const bool dense = p->format == CNHE_DENSE;
+            c.check(launch_ct_add_plain(e->ptr(ch), o->ptr(ch), e->blocks, 2, p->ptr(ch), dense ? c.N : 1, dense ? (int)c.N : 1, c.k, c.logN, c.d_bc,
+                                        c.ch[ch].pc, sub, c.stream),
+                    "ct_add_plain");
+        }
+    }
+    return o;
+}
+extern "C" int cnhe_vec_add(cnhe_ctx *h, const cnhe_vec *a, const cnhe_vec *b, cnhe_vec **out) {
+    API_BEGIN(h)
+    same_ctx(c, a); same_ctx(c, b);
+    *out = addsub(c, a, b, false);
+    API_END
+}
+extern "C" int cnhe_vec_sub(cnhe_ctx *h, const cnhe_vec *a, const cnhe_vec *b, cnhe_vec **out) {
+    API_BEGIN(h)
+    same_ctx(c, a); same_ctx(c, b);
+    *out = addsub(c, a, b, true);
+    API_END
+}
+
+static std::vector<const u64 *> block_ptrs(const cnhe_vec *v, int ch, int repeat_first = 0) {
+    std::vector<const u64 *> p;
+    if (repeat_first) p.assign(repeat_first, v->block(ch, 0));
+    else for (int b = 0; b < v->blocks; b++) p.push_back(v->block(ch, b));
+    return p;
+}
+// PointwiseMultiplySparseDimOne (AtomicSealBfvVector.cs:774-810): `s` is the sparse dimension-one operand
+static cnhe_vec *mul_sparse_dim_one(Context &c, const cnhe_vec *self, const cnhe_vec *s) {
+    cnhe_vec *o = new_vec(c, self->dim, self->scale * s->scale, self->format, true, self->blocks);
+    std::unique_ptr<cnhe_vec> guard(o);
+    alloc_channels(o);
+    for (int ch = 0; ch < c.P; ch++) {
+        if (self->enc && s->enc) {
+            op_multiply_relin(c, ch, block_ptrs(s, ch, self->blocks), block_ptrs(self, ch), o->ptr(ch));
+        } else if (self->enc) { // constant plaintext times every block
+            std::vector<u64> sc(self->blocks, s->scalars[ch][0]);
+            if (sc[0] == 0) fail("plain cannot be zero (the result would be a transparent ciphertext)");
+            u64 *d = c.ws_alloc(sc.size());
+            CNHE_CUDA(cudaMemcpyAsync(d, sc.data(), sc.size() * 8, cudaMemcpyHostToDevice, c.stream));
+            c.check(launch_ct_scale(self->ptr(ch), o->ptr(ch), self->blocks, 2, d, c.k, c.logN, c.d_bc, c.ch[ch].pc, c.stream), "ct_scale");
+            c.sync();
+        } else { // plain blocks times the single ciphertext of s
+            if (self->format != CNHE_DENSE) fail("unsupported plain format");
+            u64 *rep = c.ws_alloc((size_t)self->blocks * c.ct_words());
+            for (int b = 0; b < self->blocks; b++)
+                CNHE_CUDA(cudaMemcpyAsync(rep + (size_t)b * c.ct_words(), s->block(ch, 0), c.ct_words() * 8, cudaMemcpyDeviceToDevice, c.stream));
+            op_multiply_plain_dense(c, ch, rep, self->blocks, self->ptr(ch), true, o->ptr(ch));
+        }
+    }
+    return guard.release();
+}
+// PointwiseMultiply (AtomicSealBfvVector.cs:813-860)
+static cnhe_vec *pointwise_multiply(Context &c, const cnhe_vec *a, const cnhe_vec *b) {
+    if (!a->enc && !b->enc) fail("multiplying two plaintexts is not implemented");
+    if (a->dim == 1 && a->format == CNHE_SPARSE) return mul_sparse_dim_one(c, b, a);
+    if (b->dim == 1 && b->format == CNHE_SPARSE) return mul_sparse_dim_one(c, a, b);
+    check_pair(a, b);
+    if (a->blocks != b->blocks) fail("Dimensions do not match");
+    cnhe_vec *o = new_vec(c, a->dim, a->scale * b->scale, a->format, true, a->blocks);
+    std::unique_ptr<cnhe_vec> guard(o);
+    alloc_channels(o);
+    const cnhe_vec *e = a->enc ? a : b, *p = a->enc ? b : a;
+    for (int ch = 0; ch < c.P; ch++) {
+        if (a->enc && b->enc) {
+            op_multiply_relin(c, ch, block_ptrs(b, ch), block_ptrs(a, ch), o->ptr(ch)); // evaluator.Multiply(ev.encData[i], encData[i])
+        } else if (p->format == CNHE_DENSE) {
+            op_multiply_plain_dense(c, ch, e->ptr(ch), e->blocks, p->ptr(ch), true, o->ptr(ch));
+        } else {
+            for (u64 s : p->scalars[ch])
+                if (s == 0) fail("plain cannot be zero (the result would be a transparent ciphertext)");
+            c.check(launch_ct_scale(e->ptr(ch), o->ptr(ch), e->blocks, 2, p->ptr(ch), c.k, c.logN, c.d_bc, c.ch[ch].pc, c.stream), "ct_scale");
+        }
+    }
+    return guard.release();
+}
+extern "C" int cnhe_vec_pointwise_multiply(cnhe_ctx *h, const cnhe_vec *a, const cnhe_vec *b, cnhe_vec **out) {
+    API_BEGIN(h)
+    same_ctx(c, a); same_ctx(c, b);
+    *out = pointwise_multiply(c, a, b);
+    API_END
+}
+
+// SumAllSlots (AtomicSealBfvVector.cs:888-955)
+static cnhe_vec *sum_all_slots(Context &c, const cnhe_vec *a, uint64_t length, int force_column) {
+    if (a->format != CNHE_DENSE) fail("Expecting dense vector format");
+    if (length != CNHE_ALL_SLOTS && force_column >= 0) fail("forcing output in a column works only when doing complete sum");
+    if (!a->enc) fail("SumAllSlots can be applied to encrypted data only");
+    if (length == 0) fail("Can't sum over less then one element");
+    if (length == 1) return alias_of(a);
+    const size_t N = c.N, ctw = c.ct_words();
+    uint64_t len = length;
+    cnhe_vec *o = new_vec(c, a->dim, a->scale, CNHE_DENSE, true, 1);
+    std::unique_ptr<cnhe_vec> guard(o);
+    alloc_channels(o);
+    for (int ch = 0; ch < c.P; ch++) {
+        len = length;
+        u64 *sum = o->ptr(ch);
+        if (a->blocks > 1) { // AddMany over the blocks
+            std::vector<const u64 *> ptrs = block_ptrs(a, ch);
+            c.check(launch_ct_add_many(upload_ptrs(c, ptrs), a->blocks, sum, ctw, c.k, c.logN, c.d_bc, c.stream), "ct_add_many");
+        } else {
+            CNHE_CUDA(cudaMemcpyAsync(sum, a->ptr(ch), ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+        }
+        u64 *tmp = c.ws_alloc(ctw);
+        if (len >= N / 2) {
+            op_rotate_columns(c, ch, sum, 1, tmp);
+            c.check(launch_ct_add(sum, tmp, sum, ctw, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+            len = N / 2;
+        }
+        for (uint64_t steps = 1; steps < len; steps *= 2) { // RotateRowsAndAdd(sum, steps): RotateRows(c, -steps)
+            op_rotate_rows(c, ch, sum, 1, -(int)steps, tmp);
+            c.check(launch_ct_add(sum, tmp, sum, ctw, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+        }
+        if (force_column >= 0) { // one-hot mask (":936-945")
+            if ((size_t)force_column >= N) fail("column out of range");
+            std::vector<u64> onehot(N, 0);
+            onehot[force_column] = 1;
+            u64 *dv = c.ws_alloc(N), *pl = c.ws_alloc(N);
+            CNHE_CUDA(cudaMemcpyAsync(dv, onehot.data(), N * 8, cudaMemcpyHostToDevice, c.stream));
+            op_encode(c, ch, dv, 1, (int)N, pl);
+            op_multiply_plain_dense(c, ch, sum, 1, pl, false, sum);
+            c.sync();
+            len = 1;
+        }
+    }
+    o->dim = (len >= N / 2) ? 1 : a->dim;
+    o->format = (len >= N) ? CNHE_SPARSE : CNHE_DENSE;
+    return guard.release();
+}
+extern "C" int cnhe_vec_sum_all_slots(cnhe_ctx *h, const cnhe_vec *a, uint64_t length, int force_column, cnhe_vec **out) {
+    API_BEGIN(h)
+    same_ctx(c, a);
+    *out = sum_all_slots(c, a, length, force_column);
+    API_END
+}
+extern "C" int cnhe_vec_dot_product(cnhe_ctx *h, const cnhe_vec *a, const cnhe_vec *b, uint64_t length, int force_column, cnhe_vec **out) {
+    API_BEGIN(h)
+    same_ctx(c, a); same_ctx(c, b);
+    std::unique_ptr<cnhe_vec> mul(pointwise_multiply(c, a, b)); // AtomicSealBfvVector.cs:964-977
+    *out = sum_all_slots(c, mul.get(), length, force_column);
+    API_END
+}
+// Rotate (AtomicSealBfvVector.cs:1414-1430): first block only
+extern "C" int cnhe_vec_rotate(cnhe_ctx *h, const cnhe_vec *a, int amount, cnhe_vec **out) {
+    API_BEGIN(h)
+    same_ctx(c, a);
+    if (!a->enc) fail("Rotate operates only on encrypted data");
+    if (a->format == CNHE_SPARSE) fail("Rotate operates only on dense vectors");
+    cnhe_vec *o = new_vec(c, a->dim, a->scale, CNHE_DENSE, true, 1);
+    std::unique_ptr<cnhe_vec> guard(o);
+    alloc_channels(o);
+    for (int ch = 0; ch < c.P; ch++) op_rotate_rows(c, ch, a->ptr(ch), 1, amount, o->ptr(ch));
+    *out = guard.release();
+    API_END
+}
+// Duplicate (AtomicSealBfvVector.cs:1370-1408)
+extern "C" int cnhe_vec_duplicate(cnhe_ctx *h, const cnhe_vec *a, uint64_t count, cnhe_vec **out) {
+    API_BEGIN(h)
+    same_ctx(c, a);
+    uint64_t shift = 1;
+    while (shift < a->dim) shift *= 2;
+    if (!a->enc) fail("Duplicate operates only on encrypted data");
+    if (a->format == CNHE_SPARSE) fail("Duplicate operates only on dense vectors");
+    const size_t N = c.N, ctw = c.ct_words();
+    if (shift * count > N) fail("Packed vector must fit in a single ciphertext");
+    cnhe_vec *o = new_vec(c, count * shift, a->scale, CNHE_DENSE, true, 1);
+    std::unique_ptr<cnhe_vec> guard(o);
+    alloc_channels(o);
+    for (int ch = 0; ch < c.P; ch++) {
+        u64 *res = o->ptr(ch), *rotator = c.ws_alloc(ctw), *tmp = c.ws_alloc(ctw);
+        CNHE_CUDA(cudaMemcpyAsync(res, a->ptr(ch), ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+        const u64 *rot_src = a->ptr(ch);
+        bool column_rotated = false;
+        for (uint64_t i = 1; i < count; i++) {
+            long long target = (long long)(i * shift);
+            if (target * 2 >= (long long)N) {
+                if (!column_rotated) {
+                    column_rotated = true;
+                    op_rotate_columns(c, ch, a->ptr(ch), 1, rotator);
+                    rot_src = rotator;
+                }
+                target -= (long long)N / 2;
+            }
+            op_rotate_rows(c, ch, rot_src, 1, -(int)target, tmp); // RotateRowsAndAdd(rotator, target, ...)
+            c.check(launch_ct_add(res, tmp, res, ctw, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+        }
+    }
+    *out = guard.release();
+    API_END
+}
+// Permute (AtomicSealBfvVector.cs:1436-1475)
+extern "C" int cnhe_vec_permute(cnhe_ctx *h, const cnhe_vec *a, const cnhe_vec *const *selections, const int *shifts, int n, uint64_t output_dim,
+                                cnhe_vec **out) {
+    API_BEGIN(h)
+    same_ctx(c, a);
+    if (a->format != CNHE_DENSE) fail("Permute works only on dense vectors");
+    if (!a->enc) fail("can permute only encrypted vectors");
+    if (a->blocks > 1) fail("can permute only a single block");
+    int first = -1;
+    for (int i = 0; i < n; i++) {
+        if (!selections[i]) continue;
+        same_ctx(c, selections[i]);
+        if (first < 0) first = i;
+        if (selections[i]->dim != a->dim) fail("dimension of selection vector does not match dimension of data vector");
+        if (selections[i]->scale != selections[first]->scale) fail("scales of all selection vectors should be the same");
+        if (selections[i]->enc) fail("encrypted size must be 2 (rotating the size-3 product of an encrypted selection is rejected by SEAL)");
+        if (selections[i]->format != CNHE_DENSE) fail("selection vectors must be dense");
+    }
+    if (first < 0) fail("permuting with no selected values is illigal");
+    const size_t ctw = c.ct_words();
+    cnhe_vec *o = new_vec(c, output_dim, a->scale * selections[first]->scale, CNHE_DENSE, true, 1);
+    std::unique_ptr<cnhe_vec> guard(o);
+    alloc_channels(o);
+    for (int ch = 0; ch < c.P; ch++) {
+        u64 *t = c.ws_alloc(ctw), *r = c.ws_alloc(ctw);
+        bool have = false;
+        for (int i = 0; i < n; i++) {
+            if (!selections[i]) continue;
+            op_multiply_plain_dense(c, ch, a->ptr(ch), 1, selections[i]->ptr(ch), false, t);
+            op_rotate_rows(c, ch, t, 1, shifts[i], r);
+            if (!have) CNHE_CUDA(cudaMemcpyAsync(o->ptr(ch), r, ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+            else c.check(launch_ct_add(o->ptr(ch), r, o->ptr(ch), ctw, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+            have = true;
+        }
+    }
+    *out = guard.release();
+    API_END
+}
+// GenerateSparseOfArray (AtomicSealBfvVector.cs:1347-1359)
+extern "C" int cnhe_vecs_generate_sparse_of_array(cnhe_ctx *h, const cnhe_vec *const *vecs, int n, cnhe_vec **out) {
+    API_BEGIN(h)
+    if (n < 1) fail("empty array");
+    for (int i = 0; i < n; i++) { same_ctx(c, vecs[i]); if (!vecs[i]->enc) fail("expecting encrypted vectors"); }
+    cnhe_vec *o = new_vec(c, (uint64_t)n, vecs[0]->scale, CNHE_SPARSE, true, n);
+    alloc_channels(o);
+    for (int ch = 0; ch < c.P; ch++)
+        for (int i = 0; i < n; i++)
+            CNHE_CUDA(cudaMemcpyAsync(o->block(ch, i), vecs[i]->block(ch, 0), c.ct_words() * 8, cudaMemcpyDeviceToDevice, c.stream));
+    *out = o;
+    API_END
+}
+
+// Inteleave (AtomicSealBfvVector.cs:600-722): place vector k at slot offset shift*k
+static void interleave_channel(Context &c, int ch, const std::vector<const cnhe_vec *> &vecs, int shift, int out_blocks, u64 *out) {
+    const int block_size = (int)c.N, half = block_size / 2;
+    const size_t ctw = c.ct_words();
+    const int abs_shift = shift < 0 ? -shift : shift;
+    if (shift < 0 && out_blocks > 1) fail("Negative shifts with multiple output blocks are not implemented yet");
+    if (abs_shift > half && out_blocks > 1) fail("Shifts of more than half block size with multiple output blocks are not implemented yet");
+    if ((long long)abs_shift * (long long)vecs.size() > (long long)block_size * out_blocks) fail("not enough room for interleaving");
+    std::vector<std::vector<const u64 *>> lower(out_blocks), upper(out_blocks);
+    auto ones_plain = [&](int count) { // BatchEncoder.Encode of `count` ones
+        std::vector<u64> v(block_size, 0);
+        for (int i = 0; i < count; i++) v[i] = 1;
+        u64 *dv = c.ws_alloc(block_size), *pl = c.ws_alloc(block_size);
+        CNHE_CUDA(cudaMemcpyAsync(dv, v.data(), (size_t)block_size * 8, cudaMemcpyHostToDevice, c.stream));
+        op_encode(c, ch, dv, 1, block_size, pl);
+        c.sync();
+        return pl;
+    };
+    for (size_t kk = 0; kk < vecs.size(); kk++) {
+        long long this_shift = (long long)shift * (long long)kk;
+        if (this_shift < 0) this_shift = half + this_shift;
+        const int in_block = (int)(this_shift % block_size);
+        const int start_block = (int)(this_shift / block_size), end_block = (int)((this_shift + abs_shift) / block_size);
+        u64 *v = c.ws_alloc(ctw);
+        const u64 *src = vecs[kk]->block(ch, 0);
+        if (in_block == 0) {
+            CNHE_CUDA(cudaMemcpyAsync(v, src, ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+            lower[start_block].push_back(v);
+        } else if (in_block + abs_shift < half) {
+            op_rotate_rows(c, ch, src, 1, -(int)this_shift, v);
+            lower[start_block].push_back(v);
+        } else if (in_block >= half) {
+            op_rotate_rows(c, ch, src, 1, -(in_block - half), v);
+            if (start_block == end_block) {
+                upper[start_block].push_back(v);
+            } else { // straddles the upper half of this block and the lower half of the next
+                const int upper_part = (in_block + abs_shift) - block_size;
+                u64 *v2 = c.ws_alloc(ctw);
+                CNHE_CUDA(cudaMemcpyAsync(v2, v, ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+                op_multiply_plain_dense(c, ch, v, 1, ones_plain(upper_part), false, v);
+                c.check(launch_ct_add(v2, v, v2, ctw, c.k, c.logN, c.d_bc, 1, c.stream), "ct_sub");
+                upper[start_block].push_back(v2);
+                if (end_block >= out_blocks) fail("not enough room for interleaving");
+                lower[end_block].push_back(v);
+            }
+        } else { // straddles lower and upper half of the same block
+            op_rotate_rows(c, ch, src, 1, -in_block, v);
+            const int upper_part = (in_block + abs_shift) - half;
+            if (upper_part > 0) {
+                u64 *v2 = c.ws_alloc(ctw);
+                CNHE_CUDA(cudaMemcpyAsync(v2, v, ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+                op_multiply_plain_dense(c, ch, v, 1, ones_plain(upper_part), false, v);
+                c.check(launch_ct_add(v2, v, v2, ctw, c.k, c.logN, c.d_bc, 1, c.stream), "ct_sub");
+                upper[start_block].push_back(v);
+                lower[start_block].push_back(v2);
+            } else {
+                lower[start_block].push_back(v);
+            }
+        }
+    }
+    for (int i = 0; i < out_blocks; i++) {
+        u64 *res = out + (size_t)i * ctw;
+        if (lower[i].empty()) fail("an output block received no vector");
+        c.check(launch_ct_add_many(upload_ptrs(c, lower[i]), (int)lower[i].size(), res, ctw, c.k, c.logN, c.d_bc, c.stream), "ct_add_many");
+        if (!upper[i].empty()) {
+            u64 *t = c.ws_alloc(ctw);
+            c.check(launch_ct_add_many(upload_ptrs(c, upper[i]), (int)upper[i].size(), t, ctw, c.k, c.logN, c.d_bc, c.stream), "ct_add_many");
+            op_rotate_columns(c, ch, t, 1, t);
+            c.check(launch_ct_add(res, t, res, ctw, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+        }
+    }
+}
+static cnhe_vec *interleave(Context &c, const cnhe_vec *const *vecs, int n, int shift) { // AtomicSealBfvVector.cs:729-750
+    if (n < 1) fail("empty array");
+    std::vector<const cnhe_vec *> vv(vecs, vecs + n);
+    for (auto v : vv) { same_ctx(c, v); if (!v->enc) fail("expecting encrypted vectors"); }
+    if (vv[0]->format != CNHE_DENSE) fail("Expecting dense vector");
+    int out_blocks = 1;
+    if (shift > 0) out_blocks = (int)std::ceil((double)(vv[0]->dim * (uint64_t)n) / (double)c.N);
+    cnhe_vec *o = new_vec(c, vv[0]->dim, vv[0]->scale, CNHE_DENSE, true, out_blocks);
+    std::unique_ptr<cnhe_vec> guard(o);
+    alloc_channels(o);
+    for (int ch = 0; ch < c.P; ch++) interleave_channel(c, ch, vv, shift, out_blocks, o->ptr(ch));
+    return guard.release();
+}
+extern "C" int cnhe_vecs_interleave(cnhe_ctx *h, const cnhe_vec *const *vecs, int n, int shift, cnhe_vec **out) {
+    API_BEGIN(h)
+    *out = interleave(c, vecs, n, shift);
+    API_END
+}
+extern "C" int cnhe_vecs_stack(cnhe_ctx *h, const cnhe_vec *const *vecs, int n, cnhe_vec **out) { // AtomicSealBfvVector.cs:756-761
+    API_BEGIN(h)
+    if (n < 1) fail("empty array");
+    cnhe_vec *o = interleave(c, vecs, n, (int)vecs[0]->dim);
+    o->dim = vecs[0]->dim * (uint64_t)n;
+    *out = o;
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------------- matrix x vector, layers
+struct RowHash {
+    size_t operator()(const std::vector<int> &r) const {
+        size_t hsh = 1469598103934665603ULL;
+        for (int v : r) hsh = (hsh ^ (size_t)(unsigned)v) * 1099511628211ULL;
+        return hsh;
+    }
+};
+// Shared body of DenseMatrixBySparseVectorMultiply (ciphertext columns x plain constants) and of the fused PoolLayer.
+// in[n_in] encrypted dense vectors (same block count), weights[m] plain sparse of dim K, bias[m] plain dense or null.
+static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int32_t *gather, const cnhe_vec *const *weights, const cnhe_vec *const *bias,
+                      int M, int K, cnhe_vec **out) {
+    if (n_in < 1 || M < 1 || K < 1) fail("bad layer shape");
+    const int bl = in[0]->blocks;
+    for (int i = 0; i < n_in; i++) {
+        same_ctx(c, in[i]);
+        if (!in[i]->enc || in[i]->format != CNHE_DENSE) fail("layer inputs must be encrypted dense vectors");
+        if (in[i]->blocks != bl || in[i]->dim != in[0]->dim || in[i]->scale != in[0]->scale) fail("all layer inputs must share dimension and scale");
+    }
+    bool const_bias = bias != nullptr;
+    for (int m = 0; m < M; m++) {
+        same_ctx(c, weights[m]);
+        if (weights[m]->enc || weights[m]->format != CNHE_SPARSE) fail("expecting a sparse vector");
+        if (weights[m]->dim != (uint64_t)K) fail("dimensions do not match");
+        if (weights[m]->scale != weights[0]->scale) fail("weight scales differ");
+        if (bias) {
+            if (!bias[m]) fail("null bias");
+            same_ctx(c, bias[m]);
+            if (bias[m]->enc || bias[m]->format != CNHE_DENSE || bias[m]->dim != in[0]->dim) fail("bias must be a plain dense vector of the input dimension");
+            if (bias[m]->scale != in[0]->scale * weights[0]->scale) fail("Scales do not match.");
+            const_bias = const_bias && bias[m]->is_const;
+        }
+    }
+    // 128-bit accumulator bound: K products of (q_l - 1)^2
+    int maxbits = 0;
+    for (u64 q : c.q) maxbits = std::max(maxbits, hm::bit_length(q));
+    if (2 * maxbits + hm::bit_length((u64)K) > 127) fail("layer too wide for the 128-bit accumulator with these coefficient moduli");
+    // tiles: outputs that share a gather row, 8 at a time
+    std::vector<int> grows;
+    std::vector<MacTile> tiles;
+    {
+        std::unordered_map<std::vector<int>, std::vector<int>, RowHash> groups;
+        std::vector<std::vector<int>> order;
+        for (int m = 0; m < M; m++) {
+            std::vector<int> row(K);
+            bool any = false;
+            for (int kk = 0; kk < K; kk++) {
+                row[kk] = gather ? gather[(size_t)m * K + kk] : kk;
+                if (row[kk] >= n_in) fail("gather index out of range");
+                if (row[kk] >= 0 && weights[m]->scalars[0][kk] != 0) any = true;
+            }
+            if (!any) fail("an output has no non-zero tap (the reference would sum an empty list)");
+            auto it = groups.find(row);
+            if (it == groups.end()) { order.push_back(row); groups[row] = {m}; }
+            else it->second.push_back(m);
+        }
+        for (auto &row : order) {
+            const int row_index = (int)(grows.size() / K);
+            grows.insert(grows.end(), row.begin(), row.end());
+            const std::vector<int> &ms = groups[row];
+            for (size_t s = 0; s < ms.size(); s += 8) {
+                MacTile t;
+                memset(&t, 0, sizeof(t));
+                t.gather_row = row_index;
+                t.n_out = (int)std::min<size_t>(8, ms.size() - s);
+                for (int j = 0; j < t.n_out; j++) t.out_index[j] = ms[s + j];
+                tiles.push_back(t);
+            }
+        }
+    }
+    int *d_gather = (int *)c.ws_alloc((grows.size() + 1) / 2 + 1);
+    CNHE_CUDA(cudaMemcpyAsync(d_gather, grows.data(), grows.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    MacTile *d_tiles = (MacTile *)c.ws_alloc((tiles.size() * sizeof(MacTile) + 7) / 8);
+    CNHE_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(MacTile), cudaMemcpyHostToDevice, c.stream));
+    const double out_scale = in[0]->scale * weights[0]->scale;
+    std::vector<BufRef> big(c.P);
+    for (int ch = 0; ch < c.P; ch++) big[ch] = c.alloc((size_t)M * bl * c.ct_words());
+    for (int ch = 0; ch < c.P; ch++) {
+        std::vector<const u64 *> wp(M);
+        for (int m = 0; m < M; m++) wp[m] = weights[m]->ptr(ch);
+        const u64 *const *d_w = upload_ptrs(c, wp);
+        const u64 *d_bias = nullptr;
+        if (bias && const_bias) {
+            std::vector<u64> bv(M);
+            for (int m = 0; m < M; m++) bv[m] = bias[m]->const_val[ch];
+            u64 *db = c.ws_alloc(M);
+            CNHE_CUDA(cudaMemcpyAsync(db, bv.data(), (size_t)M * 8, cudaMemcpyHostToDevice, c.stream));
+            d_bias = db;
+        }
+        for (int b = 0; b < bl; b++) {
+            std::vector<const u64 *> ip(n_in);
+            for (int i = 0; i < n_in; i++) ip[i] = in[i]->block(ch, b);
+            std::vector<u64 *> op(M);
+            for (int m = 0; m < M; m++) op[m] = big[ch]->p + ((size_t)m * bl + b) * c.ct_words();
+            c.check(launch_mac_layer(upload_ptrs(c, ip), d_gather, d_tiles, (int)tiles.size(), d_w, d_bias, K, upload_ptrs_mut(c, op), c.k, c.logN, c.d_bc,
+                                     c.ch[ch].pc, c.stream),
+                    "mac_layer");
+        }
+        if (bias && !const_bias) // generic AddPlain per output
+            for (int m = 0; m < M; m++) {
+                u64 *o = big[ch]->p + (size_t)m * bl * c.ct_words();
+                c.check(launch_ct_add_plain(o, o, bl, 2, bias[m]->ptr(ch), c.N, (int)c.N, c.k, c.logN, c.d_bc, c.ch[ch].pc, 0, c.stream), "ct_add_plain");
+            }
+        c.sync(); // host staging vectors
+    }
+    for (int m = 0; m < M; m++) {
+        cnhe_vec *o = new_vec(c, in[0]->dim, out_scale, CNHE_DENSE, true, bl);
+        for (int ch = 0; ch < c.P; ch++) {
+            o->buf[ch] = big[ch];
+            o->off[ch] = (size_t)m * bl * c.ct_words();
+        }
+        out[m] = o;
+    }
+}
+extern "C" int cnhe_layer_conv_dense(cnhe_ctx *h, const cnhe_vec *const *in, int n_in, const int32_t *gather, const cnhe_vec *const *weights,
+                                     const cnhe_vec *const *bias, int M, int K, cnhe_vec **out) {
+    API_BEGIN(h)
+    mac_layer(c, in, n_in, gather, weights, bias, M, K, out);
+    API_END
+}
+// DenseMatrixBySparseVectorMultiply (AtomicSealBfvVector.cs:434-521)
+extern "C" int cnhe_mat_mul_colmajor_sparse(cnhe_ctx *h, const cnhe_vec *const *cols, int K, const cnhe_vec *sparse, cnhe_vec **out) {
+    API_BEGIN(h)
+    if (K < 1) fail("empty matrix");
+    same_ctx(c, sparse);
+    for (int i = 0; i < K; i++) same_ctx(c, cols[i]);
+    if ((uint64_t)K != sparse->dim) fail("dimensions do not match");
+    if (sparse->format != CNHE_SPARSE) fail("expecting a sparse vector");
+    if (!cols[0]->enc && !sparse->enc) fail("at least one parameter has to be encrypted");
+    if (cols[0]->enc && !sparse->enc) {
+        mac_layer(c, cols, K, nullptr, &sparse, nullptr, 1, K, out);
+    } else {
+        const int bl = cols[0]->blocks;
+        const size_t ctw = c.ct_words();
+        cnhe_vec *o = new_vec(c, cols[0]->dim, cols[0]->scale * sparse->scale, CNHE_DENSE, true, bl);
+        std::unique_ptr<cnhe_vec> guard(o);
+        alloc_channels(o);
+        for (int ch = 0; ch < c.P; ch++) {
+            u64 *prod = c.ws_alloc((size_t)K * bl * ctw);
+            if (cols[0]->enc) { // both encrypted: Multiply + Relinearize per (k, block)
+                std::vector<const u64 *> a, b;
+                for (int kk = 0; kk < K; kk++)
+                    for (int i = 0; i < bl; i++) { a.push_back(cols[kk]->block(ch, i)); b.push_back(sparse->block(ch, kk)); }
+                op_multiply_relin(c, ch, a, b, prod);
+            } else { // plain columns x encrypted constants: MultiplyPlain(sparse.enc[k], denses[k].plain[i])
+                for (int kk = 0; kk < K; kk++) {
+                    u64 *rep = c.ws_alloc((size_t)bl * ctw);
+                    for (int i = 0; i < bl; i++)
+                        CNHE_CUDA(cudaMemcpyAsync(rep + (size_t)i * ctw, sparse->block(ch, kk), ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+                    op_multiply_plain_dense(c, ch, rep, bl, cols[kk]->ptr(ch), true, prod + (size_t)kk * bl * ctw);
+                }
+            }
+            for (int i = 0; i < bl; i++) {
+                std::vector<const u64 *> terms;
+                for (int kk = 0; kk < K; kk++) terms.push_back(prod + ((size_t)kk * bl + i) * ctw);
+                c.check(launch_ct_add_many(upload_ptrs(c, terms), K, o->block(ch, i), ctw, c.k, c.logN, c.d_bc, c.stream), "ct_add_many");
+            }
+            c.sync();
+        }
+        *out = guard.release();
+    }
+    API_END
+}
+// SquareActivation over a whole matrix: every column PointwiseMultiply'd with itself in one wave per channel
+extern "C" int cnhe_layer_square(cnhe_ctx *h, const cnhe_vec *const *in, int n, cnhe_vec **out) {
+    API_BEGIN(h)
+    if (n < 1) fail("empty layer");
+    std::vector<int> first(n + 1, 0);
+    for (int i = 0; i < n; i++) {
+        same_ctx(c, in[i]);
+        if (!in[i]->enc) fail("multiplying two plaintexts is not implemented");
+        first[i + 1] = first[i] + in[i]->blocks;
+    }
+    const int total = first[n];
+    std::vector<BufRef> big(c.P);
+    for (int ch = 0; ch < c.P; ch++) {
+        big[ch] = c.alloc((size_t)total * c.ct_words());
+        std::vector<const u64 *> ptrs;
+        for (int i = 0; i < n; i++)
+            for (int b = 0; b < in[i]->blocks; b++) ptrs.push_back(in[i]->block(ch, b));
+        op_multiply_relin(c, ch, ptrs, ptrs, big[ch]->p);
+    }
+    for (int i = 0; i < n; i++) {
+        cnhe_vec *o = new_vec(c, in[i]->dim, in[i]->scale * in[i]->scale, in[i]->format, true, in[i]->blocks);
+        for (int ch = 0; ch < c.P; ch++) {
+            o->buf[ch] = big[ch];
+            o->off[ch] = (size_t)first[i] * c.ct_words();
+        }
+        out[i] = o;
+    }
+    API_END
+}

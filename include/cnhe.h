@@ -1,0 +1,144 @@
+/*
+ * cnhe.h -- C ABI of libcnhe.so, the B200-native BFV engine behind the CryptoNets plugin API.
+ *
+ * This is the drop-in boundary.  A C# `B200BfvFactory : IFactory` binds these entry points
+ * with [DllImport("cnhe")] (stub in INTEGRATION.md); the Python mirror in cryptonets_b200/ binds them with ctypes.
+ * One cnhe_vec is one reference `EncryptedSealBfvVector` ("HE Wrapper/EncryptedSealBfvVector.cs:150-573"): P
+ * plaintext-modulus channels, each an `AtomicSealBfvEncryptedVector` ("HE Wrapper/AtomicSealBfvVector.cs:303-1476")
+ * whose SEAL Ciphertext[] / Plaintext[] live in B200 HBM.  Every call is batched over blocks and channels;
+ * nothing here computes on the CPU and the library fails at load/first call when no CUDA device is present.
+ *
+ * Conventions: every function returns 0 (CNHE_OK) or a negative error code; cnhe_last_error() gives the message of
+ * the last failure on the calling thread (the reference throws System.Exception with the same wording where it has
+ * one).  Nothing throws across the ABI.  Handles are opaque; vectors are immutable after creation except for the
+ * metadata setters; destroying a vector that another vector/matrix aliases is safe (buffers are reference counted,
+ * mirroring `CopyVectors:false` / `DataDisposedExternaly` in "HE Wrapper/EncryptedSealBfvMatrix.cs:32-58").
+ * Calls may come from several host threads (reference: one IComputationEnvironment per thread,
+ * "HE Wrapper/Utils.cs:46-88"); work is serialised onto the context's CUDA stream.
+ *
+ * Raw ciphertext layout (import/export): SEAL's in-memory layout, [poly][residue][coefficient] uint64, coefficient
+ * (non-NTT) form, canonical residues.
+ */
+#ifndef CNHE_H
+#define CNHE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNHE_OK 0
+#define CNHE_ERR_INVALID (-1)   /* bad argument / dimension / format / scale mismatch (reference: System.Exception) */
+#define CNHE_ERR_CUDA (-2)      /* CUDA runtime failure, including "no device" */
+#define CNHE_ERR_STATE (-3)     /* keys missing, etc. */
+#define CNHE_ERR_UNSUPPORTED (-4)
+
+#define CNHE_DENSE 0  /* EVectorFormat.dense  ("HE Wrapper/IVector.cs:15-18") */
+#define CNHE_SPARSE 1 /* EVectorFormat.sparse */
+#define CNHE_ALL_SLOTS 0x7fffffffu /* Int32.MaxValue length of SumAllSlots ("AtomicSealBfvVector.cs:873,880") */
+
+typedef struct cnhe_ctx cnhe_ctx; /* == EncryptedSealBfvFactory + its reference EncryptedSealBfvEnvironment */
+typedef struct cnhe_vec cnhe_vec; /* == EncryptedSealBfvVector */
+
+const char *cnhe_last_error(void);
+const char *cnhe_version(void);
+
+/* ---- context & keys ------------------------------------------------------------------------------------------ */
+/* new EncryptedSealBfvFactory(primes, n, DecompositionBitCount, GaloisDecompositionBitCount, SmallModulusCount)
+ * ("HE Wrapper/IFactory.cs:255-260"); coefficient modulus = first small_modulus_count entries (<=0: all) of
+ * DefaultParams.CoeffModulus128(N) ("AtomicSealBfvVector.cs:140-151").  Builds every device table; no keys yet. */
+int cnhe_context_create(const uint64_t *plain_primes, int P, uint32_t N, int dbc_relin, int dbc_galois,
+                        int small_modulus_count, int device, cnhe_ctx **out);
+/* same with explicit coefficient moduli (AtomicSealBfvVector.cs:152-161 Parms(t, n, coefModulus)) */
+int cnhe_context_create_custom(const uint64_t *plain_primes, int P, uint32_t N, const uint64_t *coeff_moduli, int k,
+                               int dbc_relin, int dbc_galois, int device, cnhe_ctx **out);
+int cnhe_context_destroy(cnhe_ctx *);
+int cnhe_context_info(const cnhe_ctx *, uint32_t *N, int *k, int *P, int *relin_digits, int *galois_digits, int *galois_elts);
+int cnhe_context_coeff_moduli(const cnhe_ctx *, uint64_t *out_k);
+int cnhe_context_plain_moduli(const cnhe_ctx *, uint64_t *out_P);
+int cnhe_context_galois_elts(const cnhe_ctx *, uint64_t *out);
+/* options: "behz_centered_mtilde" (0/1), "chunk" (ciphertexts per multiply/key-switch wave) */
+int cnhe_context_set_option(cnhe_ctx *, const char *name, int64_t value);
+int cnhe_context_sync(cnhe_ctx *);
+/* EncryptedSealBfvEnvironment.GenerateEncryptionKeys ("EncryptedSealBfvVector.cs:92-102") -> KeyGenerator, RelinKeys(dbc),
+ * GaloisKeys(dbc) ("AtomicSealBfvVector.cs:62-74"); channel c is seeded with seed + c.  Device-side sampling. */
+int cnhe_keys_generate(cnhe_ctx *, uint64_t seed);
+/* what: 0 secret key [k][N] (NTT form), 1 public key [2][k][N], 2 relin keys [D][2][k][N], 3 Galois key of element
+ * `arg` [D][2][k][N].  Stand-in for the SEAL key streams of SaveToStream/LoadFromStream ("AtomicSealBfvVector.cs:93-130"). */
+int cnhe_keys_export(cnhe_ctx *, int channel, int what, uint64_t arg, uint64_t *dst, size_t cap_words);
+int cnhe_keys_import(cnhe_ctx *, int channel, int what, uint64_t arg, const uint64_t *src, size_t words);
+int cnhe_keys_set_seed(cnhe_ctx *, int channel, uint64_t seed); /* seed used by later encryptions of that channel */
+
+/* ---- vectors: creation, metadata, disposal ---------------------------------------------------------------------- */
+/* IFactory.GetEncryptedVector / GetPlainVector ("HE Wrapper/IFactory.cs:311-328"): round(v*scale), CRT split over the
+ * plain primes ("EncryptedSealBfvVector.cs:352-365"), BatchEncoder.Encode per N-slot block (dense) or one constant
+ * polynomial per element (sparse) ("AtomicSealBfvVector.cs:1114-1142"), Encryptor.Encrypt (":1202-1216"). */
+int cnhe_vec_encrypt(cnhe_ctx *, const double *v, uint64_t dim, double scale, int format, cnhe_vec **out);
+int cnhe_vec_plain(cnhe_ctx *, const double *v, uint64_t dim, double scale, int format, cnhe_vec **out);
+/* batched form of IFactory.GetEncryptedMatrix ("IFactory.cs:353-380"): n dense vectors of `dim` values, v row-major [n][dim] */
+int cnhe_vecs_encrypt(cnhe_ctx *, const double *v, int n, uint64_t dim, double scale, cnhe_vec **out);
+/* IVector.Decrypt ("EncryptedSealBfvVector.cs:332-337,381-395"; "AtomicSealBfvVector.cs:1030-1067") */
+int cnhe_vec_decrypt(cnhe_ctx *, const cnhe_vec *, double *out, uint64_t cap);
+int cnhe_vecs_decrypt(cnhe_ctx *, const cnhe_vec *const *vecs, int n, double *out /*[n][dim]*/, uint64_t dim);
+int cnhe_vec_copy(cnhe_ctx *, const cnhe_vec *, cnhe_vec **out); /* IFactory.CopyVector */
+int cnhe_vec_destroy(cnhe_vec *);
+int cnhe_vec_meta(const cnhe_vec *, uint64_t *dim, double *scale, int *format, int *is_encrypted, int *blocks, uint64_t *block_size);
+int cnhe_vec_register_scale(cnhe_vec *, double scale); /* IVector.RegisterScale */
+int cnhe_vec_register_dim(cnhe_vec *, uint64_t dim);   /* AtomicSealBfvVector.cs:316-319 */
+/* raw ciphertext access for parity tests: block `block` of channel `channel`, 2*k*N words */
+int cnhe_vec_export_raw(cnhe_ctx *, const cnhe_vec *, int channel, int block, uint64_t *dst, size_t cap_words);
+int cnhe_vec_import_raw(cnhe_ctx *, const uint64_t *src /*[P][blocks][2kN]*/, int blocks, uint64_t dim, double scale, int format,
+                        cnhe_vec **out);
+/* device pointer of a channel's ciphertext blocks (for NCCL gathers through torch; plumbing only) */
+int cnhe_vec_device_ptr(const cnhe_vec *, int channel, uint64_t *dptr, size_t *words);
+int cnhe_noise_budget(cnhe_ctx *, const cnhe_vec *, int channel, int block, int *bits); /* CryptoTracker.cs:41-52 */
+
+/* ---- IVector operations ------------------------------------------------------------------------------------------ */
+int cnhe_vec_add(cnhe_ctx *, const cnhe_vec *a, const cnhe_vec *b, cnhe_vec **out);          /* AtomicSealBfvVector.cs:983-1024 */
+int cnhe_vec_sub(cnhe_ctx *, const cnhe_vec *a, const cnhe_vec *b, cnhe_vec **out);          /* :1238-1271 */
+int cnhe_vec_pointwise_multiply(cnhe_ctx *, const cnhe_vec *a, const cnhe_vec *b, cnhe_vec **out); /* :813-860, :774-810 */
+/* length == CNHE_ALL_SLOTS: full sum; force_column < 0: none */
+int cnhe_vec_sum_all_slots(cnhe_ctx *, const cnhe_vec *a, uint64_t length, int force_column, cnhe_vec **out); /* :888-955 */
+int cnhe_vec_dot_product(cnhe_ctx *, const cnhe_vec *a, const cnhe_vec *b, uint64_t length, int force_column, cnhe_vec **out); /* :964-977 */
+int cnhe_vec_rotate(cnhe_ctx *, const cnhe_vec *a, int amount, cnhe_vec **out);              /* :1414-1430 */
+int cnhe_vec_duplicate(cnhe_ctx *, const cnhe_vec *a, uint64_t count, cnhe_vec **out);       /* :1370-1408 */
+int cnhe_vec_permute(cnhe_ctx *, const cnhe_vec *a, const cnhe_vec *const *selections, const int *shifts, int n,
+                     uint64_t output_dim, cnhe_vec **out);                                   /* :1436-1475 */
+int cnhe_vecs_interleave(cnhe_ctx *, const cnhe_vec *const *vecs, int n, int shift, cnhe_vec **out); /* :600-750 */
+int cnhe_vecs_stack(cnhe_ctx *, const cnhe_vec *const *vecs, int n, cnhe_vec **out);         /* :756-761 */
+int cnhe_vecs_generate_sparse_of_array(cnhe_ctx *, const cnhe_vec *const *vecs, int n, cnhe_vec **out); /* :1347-1359 */
+
+/* ---- IMatrix.Mul and the fused layer entry points ------------------------------------------------------------------ */
+/* ColumnMajor matrix x sparse vector ("EncryptedSealBfvMatrix.cs:70-78" -> "AtomicSealBfvVector.cs:434-521") */
+int cnhe_mat_mul_colmajor_sparse(cnhe_ctx *, const cnhe_vec *const *cols, int K, const cnhe_vec *sparse, cnhe_vec **out);
+/* Whole PoolLayer.Apply with weights ("NeuralNetworks/PoolLayer.cs:149-229"): out[m] = sum_k weights[m][k] * in[gather[m*K+k]]
+ * + bias[m].  weights[m] is a plain SPARSE vector of dim K, bias[m] a plain DENSE vector (or NULL); gather < 0 is a
+ * padded tap (the reference multiplies a fresh encryption of zero there; we add nothing -- same decryption). */
+int cnhe_layer_conv_dense(cnhe_ctx *, const cnhe_vec *const *in, int n_in, const int32_t *gather, const cnhe_vec *const *weights,
+                          const cnhe_vec *const *bias, int M, int K, cnhe_vec **out /*M*/);
+/* SquareActivation.Apply over a whole matrix ("NeuralNetworks/SquareActivation.cs:10-13"): out[i] = in[i] (.) in[i] */
+int cnhe_layer_square(cnhe_ctx *, const cnhe_vec *const *in, int n, cnhe_vec **out /*n*/);
+
+/* ---- micro-benchmark / kernel-level entry points on caller-owned device memory ("raw") --------------------------- */
+int cnhe_dev_alloc(cnhe_ctx *, size_t words, uint64_t *dptr);
+int cnhe_dev_free(cnhe_ctx *, uint64_t dptr);
+int cnhe_dev_upload(cnhe_ctx *, uint64_t dptr, const uint64_t *src, size_t words);
+int cnhe_dev_download(cnhe_ctx *, uint64_t *dst, uint64_t dptr, size_t words);
+/* n_polys residue polynomials at src; polynomial b uses modulus id mod_base + b % mod_count
+ * (ids: 0..k-1 q_i, k..2k Bsk, 2k+1+c plain modulus c) */
+int cnhe_raw_ntt(cnhe_ctx *, uint64_t src, uint64_t dst, int n_polys, int mod_base, int mod_count, int inverse);
+int cnhe_raw_multiply(cnhe_ctx *, int channel, uint64_t a, uint64_t b, int n, uint64_t out3);     /* Evaluator.Multiply, size 3 out */
+int cnhe_raw_relinearize(cnhe_ctx *, int channel, uint64_t in3, int n, uint64_t out2);
+int cnhe_raw_multiply_relin(cnhe_ctx *, int channel, uint64_t a, uint64_t b, int n, uint64_t out2);
+int cnhe_raw_apply_galois(cnhe_ctx *, int channel, uint64_t in, int n, uint64_t galois_elt, uint64_t out);
+int cnhe_raw_rotate_rows(cnhe_ctx *, int channel, uint64_t in, int n, int steps, uint64_t out);
+int cnhe_raw_behz_lift(cnhe_ctx *, uint64_t in_cts, int n, uint64_t out_together);
+int cnhe_raw_behz_floor(cnhe_ctx *, int channel, uint64_t d_together, int n, uint64_t out3);
+int cnhe_raw_event_timing(cnhe_ctx *, int start); /* start=1: record start event; start=0: record stop, return via cnhe_raw_elapsed_ms */
+int cnhe_raw_elapsed_ms(cnhe_ctx *, float *ms);
+uint64_t cnhe_kernel_launch_count(const cnhe_ctx *); /* kernels launched by this library since context creation */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,213 @@
+"""GPU parity: every CUDA kernel / device pipeline of libcnhe against the CPU oracle on identical inputs, keys and
+parameters -- bit-exact (integer arithmetic).  Calls go through the C ABI (cryptonets_b200.engine -> libcnhe.so)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = {
+    "default4096": dict(t=40961, N=4096, count=-1, dbc_r=10, dbc_g=20),       # IFactory.cs:247-253
+    "cryptonets8192": dict(t=549764251649, N=8192, count=-1, dbc_r=10, dbc_g=20),  # CryptoNets.cs:17
+    "lola8192": dict(t=2277377, N=8192, count=3, dbc_r=40, dbc_g=40),          # LoLaCryptonets.cs:285
+    "cifar16384": dict(t=957181001729, N=16384, count=8, dbc_r=60, dbc_g=60),  # LolaCifarCryptoNet.cs:35
+}
+
+
+@pytest.fixture(scope="module", params=list(CONFIGS))
+def pair(request):
+    from cryptonets_b200.engine import Engine
+    from oracle.oracle_py import Oracle
+    cfg = CONFIGS[request.param]
+    eng = Engine([cfg["t"]], cfg["N"], cfg["dbc_r"], cfg["dbc_g"], cfg["count"])
+    orc = Oracle(cfg["t"], cfg["N"], cfg["count"], cfg["dbc_r"], cfg["dbc_g"])
+    assert eng.q == orc.q
+    eng.keygen(1234)
+    orc.keygen(1234)
+    yield eng, orc, request.param
+    eng.close()
+
+
+def test_ntt_all_moduli(pair):
+    eng, orc, _ = pair
+    rng = np.random.default_rng(1)
+    N, k = eng.N, eng.k
+    for which in list(range(2 * k + 1)) + [2 * k + 1]:
+        p = orc.modulus_of(which)
+        polys = rng.integers(0, p, (3, N), dtype=np.uint64)
+        polys[0, :4] = [0, 1, p - 1, p - 2]
+        d = eng.dev_from(polys)
+        eng.raw_ntt(d, d, 3, which, 1, False)
+        got = eng.dev_download(d, 3 * N).reshape(3, N)
+        want = np.stack([orc.ntt(which, polys[i]) for i in range(3)])
+        assert np.array_equal(got, want), which
+        eng.raw_ntt(d, d, 3, which, 1, True)
+        back = eng.dev_download(d, 3 * N).reshape(3, N)
+        assert np.array_equal(back, polys), which
+        eng.dev_free(d)
+
+
+def test_ntt_mixed_batch(pair):
+    eng, orc, _ = pair
+    rng = np.random.default_rng(2)
+    N, k = eng.N, eng.k
+    kt = 2 * k + 1
+    polys = np.stack([rng.integers(0, orc.modulus_of(b % kt), N, dtype=np.uint64) for b in range(2 * kt)])
+    d = eng.dev_from(polys)
+    out = eng.dev_alloc(polys.size)
+    eng.raw_ntt(d, out, 2 * kt, 0, kt, False)
+    got = eng.dev_download(out, polys.size).reshape(polys.shape)
+    for b in range(2 * kt):
+        assert np.array_equal(got[b], orc.ntt(b % kt, polys[b])), b
+    eng.dev_free(d)
+    eng.dev_free(out)
+
+
+def test_keygen_bit_identical(pair):
+    eng, orc, _ = pair
+    assert np.array_equal(eng.export_key(0, 0), orc.secret_key())
+    assert np.array_equal(eng.export_key(0, 1), orc.public_key())
+    assert np.array_equal(eng.export_key(0, 2), orc.relin_keys().ravel())
+    assert eng.galois_elts() == orc.galois_elts()
+    for elt in eng.galois_elts()[:3] + eng.galois_elts()[-1:]:
+        assert np.array_equal(eng.export_key(0, 3, elt), orc.galois_key(elt).ravel()), elt
+
+
+def _fresh_cts(orc, n, seed, nonce0=100):
+    rng = np.random.default_rng(seed)
+    vals = rng.integers(0, orc.t, (n, orc.N), dtype=np.uint64)
+    return vals, np.stack([orc.encrypt(orc.encode(vals[i]), nonce0 + i) for i in range(n)])
+
+
+def test_encrypt_decrypt(pair):
+    from cryptonets_b200.engine import DENSE
+    eng, orc, _ = pair
+    rng = np.random.default_rng(3)
+    half = orc.t // 2
+    vals = rng.integers(-min(half, 2**40), min(half, 2**40), eng.N + 17).astype(np.float64)
+    v = eng.encrypt(vals, 1.0, DENSE)  # nonces 1, 2 on a fresh context
+    assert v.blocks == 2
+    lifted = np.where(vals < 0, vals + orc.t, vals).astype(np.uint64)
+    want0 = orc.encrypt(orc.encode(lifted[: eng.N]), 1)
+    want1 = orc.encrypt(orc.encode(lifted[eng.N:]), 2)
+    assert np.array_equal(v.export_raw(0, 0), want0)
+    assert np.array_equal(v.export_raw(0, 1), want1)
+    assert np.array_equal(eng.decrypt(v), vals)
+    assert eng.noise_budget(v, 0, 0) == orc.noise_budget(want0)
+
+
+def test_behz_stages(pair):
+    eng, orc, _ = pair
+    N, k = eng.N, eng.k
+    kt = 2 * k + 1
+    _, cts = _fresh_cts(orc, 2, 5)
+    d = eng.dev_from(cts)
+    out = eng.dev_alloc(2 * 2 * kt * N)
+    eng.raw_behz_lift(d, 2, out)
+    got = eng.dev_download(out, 2 * 2 * kt * N).reshape(2, 2, kt, N)
+    for c in range(2):
+        for part in range(2):
+            poly = cts[c].reshape(2, k, N)[part]
+            assert np.array_equal(got[c, part, :k], poly)
+            assert np.array_equal(got[c, part, k:].ravel(), orc.behz_lift(poly))
+    rng = np.random.default_rng(6)
+    dd = np.stack([np.stack([rng.integers(0, orc.modulus_of(l), N, dtype=np.uint64) for l in range(kt)]) for _ in range(3)])
+    d2 = eng.dev_from(dd)
+    out3 = eng.dev_alloc(3 * k * N)
+    eng.raw_behz_floor(0, d2, 1, out3)
+    got = eng.dev_download(out3, 3 * k * N).reshape(3, k * N)
+    for i in range(3):
+        scaled = np.stack([(dd[i, l].astype(object) * orc.t % orc.modulus_of(l)) for l in range(kt)]).astype(np.uint64)
+        assert np.array_equal(got[i], orc.behz_floor(scaled)), i
+    for p in (d, out, d2, out3):
+        eng.dev_free(p)
+
+
+@pytest.mark.parametrize("centered", [0, 1])
+def test_multiply_relinearize(pair, centered):
+    eng, orc, name = pair
+    eng.set_option("behz_centered_mtilde", centered)
+    orc.set_centered_mtilde(centered)
+    try:
+        N, k = eng.N, eng.k
+        n = 3
+        vals, cts = _fresh_cts(orc, 2 * n, 7)
+        a, b = eng.dev_from(cts[:n]), eng.dev_from(cts[n:])
+        out3, out2, outmr, outsq = eng.dev_alloc(n * 3 * k * N), eng.dev_alloc(n * 2 * k * N), eng.dev_alloc(n * 2 * k * N), eng.dev_alloc(n * 2 * k * N)
+        eng.raw_multiply(0, a, b, n, out3)
+        got3 = eng.dev_download(out3, n * 3 * k * N).reshape(n, -1)
+        want3 = np.stack([orc.multiply(cts[i], cts[n + i]) for i in range(n)])
+        assert np.array_equal(got3, want3)
+        eng.raw_relinearize(0, out3, n, out2)
+        got2 = eng.dev_download(out2, n * 2 * k * N).reshape(n, -1)
+        want2 = np.stack([orc.relinearize(want3[i]) for i in range(n)])
+        assert np.array_equal(got2, want2)
+        eng.raw_multiply_relin(0, a, b, n, outmr)
+        assert np.array_equal(eng.dev_download(outmr, n * 2 * k * N).reshape(n, -1), want2)
+        eng.raw_multiply_relin(0, a, a, n, outsq)  # squaring path (SquareActivation)
+        wantsq = np.stack([orc.relinearize(orc.multiply(cts[i], cts[i])) for i in range(n)])
+        assert np.array_equal(eng.dev_download(outsq, n * 2 * k * N).reshape(n, -1), wantsq)
+        if name != "cifar16384":  # t^2 products need the CRT wrapper there; slots still multiply mod t
+            dec = orc.decode(orc.decrypt(want2[0]))
+            assert np.array_equal(dec, (vals[0].astype(object) * vals[n].astype(object) % orc.t).astype(np.uint64))
+        for p in (a, b, out3, out2, outmr, outsq):
+            eng.dev_free(p)
+    finally:
+        eng.set_option("behz_centered_mtilde", 0)
+        orc.set_centered_mtilde(0)
+
+
+def test_galois_and_rotations(pair):
+    eng, orc, _ = pair
+    N, k = eng.N, eng.k
+    n = 2
+    _, cts = _fresh_cts(orc, n, 9)
+    a = eng.dev_from(cts)
+    out = eng.dev_alloc(n * 2 * k * N)
+    for elt in [2 * N - 1, 3, eng.galois_elts()[2]]:
+        eng.raw_apply_galois(0, a, n, elt, out)
+        got = eng.dev_download(out, n * 2 * k * N).reshape(n, -1)
+        for i in range(n):
+            assert np.array_equal(got[i], orc.apply_galois(cts[i], elt)), elt
+    for steps in [1, -1, 4, -64, 169, -507, 0]:
+        eng.raw_rotate_rows(0, a, n, steps, out)
+        got = eng.dev_download(out, n * 2 * k * N).reshape(n, -1)
+        for i in range(n):
+            assert np.array_equal(got[i], orc.rotate_rows(cts[i], steps)), steps
+    eng.dev_free(a)
+    eng.dev_free(out)
+
+
+def test_mac_layer_and_square_layer(pair):
+    from cryptonets_b200.engine import DENSE, SPARSE
+    eng, orc, name = pair
+    N = eng.N
+    rng = np.random.default_rng(11)
+    n_in, M, K = 12, 10, 5
+    vals, cts = _fresh_cts(orc, n_in, 12, nonce0=500)
+    ins = [eng.import_raw(cts[i], 1, N, 4.0) for i in range(n_in)]
+    gather = rng.integers(-1, n_in, (M, K)).astype(np.int32)
+    gather[:, 0] = np.arange(M) % n_in  # at least one real tap per output
+    gather[5:] = gather[4]              # outputs 4.. share a gather row (tile reuse path)
+    w = rng.integers(-300, 300, (M, K)).astype(np.float64)
+    w[:, 0] = np.where(w[:, 0] == 0, 7, w[:, 0])
+    w[2, 1] = 0
+    bias = rng.integers(-1000, 1000, M).astype(np.float64)
+    wv = [eng.plain(w[m], 8.0, SPARSE) for m in range(M)]
+    bv = [eng.plain(np.full(N, bias[m]), 32.0, DENSE) for m in range(M)]
+    outs = eng.layer_conv_dense(ins, gather, wv, bv, M, K)
+    t = orc.t
+    wres = np.where(w * 8 < 0, w * 8 + t, w * 8).astype(np.uint64)
+    bres = np.where(bias * 32 < 0, bias * 32 + t, bias * 32).astype(np.uint64)
+    want = orc.mac_layer(cts, gather, wres, bres, M, K, threads=4).reshape(M, -1)
+    for m in range(M):
+        assert np.array_equal(outs[m].export_raw(0, 0), want[m]), m
+        assert outs[m].scale == 32.0
+    # no bias, identity gather == IMatrix.Mul(ColumnMajor, sparse)  (AtomicSealBfvVector.cs:434-521)
+    one = eng.mat_mul_colmajor_sparse(ins[:K], wv[0])
+    want1 = orc.mac_layer(cts[:K], None, wres[:1], None, 1, K)
+    assert np.array_equal(one.export_raw(0, 0), want1)
+    sq = eng.layer_square(outs[:4])
+    wantsq = orc.square_layer(want[:4], threads=4).reshape(4, -1)
+    for i in range(4):
+        assert np.array_equal(sq[i].export_raw(0, 0), wantsq[i]), i
+        assert sq[i].scale == 32.0 * 32.0
