@@ -1,0 +1,83 @@
+"""Network topologies of the reference apps, built from the layer API exactly as the C# mains build them.
+
+cryptonets_mnist  <- `CryptoNets/CryptoNets.cs:12-75`   (config 2 of BASELINE.json)
+lola_small        <- `LowLatencyCryptoNets/LoLaCryptonets.cs:280-329` (config 3)
+Weights come from tests/golden/*.npz (extracted from the reference's shipped constants by tools/extract_reference_weights.py)
+or, when absent, from a seeded generator of the same shapes."""
+import os
+
+import numpy as np
+
+from .layers import (EncryptLayer, LLConvReader, LLDenseLayer, LLPoolLayer, LLVectorizeLayer, MatrixSource, PoolLayer, SquareActivation,
+                     TimingLayer)
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+CRYPTONETS_PRIMES = [549764251649, 549764284417]  # CryptoNets.cs:17
+LOLA_SMALL_PRIMES = [2277377, 2424833]            # LoLaCryptonets.cs:285
+
+
+def load_weights(name, shapes, seed=0):
+    path = os.path.join(_GOLDEN, name)
+    if os.path.exists(path):
+        z = np.load(path)
+        return {k: z[k] for k in z.files}
+    rng = np.random.default_rng(seed)
+    return {k: rng.normal(0, s, n) for k, (n, s) in shapes.items()}
+
+
+def cryptonets_weights():
+    return load_weights("cryptonets_mnist_weights.npz",
+                        dict(Weights_0=(130, 0.4), Weights_1=(84500, 0.006), Weights_3=(1000, 0.1), Biases_2=(100, 0.05), Biases_3=(10, 0.1)))
+
+
+def lola_small_weights():
+    return load_weights("lola_small_weights.npz", dict(Weights_0=(130, 0.4), Weights_1=(8450, 0.05), Biases_1=(10, 0.1)))
+
+
+def transpose(weights, inputShapeSize, outputMaps):  # CryptoNets.cs:111-122
+    res = np.zeros(len(weights))
+    for i in range(inputShapeSize):
+        for j in range(outputMaps):
+            res[i + inputShapeSize * j] = weights[outputMaps * i + j]
+    return res
+
+
+def synthetic_mnist(n_images, seed=20240917):
+    """MNIST-shaped synthetic batch: uint8 pixels, ~80% zeros."""
+    rng = np.random.default_rng(seed)
+    px = rng.integers(0, 256, (n_images, 784))
+    px[rng.random((n_images, 784)) < 0.8] = 0
+    return px.astype(np.float64)
+
+
+def cryptonets_mnist(factory, images, batch_size=None, fused=True, weights=None, timing=True):
+    """Returns (network, reader).  network.GetNext() yields the 10-column score matrix of one batch."""
+    w = weights or cryptonets_weights()
+    weightscale = 32
+    reader = MatrixSource(images, Scale=16.0, NormalizationFactor=1.0 / 256.0, MaxSlots=batch_size or len(images))
+    enc = EncryptLayer(Source=reader, Factory=factory)
+    src = TimingLayer(Source=enc, StartCounters=["Batch-Time"]) if timing else enc
+    conv1 = PoolLayer(Source=src, InputShape=[28, 28], KernelShape=[5, 5], Upperpadding=[1, 1], Stride=[2, 2], MapCount=[5, 1],
+                      WeightsScale=weightscale, Weights=w["Weights_0"], Fused=fused)
+    act2 = SquareActivation(Source=conv1)
+    dense3 = PoolLayer(Source=act2, InputShape=[5 * 13 * 13], KernelShape=[5 * 13 * 13], Stride=[1000], MapCount=[100],
+                       Weights=transpose(w["Weights_1"], 5 * 13 * 13, 100), Bias=w["Biases_2"], WeightsScale=weightscale * weightscale, Fused=fused)
+    act4 = SquareActivation(Source=dense3)
+    dense5 = PoolLayer(Source=act4, InputShape=[100], KernelShape=[100], Stride=[1000], MapCount=[10], Weights=w["Weights_3"],
+                       Bias=w["Biases_3"], WeightsScale=weightscale, Fused=fused)
+    net = TimingLayer(Source=dense5, StopCounters=["Batch-Time"]) if timing else dense5
+    return net, reader
+
+
+def lola_small(factory, images, weights=None):
+    w = weights or lola_small_weights()
+    weightscale = 64
+    reader = LLConvReader(images, Scale=16.0, NormalizationFactor=1.0 / 256.0, InputShape=[28, 28], KernelShape=[5, 5], Stride=[2, 2],
+                          Upperpadding=[1, 1])
+    enc = EncryptLayer(Source=reader, Factory=factory)
+    conv1 = LLPoolLayer(Source=enc, InputShape=[28, 28], KernelShape=[5, 5], Upperpadding=[1, 1], Stride=[2, 2], MapCount=[5, 1],
+                        WeightsScale=weightscale, Weights=w["Weights_0"])
+    vec2 = LLVectorizeLayer(Source=conv1)
+    act3 = SquareActivation(Source=vec2)
+    dense4 = LLDenseLayer(Source=act3, Bias=w["Biases_1"], Weights=w["Weights_1"], WeightsScale=weightscale)
+    return dense4, reader

@@ -1,0 +1,159 @@
+"""The reference's own known-answer tests, restated on the B200 backend: `HE Wrapper Tests/BasicOperations.cs` (default factory:
+N=4096, primes {40961,65537,114689,147457,188417}, IFactory.cs:247-253) and the BasicExample of README.md:61-73.
+Decrypted results must equal the plain results exactly, as in the reference (`Compare`, BasicOperations.cs:41-55)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+values1 = np.array([-1, 9, 3, 20, 1000, -6945], dtype=np.float64)
+values2 = np.array([8, -22, 5, 4, 254, -12], dtype=np.float64)
+values_m = np.array([[1, -2, 3, -44, 5, 7], [99, 12, -88, 22, 16, 13]], dtype=np.float64)
+scale = 12
+
+
+@pytest.fixture(scope="module")
+def F():
+    from cryptonets_b200.he import B200BfvFactory
+    f = B200BfvFactory()
+    yield f
+    f.Dispose()
+
+
+@pytest.fixture(scope="module")
+def objs(F):
+    from cryptonets_b200.interfaces import EMatrixFormat, EVectorFormat
+    return dict(enc1=F.GetEncryptedVector(values1, EVectorFormat.dense, scale), enc2=F.GetEncryptedVector(values2, EVectorFormat.dense, scale),
+                plain2=F.GetPlainVector(values2, EVectorFormat.dense, scale), mat=F.GetEncryptedMatrix(values_m, EMatrixFormat.ColumnMajor, scale))
+
+
+def test_decrypt(F, objs):
+    assert np.array_equal(objs["enc1"].Decrypt(), values1)
+    assert np.array_equal(objs["mat"].Decrypt(), values_m)
+    assert np.array_equal(objs["mat"].GetColumn(0).Decrypt(), values_m[:, 0])
+
+
+def test_matrix_vector_multiplication(F, objs):
+    from cryptonets_b200.interfaces import EVectorFormat
+    enc_sparse = F.GetEncryptedVector(values1, EVectorFormat.sparse, scale)
+    assert np.array_equal(objs["mat"].Mul(enc_sparse).Decrypt(), values_m @ values1)
+    plain_sparse = F.GetPlainVector(values1, EVectorFormat.sparse, scale)
+    assert np.array_equal(objs["mat"].Mul(plain_sparse).Decrypt(), values_m @ values1)
+
+
+def test_add_subtract_multiply(F, objs):
+    e1, e2, p2 = objs["enc1"], objs["enc2"], objs["plain2"]
+    assert np.array_equal(e1.Add(e2).Decrypt(), values1 + values2)
+    assert np.array_equal(e1.Add(p2).Decrypt(), values1 + values2)
+    assert np.array_equal(e1.Subtract(e2).Decrypt(), values1 - values2)
+    assert np.array_equal(e1.Subtract(p2).Decrypt(), values1 - values2)
+    assert np.array_equal(e1.PointwiseMultiply(e2).Decrypt(), values1 * values2)
+    assert np.array_equal(e1.PointwiseMultiply(p2).Decrypt(), values1 * values2)
+
+
+def test_dot_product_and_sum(F, objs):
+    e1, e2, p2 = objs["enc1"], objs["enc2"], objs["plain2"]
+    assert e1.DotProduct(e2).Decrypt()[0] == float(values1 @ values2)
+    assert e1.DotProduct(p2).Decrypt()[0] == float(values1 @ values2)
+    assert e1.SumAllSlots().Decrypt()[0] == values1.sum()
+    # README.md:61-73 BasicExample: (1,2,3).(1,2,3) = 14, sum = 6, elementwise (1,2,3)*(-1,5,-4)
+    from cryptonets_b200.interfaces import EVectorFormat
+    a = F.GetEncryptedVector(np.array([1.0, 2, 3]), EVectorFormat.dense, 1)
+    b = F.GetEncryptedVector(np.array([-1.0, 5, -4]), EVectorFormat.dense, 1)
+    assert a.DotProduct(a).Decrypt()[0] == 14
+    assert a.SumAllSlots().Decrypt()[0] == 6
+    assert list(a.PointwiseMultiply(b).Decrypt()) == [-1, 10, -12]
+
+
+def test_meta(F, objs):
+    e1 = objs["enc1"]
+    assert e1.IsEncrypted and not objs["plain2"].IsEncrypted
+    assert e1.Scale == scale
+    c = F.CopyVector(e1)
+    c.RegisterScale(20)
+    assert np.array_equal(c.Decrypt(), values1 * scale / 20)
+
+
+@pytest.mark.parametrize("count", [4096 // 8, 10, 4096 // 8 - 5])
+def test_duplicate(F, objs, count):
+    dup = objs["enc1"].Duplicate(count)
+    assert dup.Dim == count * 8
+    d = dup.Decrypt()
+    exp = np.zeros(8)
+    exp[:6] = values1
+    assert np.array_equal(d, np.tile(exp, count))
+
+
+def test_packed_dot_products(F, objs):
+    from cryptonets_b200.interfaces import EVectorFormat
+    res = objs["enc1"].DotProduct(objs["enc2"], length=4).Decrypt()
+    assert res[3] == float(values1[:4] @ values2[:4])
+    rng = np.random.default_rng(5)
+    data = np.rint(rng.normal(0, 1, 4096) * 10)
+    enc = F.GetEncryptedVector(data, EVectorFormat.dense, 1)
+    res = enc.DotProduct(enc, length=1024).Decrypt()
+    for i in range(4):
+        assert res[1024 * i + 1023] == float(data[i * 1024:(i + 1) * 1024] @ data[i * 1024:(i + 1) * 1024])
+
+
+def test_interleave(F):
+    from cryptonets_b200.interfaces import EMatrixFormat
+    mat = np.array([[1, 0, 0, 2, 0, 0], [3, 0, 0, 4, 0, 0]], dtype=np.float64).T
+    m = F.GetEncryptedMatrix(mat, EMatrixFormat.ColumnMajor, 10)
+    assert list(m.Interleave(1).Decrypt()) == [1, 3, 0, 2, 4, 0]
+    mat = np.array([[0, 0, 1, 0, 0, 2], [0, 0, 3, 0, 0, 4], [0, 0, 5, 0, 0, 6]], dtype=np.float64).T
+    m = F.GetEncryptedMatrix(mat, EMatrixFormat.ColumnMajor, 10)
+    assert list(m.Interleave(-1).Decrypt()) == [5, 3, 1, 6, 4, 2]
+
+
+def test_permute(F):
+    from cryptonets_b200.interfaces import EVectorFormat
+    v = F.GetEncryptedVector(np.arange(1, 11, dtype=np.float64), EVectorFormat.dense, 1)
+    s1, s2 = np.zeros(10), np.zeros(10)
+    s1[[1, 4]] = 1
+    s2[[3, 6]] = 1
+    sel1, sel2 = F.GetPlainVector(s1, EVectorFormat.dense, 1), F.GetPlainVector(s2, EVectorFormat.dense, 1)
+    w = v.Permute([sel1, sel2], [1, 2], 5)
+    assert list(w.Decrypt()) == [2, 4, 0, 5, 7]
+
+
+def test_big_stack(F):
+    from cryptonets_b200.interfaces import EMatrixFormat, EVectorFormat
+    n = 1050
+    v = [F.GetEncryptedVector(np.arange(i * n, (i + 1) * n, dtype=np.float64), EVectorFormat.dense, 1) for i in range(4)]
+    m = F.GetMatrix(v, EMatrixFormat.ColumnMajor)
+    vec = m.ConvertToColumnVector()
+    assert np.array_equal(vec.Decrypt(), np.arange(4 * n, dtype=np.float64))
+
+
+def test_generate_value_from_string(F):
+    primes = [40961, 65537, 114689, 147457, 188417]
+    expected = [21399, 63588, 101610, 90324, 148561]
+    v = F.GetValueFromString(",".join(str(x) for x in expected))
+    assert [v % p for p in primes] == expected
+    assert F.GetStringFromValue(v) == ",".join(str(x) for x in expected)
+
+
+def test_rotate_matches_raw_semantics(F):
+    from cryptonets_b200.interfaces import EVectorFormat
+    from cryptonets_b200.raw import RawFactory
+    vals = np.arange(1, 21, dtype=np.float64)
+    enc = F.GetEncryptedVector(vals, EVectorFormat.dense, 1)
+    raw = RawFactory(4096 // 2).GetEncryptedVector(vals, EVectorFormat.dense, 1)  # one batching row
+    for amount in (1, 3, -2):
+        got = enc.Rotate(amount).Decrypt()
+        want = raw.Rotate(amount).Decrypt()
+        assert np.array_equal(got, want), amount
+
+
+def test_errors_mirror_reference(F, objs):
+    from cryptonets_b200 import CnheError
+    from cryptonets_b200.interfaces import EVectorFormat
+    other = F.GetEncryptedVector(values1, EVectorFormat.dense, 7)
+    with pytest.raises(CnheError, match="Scales do not match"):
+        objs["enc1"].Add(other)
+    short = F.GetEncryptedVector(values1[:3], EVectorFormat.dense, scale)
+    with pytest.raises(CnheError, match="Dimensions do not match"):
+        objs["enc1"].Add(short)
+    with pytest.raises(CnheError, match="multiplying two plaintexts"):
+        objs["plain2"].PointwiseMultiply(objs["plain2"])

@@ -36,7 +36,10 @@ if __name__ == "__main__":
         peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    for N, count, n in [(4096, 3, 32768), (8192, 5, 16384), (16384, 6, 8192), (8192, 2, 16384)]:
+    cases = [(4096, 3, 32768), (8192, 5, 16384), (16384, 6, 8192), (8192, 2, 16384)]
+    if len(sys.argv) > 3:
+        cases = [(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]))]
+    for N, count, n in cases:
         r = run(N, count, n)
         for d, v in r.items():
             print(json.dumps(dict(N=N, k=count, n_polys=n, dir=d, ms=round(v["ms"], 4), algo_GBs=round(v["gbs"], 1),
