@@ -34,6 +34,43 @@ u64 *Context::ws_alloc(size_t words) {
 }
 void Context::ws_reserve(size_t) {}
 void Context::sync() { CNHE_CUDA(cudaStreamSynchronize(stream)); }
+void Context::prof_begin(int family, double bytes) {
+    if (!prof) return;
+    ProfRec r;
+    r.family = family;
+    r.bytes = bytes;
+    for (cudaEvent_t *e : {&r.e0, &r.e1}) {
+        if (!prof_pool.empty()) { *e = prof_pool.back(); prof_pool.pop_back(); }
+        else CNHE_CUDA(cudaEventCreate(e));
+    }
+    CNHE_CUDA(cudaEventRecord(r.e0, stream));
+    prof_recs.push_back(r);
+}
+void Context::prof_end() {
+    if (!prof) return;
+    CNHE_CUDA(cudaEventRecord(prof_recs.back().e1, stream));
+    if (prof_recs.size() >= 4096) prof_flush();
+}
+void Context::prof_flush() {
+    if (prof_recs.empty()) return;
+    CNHE_CUDA(cudaStreamSynchronize(stream));
+    for (auto &r : prof_recs) {
+        float ms = 0;
+        CNHE_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        prof_ms[r.family] += ms;
+        prof_bytes[r.family] += r.bytes;
+        prof_n[r.family]++;
+        prof_pool.push_back(r.e0);
+        prof_pool.push_back(r.e1);
+    }
+    prof_recs.clear();
+}
+struct ProfScope {
+    Context &c;
+    ProfScope(Context &ctx, int family, double bytes) : c(ctx) { c.prof_begin(family, bytes); }
+    ~ProfScope() { c.prof_end(); }
+};
+#define PROF(family, bytes) ProfScope prof_scope_##__LINE__(c, family, bytes)
 Context::~Context() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
@@ -43,6 +80,8 @@ Context::~Context() {
     if (d_tabs) cudaFree(d_tabs);
     if (d_table_mem) cudaFree(d_table_mem);
     if (d_index_map) cudaFree(d_index_map);
+    for (auto &r : prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto e : prof_pool) cudaEventDestroy(e);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -302,6 +341,7 @@ u64 *const *upload_ptrs_mut(Context &c, const std::vector<u64 *> &ptrs) {
 
 // ---------------------------------------------------------------- core operations
 void op_ntt(Context &c, const u64 *src, u64 *dst, int n_polys, int mod_base, int mod_count, bool inverse) {
+    PROF(inverse ? 1 : 0, 16.0 * c.N * n_polys);
     c.check(inverse ? launch_ntt_inverse(src, dst, n_polys, c.logN, c.d_tabs, mod_base, mod_count, c.stream)
                     : launch_ntt_forward(src, dst, n_polys, c.logN, c.d_tabs, mod_base, mod_count, c.stream),
             "ntt");
@@ -315,8 +355,15 @@ void op_key_switch(Context &c, const u64 *target, int n, const u64 *key, const D
         const int m = std::min(c.chunk, n - c0);
         u64 *digits = c.ws_alloc((size_t)m * dm.D * k * N);
         u64 *acc = c.ws_alloc((size_t)m * 2 * k * N);
-        c.check(launch_ntt_forward_digits(target + (size_t)c0 * k * N, digits, m, k, dm, c.logN, c.d_tabs, c.stream), "ntt_forward_digits");
-        c.check(launch_ks_mac(digits, key, acc, m, dm.D, k, c.logN, c.d_bc, c.stream), "ks_mac");
+        {
+            PROF(0, 8.0 * N * ((double)m * dm.D * k + (double)m * k));
+            c.check(launch_ntt_forward_digits(target + (size_t)c0 * k * N, digits, m, k, dm, c.logN, c.d_tabs, c.stream), "ntt_forward_digits");
+        }
+        {
+            PROF(3, 8.0 * N * ((double)m * dm.D * k + (double)dm.D * 2 * k + (double)m * 2 * k));
+            c.check(launch_ks_mac(digits, key, acc, m, dm.D, k, c.logN, c.d_bc, c.stream), "ks_mac");
+        }
+        PROF(1, 24.0 * N * m * 2 * k);
         c.check(launch_ntt_inverse_add(acc, base + (size_t)c0 * 2 * k * N, out + (size_t)c0 * 2 * k * N, m * 2 * k, c.logN, c.d_tabs, 0, k, c.stream),
                 "ntt_inverse_add");
     }
@@ -329,8 +376,14 @@ static void multiply_chunk(Context &c, int ch, const std::vector<const u64 *> &a
     for (int i = 0; i < m; i++) square = square && a[c0 + i] == b[c0 + i];
     std::vector<const u64 *> pa(a.begin() + c0, a.begin() + c0 + m);
     u64 *A = c.ws_alloc((size_t)m * 2 * kt * N);
-    c.check(launch_behz_lift(upload_ptrs(c, pa), A, m, c.logN, c.d_bc, c.stream), "behz_lift");
-    c.check(launch_ntt_forward(A, A, m * 2 * kt, c.logN, c.d_tabs, 0, kt, c.stream), "ntt_forward");
+    {
+        PROF(2, 8.0 * N * m * 2 * (k + kt));
+        c.check(launch_behz_lift(upload_ptrs(c, pa), A, m, c.logN, c.d_bc, c.stream), "behz_lift");
+    }
+    {
+        PROF(0, 16.0 * N * m * 2 * kt);
+        c.check(launch_ntt_forward(A, A, m * 2 * kt, c.logN, c.d_tabs, 0, kt, c.stream), "ntt_forward");
+    }
     u64 *B = A;
     if (!square) {
         std::vector<const u64 *> pb(b.begin() + c0, b.begin() + c0 + m);
@@ -339,8 +392,15 @@ static void multiply_chunk(Context &c, int ch, const std::vector<const u64 *> &a
         c.check(launch_ntt_forward(B, B, m * 2 * kt, c.logN, c.d_tabs, 0, kt, c.stream), "ntt_forward");
     }
     u64 *D = c.ws_alloc((size_t)m * 3 * kt * N);
-    c.check(launch_behz_tensor(A, B, D, m, k, c.logN, c.d_bc, c.stream), "behz_tensor");
-    c.check(launch_ntt_inverse(D, D, m * 3 * kt, c.logN, c.d_tabs, 0, kt, c.stream), "ntt_inverse");
+    {
+        PROF(2, 8.0 * N * m * kt * (square ? 5 : 7));
+        c.check(launch_behz_tensor(A, B, D, m, k, c.logN, c.d_bc, c.stream), "behz_tensor");
+    }
+    {
+        PROF(1, 16.0 * N * m * 3 * kt);
+        c.check(launch_ntt_inverse(D, D, m * 3 * kt, c.logN, c.d_tabs, 0, kt, c.stream), "ntt_inverse");
+    }
+    PROF(2, 8.0 * N * m * 3 * (kt + k));
     c.check(launch_behz_floor(D, out3, m, c.ch[ch].t, c.logN, c.d_bc, c.stream), "behz_floor");
 }
 void op_multiply(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out3) {

@@ -63,6 +63,16 @@ struct Context {
     std::recursive_mutex mu;
     int chunk = 128;
     uint64_t launches = 0;
+    // optional per-kernel-family timing
+    bool prof = false;
+    struct ProfRec { int family; double bytes; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[6] = {0, 0, 0, 0, 0, 0}, prof_bytes[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t prof_n[6] = {0, 0, 0, 0, 0, 0};
+    void prof_begin(int family, double bytes);
+    void prof_end();
+    void prof_flush();
     // workspace arena (grown on demand, reused by every op)
     u64 *ws = nullptr;
     size_t ws_words = 0, ws_used = 0;

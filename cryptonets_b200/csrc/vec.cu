@@ -235,6 +235,27 @@ extern "C" int cnhe_raw_behz_floor(cnhe_ctx *h, int channel, uint64_t d, int n, 
     c.check(launch_behz_floor((const u64 *)d, (u64 *)out3, n, c.ch[channel].t, c.logN, c.d_bc, c.stream), "behz_floor");
     API_END
 }
+extern "C" int cnhe_dev_copy(cnhe_ctx *h, uint64_t dst, uint64_t src, size_t words) {
+    API_BEGIN(h)
+    CNHE_CUDA(cudaMemcpyAsync((void *)dst, (const void *)src, words * 8, cudaMemcpyDeviceToDevice, c.stream));
+    API_END
+}
+extern "C" int cnhe_prof_enable(cnhe_ctx *h, int on) {
+    API_BEGIN(h)
+    c.prof_flush();
+    c.prof = on != 0;
+    if (on) for (int i = 0; i < 6; i++) { c.prof_ms[i] = 0; c.prof_bytes[i] = 0; c.prof_n[i] = 0; }
+    API_END
+}
+extern "C" int cnhe_prof_collect(cnhe_ctx *h, int family, double *total_ms, uint64_t *launches, double *bytes) {
+    API_BEGIN(h)
+    if (family < 0 || family > 5) fail("bad family");
+    c.prof_flush();
+    if (total_ms) *total_ms = c.prof_ms[family];
+    if (launches) *launches = c.prof_n[family];
+    if (bytes) *bytes = c.prof_bytes[family];
+    API_END
+}
 extern "C" int cnhe_raw_event_timing(cnhe_ctx *h, int start) {
     API_BEGIN(h)
     CNHE_CUDA(cudaEventRecord(start ? c.ev0 : c.ev1, c.stream));
@@ -508,6 +529,37 @@ extern "C" int cnhe_vec_import_raw(cnhe_ctx *h, const uint64_t *src, int blocks,
         CNHE_CUDA(cudaMemcpyAsync(o->ptr(ch), src + (size_t)ch * words, words * 8, cudaMemcpyHostToDevice, c.stream));
     c.sync();
     *out = o;
+    API_END
+}
+extern "C" int cnhe_vecs_import_raw(cnhe_ctx *h, const uint64_t *src, int n, int blocks, uint64_t dim, double scale, int format, cnhe_vec **out) {
+    API_BEGIN(h)
+    if (!src || n < 1 || blocks < 1 || !out) fail("bad arguments");
+    const size_t per = (size_t)blocks * c.ct_words(), words = (size_t)n * per;
+    std::vector<BufRef> big(c.P);
+    for (int ch = 0; ch < c.P; ch++) {
+        big[ch] = c.alloc(words);
+        CNHE_CUDA(cudaMemcpyAsync(big[ch]->p, src + (size_t)ch * words, words * 8, cudaMemcpyHostToDevice, c.stream));
+    }
+    for (int i = 0; i < n; i++) {
+        cnhe_vec *o = new_vec(c, dim, scale, format, true, blocks);
+        for (int ch = 0; ch < c.P; ch++) { o->buf[ch] = big[ch]; o->off[ch] = (size_t)i * per; }
+        out[i] = o;
+    }
+    API_END
+}
+extern "C" int cnhe_vecs_export_raw(cnhe_ctx *h, const cnhe_vec *const *vecs, int n, uint64_t *dst, size_t cap) {
+    API_BEGIN(h)
+    if (n < 1 || !dst) fail("bad arguments");
+    const int blocks = vecs[0]->blocks;
+    const size_t per = (size_t)blocks * c.ct_words();
+    if (cap < (size_t)c.P * n * per) fail("destination too small");
+    for (int i = 0; i < n; i++) {
+        same_ctx(c, vecs[i]);
+        if (!vecs[i]->enc || vecs[i]->blocks != blocks) fail("expecting encrypted vectors with equal block counts");
+        for (int ch = 0; ch < c.P; ch++)
+            CNHE_CUDA(cudaMemcpyAsync(dst + ((size_t)ch * n + i) * per, vecs[i]->ptr(ch), per * 8, cudaMemcpyDeviceToHost, c.stream));
+    }
+    c.sync();
     API_END
 }
 extern "C" int cnhe_vec_device_ptr(const cnhe_vec *v, int channel, uint64_t *dptr, size_t *words) {
@@ -981,9 +1033,13 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
             for (int i = 0; i < n_in; i++) ip[i] = in[i]->block(ch, b);
             std::vector<u64 *> op(M);
             for (int m = 0; m < M; m++) op[m] = big[ch]->p + ((size_t)m * bl + b) * c.ct_words();
+            double used = 0;
+            for (auto &t : tiles) { int kk = 0; for (int j = 0; j < K; j++) kk += grows[(size_t)t.gather_row * K + j] >= 0; used += kk + t.n_out; }
+            c.prof_begin(4, used * 8.0 * c.ct_words());
             c.check(launch_mac_layer(upload_ptrs(c, ip), d_gather, d_tiles, (int)tiles.size(), d_w, d_bias, K, upload_ptrs_mut(c, op), c.k, c.logN, c.d_bc,
                                      c.ch[ch].pc, c.stream),
                     "mac_layer");
+            c.prof_end();
         }
         if (bias && !const_bias) // generic AddPlain per output
             for (int m = 0; m < M; m++) {

@@ -3,6 +3,7 @@
 This is binding code only -- every method is one call into libcnhe.so.  The reference-shaped API (IFactory, IVector,
 IMatrix, layers) lives in he.py / layers.py on top of this."""
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -36,10 +37,12 @@ class Vec:
     def __init__(self, eng, handle):
         self.eng = eng
         self.h = VECP(handle) if not isinstance(handle, VECP) else handle
+        eng._live.add(self)
 
     def dispose(self):
         if self.h:
-            self.eng.L.cnhe_vec_destroy(self.h)
+            if self.eng.h:  # a closed engine has already released every vector
+                self.eng.L.cnhe_vec_destroy(self.h)
             self.h = VECP(None)
 
     def __del__(self):
@@ -83,6 +86,7 @@ class Engine:
 
     def __init__(self, plain_primes, N, dbc_relin=10, dbc_galois=20, small_modulus_count=-1, device=0, coeff_moduli=None):
         self.L = _lib.lib()
+        self._live = weakref.WeakSet()
         pp = _u64(plain_primes)
         h = C.c_void_p()
         if coeff_moduli is None:
@@ -103,6 +107,8 @@ class Engine:
 
     def close(self):
         if self.h:
+            for v in list(self._live):  # vectors hold device buffers of this context: release them first
+                v.dispose()
             self.L.cnhe_context_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -183,6 +189,43 @@ class Engine:
         out = VECP()
         check(self.L.cnhe_vec_import_raw(self.h, _p(a), blocks, int(dim), float(scale), fmt, C.byref(out)))
         return Vec(self, out)
+
+    def import_raw_many(self, host_ptr_or_array, n, blocks, dim, scale=1.0, fmt=DENSE):
+        """host layout [P][n][blocks][2kN]; accepts a numpy array or a raw host address (e.g. a pinned torch tensor's data_ptr())."""
+        if isinstance(host_ptr_or_array, int):
+            src = C.cast(host_ptr_or_array, U64P)
+        else:
+            a = _u64(host_ptr_or_array).ravel()
+            assert a.size == self.P * n * blocks * self.ct_words
+            src = _p(a)
+        out = (VECP * n)()
+        check(self.L.cnhe_vecs_import_raw(self.h, src, n, blocks, int(dim), float(scale), fmt, out))
+        return [Vec(self, out[i]) for i in range(n)]
+
+    def export_raw_many(self, vecs, host_ptr=None):
+        n, blocks = len(vecs), vecs[0].blocks
+        words = self.P * n * blocks * self.ct_words
+        if host_ptr is None:
+            a = np.zeros(words, np.uint64)
+            check(self.L.cnhe_vecs_export_raw(self.h, _vec_array(vecs), n, _p(a), words))
+            return a.reshape(self.P, n, blocks, self.ct_words)
+        check(self.L.cnhe_vecs_export_raw(self.h, _vec_array(vecs), n, C.cast(host_ptr, U64P), words))
+        return None
+
+    def dev_copy(self, dst, src, words):
+        check(self.L.cnhe_dev_copy(self.h, int(dst), int(src), int(words)))
+
+    def prof_enable(self, on=True):
+        check(self.L.cnhe_prof_enable(self.h, int(on)))
+
+    def prof_collect(self):
+        names = ["ntt_forward", "ntt_inverse", "behz_elementwise", "keyswitch_mac", "scalar_mac_layer", "other"]
+        out = {}
+        for i, nm in enumerate(names):
+            ms, n, b = C.c_double(), C.c_uint64(), C.c_double()
+            check(self.L.cnhe_prof_collect(self.h, i, C.byref(ms), C.byref(n), C.byref(b)))
+            out[nm] = dict(ms=ms.value, launches=n.value, bytes=b.value)
+        return out
 
     def copy(self, vec):
         out = VECP()

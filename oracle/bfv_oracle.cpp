@@ -817,7 +817,7 @@ extern "C" int orc_multiply_plain(const orc_ctx *c, const u64 *ct, int size, con
 extern "C" void orc_behz_lift(const orc_ctx *c, const u64 *in, u64 *out) {
     const int k = c->k;
     const size_t N = c->N;
-    std::vector<u64> tmp(k);
+    u64 tmp[16];
     for (size_t n = 0; n < N; n++) {
         /* fastbconv_mtilde: |x * m~ * qhat_i^-1|_qi, then sum against qhat_i mod target */
         u64 sm = 0;
@@ -846,7 +846,7 @@ extern "C" void orc_behz_floor(const orc_ctx *c, const u64 *in, u64 *out) {
     const size_t N = c->N;
     const Mod &msk = c->bsk[k];
     const u64 msk_div_2 = msk.p >> 1;
-    std::vector<u64> tmp(k), fl(k + 1);
+    u64 tmp[16], fl[17];
     for (size_t n = 0; n < N; n++) {
         /* fast_floor: (x_bsk - fastbconv_q->bsk(x_q)) * q^-1 mod bsk_j */
         for (int i = 0; i < k; i++) tmp[i] = mulmod(in[i * N + n], c->inv_qhat_mod_q[i], c->q[i]);
@@ -877,7 +877,13 @@ extern "C" int orc_multiply(const orc_ctx *c, const u64 *a, const u64 *b, u64 *o
     const int k = c->k, kb = k + 1;
     const size_t N = c->N;
     /* steps 0-1: both operands into Bsk, then NTT everything */
-    std::vector<u64> aq(a, a + 2 * k * N), bq(b, b + 2 * k * N), ab(2 * kb * N), bb(2 * kb * N);
+    static thread_local std::vector<u64> aq, bq, ab, bb, tog, d;
+    aq.assign(a, a + 2 * k * N);
+    bq.assign(b, b + 2 * k * N);
+    ab.resize(2 * kb * N);
+    bb.resize(2 * kb * N);
+    tog.resize((size_t)(k + kb) * N);
+    d.resize(N);
     for (int s = 0; s < 2; s++) {
         orc_behz_lift(c, a + (size_t)s * k * N, &ab[(size_t)s * kb * N]);
         orc_behz_lift(c, b + (size_t)s * k * N, &bb[(size_t)s * kb * N]);
@@ -887,7 +893,6 @@ extern "C" int orc_multiply(const orc_ctx *c, const u64 *a, const u64 *b, u64 *o
         for (int j = 0; j < kb; j++) { ntt_fwd(&ab[((size_t)s * kb + j) * N], c->ntt_bsk[j]); ntt_fwd(&bb[((size_t)s * kb + j) * N], c->ntt_bsk[j]); }
     }
     /* step 2: tensor, INTT, times t, gathered as [q | Bsk] per destination polynomial */
-    std::vector<u64> tog((size_t)(k + kb) * N), d(N);
     for (int dst = 0; dst < 3; dst++) {
         for (int l = 0; l < k + kb; l++) {
             const bool inq = l < k;
@@ -919,8 +924,13 @@ extern "C" int orc_multiply(const orc_ctx *c, const u64 *a, const u64 *b, u64 *o
 static void key_switch(const orc_ctx *c, const u64 *target /*k*N coeff form*/, const KSKey &key, int w, u64 *acc0, u64 *acc1) {
     const int k = c->k;
     const size_t N = c->N;
-    std::vector<u128> w0((size_t)k * N, 0), w1((size_t)k * N, 0);
-    std::vector<u64> dig(N), tmp(N);
+    /* per-thread scratch (SEAL uses a per-thread MemoryPoolHandle the same way, AtomicSealBfvVector.cs:27) */
+    static thread_local std::vector<u128> w0, w1;
+    static thread_local std::vector<u64> dig, tmp;
+    w0.assign((size_t)k * N, 0);
+    w1.assign((size_t)k * N, 0);
+    dig.resize(N);
+    tmp.resize(N);
     int idx = 0;
     const u64 mask = (w >= 64) ? ~0ULL : ((1ULL << w) - 1);
     for (int i = 0; i < k; i++) {
@@ -963,7 +973,9 @@ extern "C" int orc_relinearize(const orc_ctx *c, const u64 *ct3, u64 *out) {
     if (!c->have_keys) return fail("no keys");
     const int k = c->k;
     const size_t N = c->N;
-    std::vector<u64> a0(k * N), a1(k * N);
+    static thread_local std::vector<u64> a0, a1;
+    a0.resize(k * N);
+    a1.resize(k * N);
     key_switch(c, ct3 + (size_t)2 * k * N, c->rlk, c->dbc_relin, a0.data(), a1.data());
     for (int l = 0; l < k; l++)
         for (size_t x = 0; x < N; x++) {
@@ -1058,7 +1070,6 @@ extern "C" int orc_mac_layer(const orc_ctx *c, const u64 *in, int n_in, const in
     parallel_for((int)ms.size(), threads, [&](int mi) {
         int m = ms[mi];
         u64 *dst = out + (size_t)m * ctw;
-        std::vector<u64> tmp(ctw);
         bool first = true;
         for (int kk = 0; kk < K; kk++) {
             int g = gather ? gather[(size_t)m * K + kk] : kk;
@@ -1092,7 +1103,8 @@ extern "C" int orc_square_layer(const orc_ctx *c, const u64 *in, int n, u64 *out
     for (int i = begin; i < n; i += step) is.push_back(i);
     parallel_for((int)is.size(), threads, [&](int ii) {
         int i = is[ii];
-        std::vector<u64> t3(ctw / 2 * 3);
+        static thread_local std::vector<u64> t3;
+        t3.resize(ctw / 2 * 3);
         orc_multiply(c, in + (size_t)i * ctw, in + (size_t)i * ctw, t3.data());
         orc_relinearize(c, t3.data(), out + (size_t)i * ctw);
     });
