@@ -20,6 +20,7 @@ _SIGS = {
     "cnhe_context_info": [C.c_void_p, C.POINTER(C.c_uint32)] + [C.POINTER(i32)] * 5,
     "cnhe_context_coeff_moduli": [C.c_void_p, U64P],
     "cnhe_context_plain_moduli": [C.c_void_p, U64P],
+    "cnhe_context_bsk_moduli": [C.c_void_p, U64P, C.POINTER(i32)],
     "cnhe_context_galois_elts": [C.c_void_p, U64P],
     "cnhe_context_set_option": [C.c_void_p, C.c_char_p, i64],
     "cnhe_context_sync": [C.c_void_p],

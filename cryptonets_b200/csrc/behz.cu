@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) k_behz_lift(const u64 *const *__restrict_
                                                   const BehzConst *__restrict__ gbc) {
     __shared__ BehzConst bc;
     load_consts(&bc, gbc);
-    const int N = 1 << logn, k = bc.k, kt = 2 * k + 1;
+    const int N = 1 << logn, k = bc.k, kb = bc.kb, kt = k + kb;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)n_polys << logn) return;
     const int x = (int)(gid & (N - 1)), poly = (int)(gid >> logn);
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_behz_lift(const u64 *const *__restrict_
     }
     sm &= MT_MASK;
     const u64 r = (M_TILDE - ((sm * bc.inv_q_mod_mtilde) & MT_MASK)) & MT_MASK;
-    for (int j = 0; j <= k; j++) {
+    for (int j = 0; j < kb; j++) {
         const DMod bj = bc.bsk[j];
         U128 acc = {0, 0};
 #pragma unroll
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_behz_tensor(const u64 *a, const u64 *b,
                                                     const BehzConst *__restrict__ gbc) {
     __shared__ BehzConst bc;
     load_consts(&bc, gbc);
-    const int N = 1 << logn, k = bc.k, kt = 2 * k + 1;
+    const int N = 1 << logn, k = bc.k, kb = bc.kb, kt = k + kb;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= ((size_t)n * kt) << logn) return;
     const int x = (int)(gid & (N - 1));
@@ -98,13 +98,14 @@ __global__ void __launch_bounds__(256) k_behz_floor(const u64 *__restrict__ d, u
                                                    const BehzConst *__restrict__ gbc) {
     __shared__ BehzConst bc;
     load_consts(&bc, gbc);
-    const int N = 1 << logn, k = bc.k, kt = 2 * k + 1;
+    const int N = 1 << logn, k = bc.k, kb = bc.kb, kt = k + kb;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)n_polys << logn) return;
     const int x = (int)(gid & (N - 1)), poly = (int)(gid >> logn);
     const u64 *src = d + (size_t)poly * kt * N + x;
     u64 *dst = out + (size_t)poly * k * N + x;
-    u64 tmp[KMAX], fl[KMAX + 1];
+    const int na = kb - 1; // auxiliary primes (the base B); bsk[na] is m_sk
+    u64 tmp[KBMAX], fl[KBMAX];
 #pragma unroll
     for (int i = 0; i < KMAX; i++)
         if (i < k) {
@@ -112,8 +113,8 @@ __global__ void __launch_bounds__(256) k_behz_floor(const u64 *__restrict__ d, u
             tmp[i] = mulmod(v, bc.inv_qhat_mod_q[i], bc.q[i]);
         }
 #pragma unroll
-    for (int j = 0; j <= KMAX; j++)
-        if (j <= k) {
+    for (int j = 0; j < KBMAX; j++)
+        if (j < kb) {
             const DMod bj = bc.bsk[j];
             U128 acc = {0, 0};
 #pragma unroll
@@ -123,22 +124,22 @@ __global__ void __launch_bounds__(256) k_behz_floor(const u64 *__restrict__ d, u
             u64 xb = mulmod(src[(size_t)(k + j) * N], t, bj);
             fl[j] = mulmod(xb + (bj.p - conv), bc.inv_q_mod_bsk[j], bj);
         }
-    const DMod msk = bc.bsk[k];
+    const DMod msk = bc.bsk[na];
 #pragma unroll
-    for (int j = 0; j < KMAX; j++)
-        if (j < k) tmp[j] = mulmod(fl[j], bc.inv_bhat_mod_b[j], bc.bsk[j]);
+    for (int j = 0; j < KBMAX; j++)
+        if (j < na) tmp[j] = mulmod(fl[j], bc.inv_bhat_mod_b[j], bc.bsk[j]);
     U128 am = {0, 0};
 #pragma unroll
-    for (int j = 0; j < KMAX; j++)
-        if (j < k) mac128(am, tmp[j], bc.bhat_mod_msk[j]);
-    const u64 alpha = mulmod(barrett128(am, msk) + (msk.p - fl[k]), bc.inv_B_mod_msk, msk);
+    for (int j = 0; j < KBMAX; j++)
+        if (j < na) mac128(am, tmp[j], bc.bhat_mod_msk[j]);
+    const u64 alpha = mulmod(barrett128(am, msk) + (msk.p - fl[na]), bc.inv_B_mod_msk, msk);
     const bool neg = alpha > (msk.p >> 1);
     for (int i = 0; i < k; i++) {
         const DMod qi = bc.q[i];
         U128 acc = {0, 0};
 #pragma unroll
-        for (int j = 0; j < KMAX; j++)
-            if (j < k) mac128(acc, tmp[j], bc.bhat_mod_q[i][j]);
+        for (int j = 0; j < KBMAX; j++)
+            if (j < na) mac128(acc, tmp[j], bc.bhat_mod_q[i][j]);
         u64 v = barrett128(acc, qi);
         U128 c = neg ? mul64wide(bc.B_mod_q[i], msk.p - alpha) : mul64wide(qi.p - bc.B_mod_q[i], alpha);
         add128(c, v);
@@ -224,9 +225,9 @@ cudaError_t launch_behz_floor(const u64 *d, u64 *out3, int n, u64 t, int logn, c
     k_behz_floor<<<blocks_for((size_t)n * 3 << logn), 256, 0, s>>>(d, out3, n * 3, t, logn, bc);
     return cudaGetLastError();
 }
-cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *d, int n, int k, int logn, const BehzConst *bc, cudaStream_t s) {
+cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *d, int n, int kt, int logn, const BehzConst *bc, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    k_behz_tensor<<<blocks_for(((size_t)n * (2 * k + 1)) << logn), 256, 0, s>>>(a, b, d, n, logn, bc);
+    k_behz_tensor<<<blocks_for(((size_t)n * kt) << logn), 256, 0, s>>>(a, b, d, n, logn, bc);
     return cudaGetLastError();
 }
 cudaError_t launch_ks_mac(const u64 *digits, const u64 *key, u64 *acc, int n, int D, int k, int logn, const BehzConst *bc, cudaStream_t s) {

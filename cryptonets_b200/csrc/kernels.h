@@ -6,12 +6,17 @@
 namespace cnhe {
 
 // NTT tables of one modulus in HBM (N words each); the kernels index an array of these by modulus id:
-//   0..k-1 coefficient primes q_i, k..2k the BEHZ base Bsk (aux primes then m_sk), 2k+1.. plain moduli.
+//   0..k-1 coefficient primes q_i, k..k+kb-1 the BEHZ base Bsk (aux primes then m_sk), k+kb.. plain moduli.
 struct NttTab {
     const u64 *w, *ws;   // psi^bitrev(i) and floor(w 2^64 / p)        (forward, Cooley-Tukey order)
     const u64 *iw, *iws; // psi^-bitrev(i) and its Shoup quotient       (inverse, Gentleman-Sande order)
     u64 inv_n, inv_n_s;  // N^-1 mod p and its Shoup quotient
     DMod mod;
+    // FP64 butterfly path (p < 2^50): the same twiddles as exact doubles, centred in (-p/2, p/2]
+    const double *wd, *iwd;
+    double pd, pinv, inv_n_d;
+    int fp_ok;                          // 1 when the FP64 path is exact for this modulus and N
+    unsigned fwd_recenter, inv_recenter; // forward: bit i = re-centre at the start of pass i; inverse: bit v = re-centre the sums of stage v
 };
 
 // Base-2^w digit decomposition used by relinearisation / Galois key switching: digit d comes from residue
@@ -28,16 +33,19 @@ enum NttStore { NTT_STORE_PLAIN = 0, NTT_STORE_ADD = 1 };
 
 // In-place / out-of-place batched negacyclic NTT.  Polynomial b (0 <= b < n_polys) uses modulus
 // mod_base + (b % mod_count).  src == dst allowed.
-cudaError_t launch_ntt_forward(const u64 *src, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base, int mod_count,
+// fp: 1 = every modulus of the range has fp_ok (FP64 butterflies), 0 = integer Harvey butterflies (any p < 2^62)
+cudaError_t launch_ntt_forward(const u64 *src, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base, int mod_count, int fp,
                                cudaStream_t s);
-cudaError_t launch_ntt_inverse(const u64 *src, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base, int mod_count,
+cudaError_t launch_ntt_inverse(const u64 *src, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base, int mod_count, int fp,
                                cudaStream_t s);
 // dst[((c*D + d)*k + l)] = NTT_l( digit d of target[c] )   target: [n_ct][k][N] coefficient form
-cudaError_t launch_ntt_forward_digits(const u64 *target, u64 *dst, int n_ct, int k, const DigitMap &dm, int logn, const NttTab *tabs,
+cudaError_t launch_ntt_forward_digits(const u64 *target, u64 *dst, int n_ct, int k, const DigitMap &dm, int logn, const NttTab *tabs, int fp,
                                       cudaStream_t s);
 // dst[b] = INTT(src[b]) + base[b]  (mod p)
 cudaError_t launch_ntt_inverse_add(const u64 *src, const u64 *base, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base,
-                                   int mod_count, cudaStream_t s);
+                                   int mod_count, int fp, cudaStream_t s);
+// pass structure shared by host (re-centring masks) and device: radix (log2) of each pass, forward and inverse
+int ntt_pass_radices(int logn, int inverse, int *radices /*4*/);
 int ntt_kernel_smem_bytes(int logn);
 
 } // namespace cnhe
@@ -45,21 +53,22 @@ int ntt_kernel_smem_bytes(int logn);
 // ---------------------------------------------------------------------------------------------------------------
 namespace cnhe {
 
-constexpr int KMAX = 9; // up to 9 coefficient primes (N = 16384 default table)
+constexpr int KMAX = 9;   // up to 9 coefficient primes (N = 16384 default table)
+constexpr int KBMAX = 12; // up to 12 primes in the BEHZ base Bsk (auxiliary primes + m_sk)
 
 // Everything the BEHZ kernels need that depends only on (q, Bsk, m~): SEAL 3.2 util::BaseConverter::generate.
 struct BehzConst {
-    int k, centered_mtilde;
-    DMod q[KMAX], bsk[KMAX + 1];
+    int k, kb, centered_mtilde, pad_; // k coefficient primes; kb primes in Bsk = (kb-1) auxiliary primes then m_sk
+    DMod q[KMAX], bsk[KBMAX];
     u64 inv_qhat_mod_q[KMAX];        // (q/q_i)^-1 mod q_i
     u64 mtilde_inv_qhat_mod_q[KMAX]; // m~ (q/q_i)^-1 mod q_i
     u64 qhat_mod_mtilde[KMAX];       // (q/q_i) mod 2^32
     u64 inv_q_mod_mtilde;            // q^-1 mod 2^32
-    u64 qhat_mod_bsk[KMAX + 1][KMAX];
-    u64 q_mod_bsk[KMAX + 1], inv_q_mod_bsk[KMAX + 1], inv_mtilde_mod_bsk[KMAX + 1];
-    u64 inv_bhat_mod_b[KMAX];        // (B/b_j)^-1 mod b_j
-    u64 bhat_mod_q[KMAX][KMAX];      // (B/b_j) mod q_i
-    u64 bhat_mod_msk[KMAX];
+    u64 qhat_mod_bsk[KBMAX][KMAX];
+    u64 q_mod_bsk[KBMAX], inv_q_mod_bsk[KBMAX], inv_mtilde_mod_bsk[KBMAX];
+    u64 inv_bhat_mod_b[KBMAX];       // (B/b_j)^-1 mod b_j
+    u64 bhat_mod_q[KMAX][KBMAX];     // (B/b_j) mod q_i
+    u64 bhat_mod_msk[KBMAX];
     u64 inv_B_mod_msk, B_mod_q[KMAX];
 };
 // Per plaintext modulus t.
@@ -102,10 +111,10 @@ cudaError_t launch_mac_layer(const u64 *const *in_ptrs, const int *gather, const
                              const u64 *bias, int K, u64 *const *out_ptrs, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
 
 // ---- K5: BEHZ multiply pieces
-// in: ct pointers (each [2][k][N]); out together layout [n][2][2k+1][N] (q residues copied, then Bsk residues)
+// in: ct pointers (each [2][k][N]); out together layout [n][2][k+kb][N] (q residues copied, then Bsk residues)
 cudaError_t launch_behz_lift(const u64 *const *ct_ptrs, u64 *out, int n, int logn, const BehzConst *bc, cudaStream_t s);
 // d[n][3][2k+1][N] from NTT-form a,b [n][2][2k+1][N]
-cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *d, int n, int k, int logn, const BehzConst *bc, cudaStream_t s);
+cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *d, int n, int kt, int logn, const BehzConst *bc, cudaStream_t s);
 // d (coefficient form) -> times t, fast_floor, fastbconv_sk -> out3[n][3][k][N]
 cudaError_t launch_behz_floor(const u64 *d, u64 *out3, int n, u64 t, int logn, const BehzConst *bc, cudaStream_t s);
 // ---- K6: key-switch inner product. digits [n][D][k][N] (NTT), key [D][2][k][N] (NTT) -> acc [n][2][k][N] (NTT)

@@ -292,6 +292,286 @@ k_ntt_inverse(const u64 *src, const u64 *base_add, u64 *dst, const NttTab *__res
     }
 }
 
+// ================================================================ FP64 butterfly path (p < 2^50)
+// On B200 a 64x64->128-bit integer product costs ~9 IMAD-pipe slots (IMAD.WIDE issues at 0.77 and mul.hi.u64 at 0.23
+// warp-instr/clk/SM, measured: profiles/r01_pipe_issue_rates.txt) while DFMA/DADD issue at 1.94 and overlap with the integer
+// ALU.  For moduli below 2^50 -- all of SEAL's default coefficient primes and the 48-bit auxiliary base -- the butterfly
+// is therefore done in double precision with error-free transformations:
+//     h = a*w, l = fma(a,w,-h) (exact product h+l),  q = rint(h/p),  r = fma(-q,p,h) + l  ==  a*w - q*p  exactly,
+// 6 DP ops for the modular product + 2 for the butterfly, no integer corrections at all: values stay centred and small
+// (|r| <= (0.5 + 1.5|a|/2^53) p) and the host schedules a re-centring pass only where the bound could reach 2^52.
+// The transform computed is the same function as the integer path (canonical output), so results are bit-identical.
+constexpr double FP_MAGIC = 6755399441055744.0;  // 1.5 * 2^52: adding and subtracting it rounds to the nearest integer
+constexpr double FP_TWO52 = 4503599627370496.0;
+__device__ __forceinline__ double u2d(u64 x) { return __dsub_rn(__longlong_as_double((long long)(x | 0x4330000000000000ULL)), FP_TWO52); }
+__device__ __forceinline__ u64 d2u(double r) { return (u64)__double_as_longlong(__dadd_rn(r, FP_TWO52)) & 0x000FFFFFFFFFFFFFULL; }
+__device__ __forceinline__ double fmodmul(double a, double w, double p, double pinv) {
+    const double h = __dmul_rn(a, w);
+    const double l = __fma_rn(a, w, -h);
+    const double q = __dsub_rn(__fma_rn(h, pinv, FP_MAGIC), FP_MAGIC);
+    return __dadd_rn(__fma_rn(-q, p, h), l);
+}
+__device__ __forceinline__ double frecenter(double x, double p, double pinv) {
+    const double q = __dsub_rn(__fma_rn(x, pinv, FP_MAGIC), FP_MAGIC);
+    return __fma_rn(-q, p, x);
+}
+__device__ __forceinline__ double fcanon(double x, double p, double pinv) { // any |x| < 2^52 -> [0, p)
+    double r = frecenter(x, p, pinv);
+    r = r < 0.0 ? __dadd_rn(r, p) : r;
+    return r >= p ? __dsub_rn(r, p) : r;
+}
+
+template <int LOGN, int S0, int R, bool FROM_G, int PASS>
+__device__ __forceinline__ void fwd_pass_fp(double *sm, const FwdSrc &src, const NttTab &tb, int tid) {
+    constexpr int T = (1 << LOGN) / 16, G = 16 >> R, E = 1 << R, LG = LOGN - S0 - R;
+    const double p = tb.pd, pinv = tb.pinv;
+    const bool rc = (tb.fwd_recenter >> PASS) & 1;
+#pragma unroll
+    for (int gg = 0; gg < G; gg++) {
+        const int gid = tid + gg * T;
+        const int c = gid & ((1 << LG) - 1), j = gid >> LG;
+        const int base = (j << (LG + R)) + c;
+        double x[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) x[e] = FROM_G ? u2d(fwd_load(src, base + (e << LG), tb.mod)) : sm[swz(base + (e << LG))];
+        if (rc) {
+#pragma unroll
+            for (int e = 0; e < E; e++) x[e] = frecenter(x[e], p, pinv);
+        }
+#pragma unroll
+        for (int u = 0; u < R; u++) {
+            const int h = E >> (u + 1);
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                if (e & h) continue;
+                const double w = __ldg(tb.wd + ((1 << (S0 + u)) + (j << u) + (e >> (R - u))));
+                const double t = fmodmul(x[e + h], w, p, pinv);
+                const double a = x[e];
+                x[e] = __dadd_rn(a, t);
+                x[e + h] = __dsub_rn(a, t);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++) sm[swz(base + (e << LG))] = x[e];
+    }
+}
+template <int LOGN, int PASS>
+__device__ __forceinline__ void fwd_last_fp(double *sm, const NttTab &tb, int tid) {
+    constexpr int S0 = LOGN - 4;
+    const double p = tb.pd, pinv = tb.pinv;
+    const bool rc = (tb.fwd_recenter >> PASS) & 1;
+    double2 *smv = reinterpret_cast<double2 *>(sm);
+    const int j = tid, xr = j & 7;
+    double x[16];
+#pragma unroll
+    for (int ch = 0; ch < 8; ch++) {
+        double2 v = smv[j * 8 + (ch ^ xr)];
+        x[2 * ch] = v.x;
+        x[2 * ch + 1] = v.y;
+    }
+    if (rc) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) x[e] = frecenter(x[e], p, pinv);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int h = 8 >> u;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            if (e & h) continue;
+            const double w = __ldg(tb.wd + ((1 << (S0 + u)) + (j << u) + (e >> (4 - u))));
+            const double t = fmodmul(x[e + h], w, p, pinv);
+            const double a = x[e];
+            x[e] = __dadd_rn(a, t);
+            x[e + h] = __dsub_rn(a, t);
+        }
+    }
+    ulonglong2 *smu = reinterpret_cast<ulonglong2 *>(sm);
+#pragma unroll
+    for (int ch = 0; ch < 8; ch++)
+        smu[j * 8 + (ch ^ xr)] = make_ulonglong2(d2u(fcanon(x[2 * ch], p, pinv)), d2u(fcanon(x[2 * ch + 1], p, pinv)));
+}
+template <int LOGN>
+__device__ __forceinline__ void fwd_body_fp(double *sm, const FwdSrc &src, const NttTab &tb, int tid) {
+    if constexpr (LOGN == 10) {
+        fwd_pass_fp<10, 0, 2, true, 0>(sm, src, tb, tid); __syncthreads();
+        fwd_pass_fp<10, 2, 4, false, 1>(sm, src, tb, tid); __syncthreads();
+        fwd_last_fp<10, 2>(sm, tb, tid);
+    } else if constexpr (LOGN == 11) {
+        fwd_pass_fp<11, 0, 3, true, 0>(sm, src, tb, tid); __syncthreads();
+        fwd_pass_fp<11, 3, 4, false, 1>(sm, src, tb, tid); __syncthreads();
+        fwd_last_fp<11, 2>(sm, tb, tid);
+    } else if constexpr (LOGN == 12) {
+        fwd_pass_fp<12, 0, 4, true, 0>(sm, src, tb, tid); __syncthreads();
+        fwd_pass_fp<12, 4, 4, false, 1>(sm, src, tb, tid); __syncthreads();
+        fwd_last_fp<12, 2>(sm, tb, tid);
+    } else if constexpr (LOGN == 13) {
+        fwd_pass_fp<13, 0, 3, true, 0>(sm, src, tb, tid); __syncthreads();
+        fwd_pass_fp<13, 3, 3, false, 1>(sm, src, tb, tid); __syncthreads();
+        fwd_pass_fp<13, 6, 3, false, 2>(sm, src, tb, tid); __syncthreads();
+        fwd_last_fp<13, 3>(sm, tb, tid);
+    } else {
+        fwd_pass_fp<14, 0, 3, true, 0>(sm, src, tb, tid); __syncthreads();
+        fwd_pass_fp<14, 3, 3, false, 1>(sm, src, tb, tid); __syncthreads();
+        fwd_pass_fp<14, 6, 4, false, 2>(sm, src, tb, tid); __syncthreads();
+        fwd_last_fp<14, 3>(sm, tb, tid);
+    }
+    __syncthreads();
+}
+template <int LOGN>
+__global__ void __launch_bounds__((1 << LOGN) / 16, min_blocks(LOGN))
+k_ntt_forward_fp(const u64 *src, u64 *dst, const NttTab *__restrict__ tabs, int mod_base, int mod_count) {
+    extern __shared__ __align__(16) u64 sm[];
+    constexpr int N = 1 << LOGN;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const NttTab tb = tabs[mod_base + b % mod_count];
+    FwdSrc fs;
+    fs.src = src + (size_t)b * N;
+    fs.digit = false; fs.need_reduce = false; fs.shift = 0; fs.mask = 0;
+    fwd_body_fp<LOGN>(reinterpret_cast<double *>(sm), fs, tb, tid);
+    smem_to_global<LOGN>(sm, dst + (size_t)b * N, tid);
+}
+template <int LOGN>
+__global__ void __launch_bounds__((1 << LOGN) / 16, min_blocks(LOGN))
+k_ntt_forward_digits_fp(const u64 *target, u64 *dst, const NttTab *__restrict__ tabs, int k, DigitMap dm) {
+    extern __shared__ __align__(16) u64 sm[];
+    constexpr int N = 1 << LOGN;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int l = b % k, d = (b / k) % dm.D, c = b / (k * dm.D);
+    const NttTab tb = tabs[l];
+    FwdSrc fs;
+    fs.src = target + ((size_t)c * k + dm.src[d]) * N;
+    fs.digit = true;
+    fs.shift = dm.shift[d];
+    fs.mask = dm.mask;
+    fs.need_reduce = dm.mask >= tb.mod.p;
+    fwd_body_fp<LOGN>(reinterpret_cast<double *>(sm), fs, tb, tid);
+    smem_to_global<LOGN>(sm, dst + (size_t)b * N, tid);
+}
+
+// ---- inverse, FP64
+template <int LOGN>
+__device__ __forceinline__ void inv_first_fp(u64 *smraw, const NttTab &tb, int tid) {
+    constexpr int N = 1 << LOGN;
+    const double p = tb.pd, pinv = tb.pinv;
+    ulonglong2 *smu = reinterpret_cast<ulonglong2 *>(smraw);
+    double2 *smv = reinterpret_cast<double2 *>(smraw);
+    const int j = tid, xr = j & 7;
+    const u64 half = tb.mod.p >> 1;
+    double x[16];
+#pragma unroll
+    for (int ch = 0; ch < 8; ch++) { // centred load: |x| <= p/2
+        ulonglong2 v = smu[j * 8 + (ch ^ xr)];
+        x[2 * ch] = v.x > half ? __dsub_rn(u2d(v.x), p) : u2d(v.x);
+        x[2 * ch + 1] = v.y > half ? __dsub_rn(u2d(v.y), p) : u2d(v.y);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int h = 1 << u;
+        const bool rc = (tb.inv_recenter >> u) & 1;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            if (e & h) continue;
+            const double w = __ldg(tb.iwd + ((N >> (u + 1)) + (j << (3 - u)) + (e >> (u + 1))));
+            const double a = x[e], bq = x[e + h];
+            const double sum = __dadd_rn(a, bq);
+            x[e] = rc ? frecenter(sum, p, pinv) : sum;
+            x[e + h] = fmodmul(__dsub_rn(a, bq), w, p, pinv);
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 8; ch++) smv[j * 8 + (ch ^ xr)] = make_double2(x[2 * ch], x[2 * ch + 1]);
+}
+template <int LOGN, int V0, int R, bool LAST, int PASS>
+__device__ __forceinline__ void inv_pass_fp(double *sm, u64 *dst, const u64 *base_add, const NttTab &tb, int tid) {
+    constexpr int N = 1 << LOGN, T = N / 16, G = 16 >> R, E = 1 << R;
+    const double p = tb.pd, pinv = tb.pinv;
+#pragma unroll
+    for (int gg = 0; gg < G; gg++) {
+        const int gid = tid + gg * T;
+        const int c = gid & ((1 << V0) - 1), j = gid >> V0;
+        const int base = (j << (V0 + R)) + c;
+        double x[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) x[e] = sm[swz(base + (e << V0))];
+#pragma unroll
+        for (int u = 0; u < R; u++) {
+            const int h = 1 << u;
+            const bool rc = (tb.inv_recenter >> (V0 + u)) & 1; // re-centre the sums of stage V0+u (host-scheduled)
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                if (e & h) continue;
+                const double w = __ldg(tb.iwd + ((N >> (V0 + u + 1)) + (j << (R - 1 - u)) + (e >> (u + 1))));
+                const double a = x[e], bq = x[e + h];
+                const double sum = __dadd_rn(a, bq);
+                x[e] = rc ? frecenter(sum, p, pinv) : sum;
+                x[e + h] = fmodmul(__dsub_rn(a, bq), w, p, pinv);
+            }
+        }
+        if constexpr (LAST) {
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                double r = fmodmul(x[e], tb.inv_n_d, p, pinv); // |x| < 2^52 (host-checked); r in (-1.3p, 1.3p)
+                r = r < 0.0 ? __dadd_rn(r, p) : r;
+                r = r < 0.0 ? __dadd_rn(r, p) : r;
+                r = r >= p ? __dsub_rn(r, p) : r;
+                u64 v = d2u(r);
+                const int idx = base + (e << V0);
+                if (base_add) v = addmod(v, base_add[idx], tb.mod.p);
+                dst[idx] = v;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; e++) sm[swz(base + (e << V0))] = x[e];
+        }
+    }
+}
+template <int LOGN>
+__global__ void __launch_bounds__((1 << LOGN) / 16, min_blocks(LOGN))
+k_ntt_inverse_fp(const u64 *src, const u64 *base_add, u64 *dst, const NttTab *__restrict__ tabs, int mod_base, int mod_count) {
+    extern __shared__ __align__(16) u64 sm[];
+    constexpr int N = 1 << LOGN;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const NttTab tb = tabs[mod_base + b % mod_count];
+    global_to_smem<LOGN>(sm, src + (size_t)b * N, tid);
+    __syncthreads();
+    inv_first_fp<LOGN>(sm, tb, tid);
+    __syncthreads();
+    double *smd = reinterpret_cast<double *>(sm);
+    u64 *d = dst + (size_t)b * N;
+    const u64 *ba = base_add ? base_add + (size_t)b * N : nullptr;
+    if constexpr (LOGN == 10) {
+        inv_pass_fp<10, 4, 4, false, 1>(smd, d, ba, tb, tid); __syncthreads();
+        inv_pass_fp<10, 8, 2, true, 2>(smd, d, ba, tb, tid);
+    } else if constexpr (LOGN == 11) {
+        inv_pass_fp<11, 4, 4, false, 1>(smd, d, ba, tb, tid); __syncthreads();
+        inv_pass_fp<11, 8, 3, true, 2>(smd, d, ba, tb, tid);
+    } else if constexpr (LOGN == 12) {
+        inv_pass_fp<12, 4, 4, false, 1>(smd, d, ba, tb, tid); __syncthreads();
+        inv_pass_fp<12, 8, 4, true, 2>(smd, d, ba, tb, tid);
+    } else if constexpr (LOGN == 13) {
+        inv_pass_fp<13, 4, 3, false, 1>(smd, d, ba, tb, tid); __syncthreads();
+        inv_pass_fp<13, 7, 3, false, 2>(smd, d, ba, tb, tid); __syncthreads();
+        inv_pass_fp<13, 10, 3, true, 3>(smd, d, ba, tb, tid);
+    } else {
+        inv_pass_fp<14, 4, 4, false, 1>(smd, d, ba, tb, tid); __syncthreads();
+        inv_pass_fp<14, 8, 3, false, 2>(smd, d, ba, tb, tid); __syncthreads();
+        inv_pass_fp<14, 11, 3, true, 3>(smd, d, ba, tb, tid);
+    }
+}
+
+int ntt_pass_radices(int logn, int inverse, int *r) {
+    static const int F[5][4] = {{2, 4, 4, 0}, {3, 4, 4, 0}, {4, 4, 4, 0}, {3, 3, 3, 4}, {3, 3, 4, 4}};
+    static const int I[5][4] = {{4, 4, 2, 0}, {4, 4, 3, 0}, {4, 4, 4, 0}, {4, 3, 3, 3}, {4, 4, 3, 3}};
+    if (logn < 10 || logn > 14) return 0;
+    int n = 0;
+    for (int i = 0; i < 4; i++) {
+        r[i] = inverse ? I[logn - 10][i] : F[logn - 10][i];
+        if (r[i]) n++;
+    }
+    return n;
+}
+
 // ---------------------------------------------------------------- launchers
 int ntt_kernel_smem_bytes(int logn) { return (1 << logn) * 8; }
 
@@ -310,9 +590,17 @@ static cudaError_t prep(K kern, int logn) {
     default: return cudaErrorInvalidValue;                                                                              \
     }
 
-cudaError_t launch_ntt_forward(const u64 *src, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base, int mod_count,
+cudaError_t launch_ntt_forward(const u64 *src, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base, int mod_count, int fp,
                                cudaStream_t s) {
     if (n_polys <= 0) return cudaSuccess;
+    if (fp) {
+        CNHE_DISPATCH_LOGN(logn, {
+            cudaError_t e = prep(k_ntt_forward_fp<L>, L);
+            if (e != cudaSuccess) return e;
+            k_ntt_forward_fp<L><<<n_polys, (1 << L) / 16, ntt_kernel_smem_bytes(L), s>>>(src, dst, tabs, mod_base, mod_count);
+        });
+        return cudaGetLastError();
+    }
     CNHE_DISPATCH_LOGN(logn, {
         cudaError_t e = prep(k_ntt_forward<L>, L);
         if (e != cudaSuccess) return e;
@@ -320,9 +608,17 @@ cudaError_t launch_ntt_forward(const u64 *src, u64 *dst, int n_polys, int logn, 
     });
     return cudaGetLastError();
 }
-cudaError_t launch_ntt_forward_digits(const u64 *target, u64 *dst, int n_ct, int k, const DigitMap &dm, int logn, const NttTab *tabs,
+cudaError_t launch_ntt_forward_digits(const u64 *target, u64 *dst, int n_ct, int k, const DigitMap &dm, int logn, const NttTab *tabs, int fp,
                                       cudaStream_t s) {
     if (n_ct <= 0) return cudaSuccess;
+    if (fp) {
+        CNHE_DISPATCH_LOGN(logn, {
+            cudaError_t e = prep(k_ntt_forward_digits_fp<L>, L);
+            if (e != cudaSuccess) return e;
+            k_ntt_forward_digits_fp<L><<<n_ct * dm.D * k, (1 << L) / 16, ntt_kernel_smem_bytes(L), s>>>(target, dst, tabs, k, dm);
+        });
+        return cudaGetLastError();
+    }
     CNHE_DISPATCH_LOGN(logn, {
         cudaError_t e = prep(k_ntt_forward_digits<L>, L);
         if (e != cudaSuccess) return e;
@@ -331,8 +627,16 @@ cudaError_t launch_ntt_forward_digits(const u64 *target, u64 *dst, int n_ct, int
     return cudaGetLastError();
 }
 static cudaError_t launch_inv(const u64 *src, const u64 *base, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base,
-                              int mod_count, cudaStream_t s) {
+                              int mod_count, int fp, cudaStream_t s) {
     if (n_polys <= 0) return cudaSuccess;
+    if (fp) {
+        CNHE_DISPATCH_LOGN(logn, {
+            cudaError_t e = prep(k_ntt_inverse_fp<L>, L);
+            if (e != cudaSuccess) return e;
+            k_ntt_inverse_fp<L><<<n_polys, (1 << L) / 16, ntt_kernel_smem_bytes(L), s>>>(src, base, dst, tabs, mod_base, mod_count);
+        });
+        return cudaGetLastError();
+    }
     CNHE_DISPATCH_LOGN(logn, {
         cudaError_t e = prep(k_ntt_inverse<L>, L);
         if (e != cudaSuccess) return e;
@@ -340,13 +644,13 @@ static cudaError_t launch_inv(const u64 *src, const u64 *base, u64 *dst, int n_p
     });
     return cudaGetLastError();
 }
-cudaError_t launch_ntt_inverse(const u64 *src, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base, int mod_count,
+cudaError_t launch_ntt_inverse(const u64 *src, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base, int mod_count, int fp,
                                cudaStream_t s) {
-    return launch_inv(src, nullptr, dst, n_polys, logn, tabs, mod_base, mod_count, s);
+    return launch_inv(src, nullptr, dst, n_polys, logn, tabs, mod_base, mod_count, fp, s);
 }
 cudaError_t launch_ntt_inverse_add(const u64 *src, const u64 *base, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base,
-                                   int mod_count, cudaStream_t s) {
-    return launch_inv(src, base, dst, n_polys, logn, tabs, mod_base, mod_count, s);
+                                   int mod_count, int fp, cudaStream_t s) {
+    return launch_inv(src, base, dst, n_polys, logn, tabs, mod_base, mod_count, fp, s);
 }
 
 } // namespace cnhe

@@ -2,6 +2,7 @@
 #include "runtime.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "hostmath.h"
@@ -114,6 +115,41 @@ static DMod make_dmod(u64 p) {
     hm::barrett_ratio(p, m.r0, m.r1);
     return m;
 }
+// Decide whether the FP64 butterfly path is exact for this modulus and schedule its re-centring points.
+// Magnitudes are tracked in units of p; every operand of a modular product must stay below 2^52 (limit L = 2^52/p, 10% margin).
+static void fp_schedule(NttTab &tb, int logN, bool force_int) {
+    tb.fp_ok = 0;
+    tb.fwd_recenter = tb.inv_recenter = 0;
+    const u64 p = tb.mod.p;
+    if (force_int || hm::bit_length(p) > 49) return;
+    const double L = 0.9 * 4503599627370496.0 / (double)p;
+    auto c = [&](double a) { return 0.5 + 0.75 * a / (L / 0.9) + 1e-6; }; // bound of |a*w mod p| for |a| <= a*p, |w| <= p/2
+    int rad[4];
+    const int np = ntt_pass_radices(logN, 0, rad);
+    double A = 1.0; // canonical input
+    for (int i = 0; i < np; i++) {
+        for (int attempt = 0; attempt < 2; attempt++) {
+            double a = attempt ? 0.51 : A;
+            bool ok = true;
+            for (int s = 0; s < rad[i]; s++) { ok = ok && a < L; a += c(a); }
+            ok = ok && a < L; // the canonicalisation / next pass consumes it
+            if (ok) { A = a; if (attempt) tb.fwd_recenter |= 1u << i; break; }
+            if (attempt) return; // even a re-centred pass overflows
+            if (i == 0) return;  // the first pass reads straight from global memory: no re-centring slot
+        }
+    }
+    // inverse: centred input (0.5); sums double every stage; bit v re-centres the sums produced by stage v
+    A = 0.5;
+    for (int v = 0; v < logN; v++) {
+        if (2 * A >= L) return;
+        const double y = c(2 * A);
+        double x = 2 * A;
+        if (2 * x >= L) { tb.inv_recenter |= 1u << v; x = 0.51; }
+        A = std::max(x, y);
+    }
+    if (A >= L) return;
+    tb.fp_ok = 1;
+}
 static DigitMap make_digit_map(const std::vector<u64> &q, int w) {
     DigitMap dm;
     memset(&dm, 0, sizeof(dm));
@@ -157,19 +193,49 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
         for (u64 qq : c.q)
             if (p >= qq) throw Error(-1, "plaintext modulus must be smaller than every coefficient prime");
     }
-    // Bsk = k auxiliary 61-bit primes (= 1 mod 2^18, descending, after m_sk and gamma) then m_sk   (SEAL small_mods)
-    const u64 M_SK = 0x1fffffffffe00001ULL, GAMMA = 0x1fffffffffc80001ULL;
+    // ---- BEHZ base Bsk = auxiliary primes then m_sk.
+    // "seal" mode reproduces SEAL 3.2's choice: k auxiliary 61-bit primes (= 1 mod 2^18, descending, after m_sk and gamma)
+    // and m_sk = 0x1fffffffffe00001.  The default "fast" mode picks 48-bit primes instead, as many as the exactness bound
+    // needs (B*m_sk > 2^8 * N*t*q): every value BEHZ computes is an integer determined by (q, t, m~) alone -- the Bsk residues
+    // only carry it -- so the multiply output is bit-identical in both modes (tests/test_gpu_kernels.py checks that), while
+    // 48-bit moduli keep every NTT of the multiply on the FP64 butterfly path.
+    const u64 M_SK_SEAL = 0x1fffffffffe00001ULL, GAMMA = 0x1fffffffffc80001ULL;
     {
-        u64 cand = (1ULL << 61) + 1;
-        int skipped = 0;
-        while ((int)c.bsk.size() < k) {
-            cand -= 1ULL << 18;
-            if (!hm::is_prime(cand)) continue;
-            if (skipped < 2) { skipped++; continue; }
-            c.bsk.push_back(cand);
+        const char *mode = getenv("CNHE_AUX_BASE");
+        const bool seal = mode && std::string(mode) == "seal";
+        if (seal) {
+            u64 cand = (1ULL << 61) + 1;
+            int skipped = 0;
+            while ((int)c.bsk.size() < k) {
+                cand -= 1ULL << 18;
+                if (!hm::is_prime(cand)) continue;
+                if (skipped < 2) { skipped++; continue; }
+                c.bsk.push_back(cand);
+            }
+            c.bsk.push_back(M_SK_SEAL);
+        } else {
+            int need = logN + 8;
+            u64 tmax = 0;
+            for (u64 t : c.t) tmax = std::max(tmax, t);
+            need += hm::bit_length(tmax);
+            for (u64 p : c.q) need += hm::bit_length(p);
+            const int count = (need + 46) / 47; // each 48-bit prime contributes more than 47 bits
+            if (count > KBMAX) throw Error(-1, "parameters too large for the auxiliary base");
+            u64 cand = (1ULL << 48) + 1;
+            while ((int)c.bsk.size() < std::max(count, 2)) {
+                cand -= 2ULL * N;
+                if (!hm::is_prime(cand)) continue;
+                bool clash = false;
+                for (u64 p : c.q) clash = clash || p == cand;
+                for (u64 p : c.t) clash = clash || p == cand;
+                if (!clash) c.bsk.push_back(cand);
+            }
+            std::reverse(c.bsk.begin(), c.bsk.end()); // m_sk (last) = the largest
         }
-        c.bsk.push_back(M_SK);
     }
+    const int kb = (int)c.bsk.size();
+    const u64 M_SK = c.bsk[kb - 1];
+    c.kb = kb;
     CNHE_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     CNHE_CUDA(cudaEventCreate(&c.ev0));
     CNHE_CUDA(cudaEventCreate(&c.ev1));
@@ -179,33 +245,42 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
         uint64_t thr = ~0ULL;
         CNHE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     }
-    // ---- NTT tables: ids 0..k-1 q, k..2k Bsk, 2k+1+c plain modulus c
-    const int n_mod = 2 * k + 1 + P;
+    // ---- NTT tables: ids 0..k-1 q, k..k+kb-1 Bsk, k+kb+c plain modulus c
+    const int n_mod = k + kb + P;
     std::vector<u64> moduli;
     for (u64 p : c.q) moduli.push_back(p);
     for (u64 p : c.bsk) moduli.push_back(p);
     for (u64 p : c.t) moduli.push_back(p);
-    std::vector<u64> host((size_t)n_mod * 4 * N);
+    std::vector<u64> host((size_t)n_mod * 6 * N);
     CNHE_CUDA(cudaMalloc((void **)&c.d_table_mem, host.size() * sizeof(u64)));
     c.h_tabs.resize(n_mod);
     for (int m = 0; m < n_mod; m++) {
         const u64 p = moduli[m];
         const u64 psi = hm::minimal_primitive_root(2ULL * N, p), ipsi = hm::inv(psi, p);
-        u64 *w = &host[((size_t)m * 4 + 0) * N], *ws = w + N, *iw = ws + N, *iws = iw + N;
+        u64 *w = &host[((size_t)m * 6 + 0) * N], *ws = w + N, *iw = ws + N, *iws = iw + N;
+        double *wd = reinterpret_cast<double *>(iws + N), *iwd = wd + N;
         u64 a = 1, b = 1;
         for (u64 i = 0; i < N; i++) {
             const u64 r = hm::bit_reverse(i, logN);
             w[r] = a; ws[r] = hm::shoup(a, p);
             iw[r] = b; iws[r] = hm::shoup(b, p);
+            wd[r] = a > p / 2 ? -(double)(p - a) : (double)a; // centred, exact below 2^53
+            iwd[r] = b > p / 2 ? -(double)(p - b) : (double)b;
             a = hm::mul(a, psi, p);
             b = hm::mul(b, ipsi, p);
         }
         NttTab &tb = c.h_tabs[m];
-        u64 *base = c.d_table_mem + (size_t)m * 4 * N;
+        u64 *base = c.d_table_mem + (size_t)m * 6 * N;
         tb.w = base; tb.ws = base + N; tb.iw = base + 2 * (size_t)N; tb.iws = base + 3 * (size_t)N;
+        tb.wd = reinterpret_cast<const double *>(base + 4 * (size_t)N);
+        tb.iwd = reinterpret_cast<const double *>(base + 5 * (size_t)N);
         tb.inv_n = hm::inv(N % p, p);
         tb.inv_n_s = hm::shoup(tb.inv_n, p);
         tb.mod = make_dmod(p);
+        tb.pd = (double)p;
+        tb.pinv = 1.0 / (double)p;
+        tb.inv_n_d = tb.inv_n > p / 2 ? -(double)(p - tb.inv_n) : (double)tb.inv_n;
+        fp_schedule(tb, logN, getenv("CNHE_NTT_INT") != nullptr);
     }
     CNHE_CUDA(cudaMemcpy(c.d_table_mem, host.data(), host.size() * sizeof(u64), cudaMemcpyHostToDevice));
     CNHE_CUDA(cudaMalloc((void **)&c.d_tabs, n_mod * sizeof(NttTab)));
@@ -227,10 +302,12 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
     BehzConst &bc = c.h_bc;
     memset(&bc, 0, sizeof(bc));
     bc.k = k;
+    bc.kb = kb;
     bc.centered_mtilde = 0;
-    std::vector<u64> B(c.bsk.begin(), c.bsk.begin() + k);
+    const int na = kb - 1;
+    std::vector<u64> B(c.bsk.begin(), c.bsk.begin() + na);
     for (int i = 0; i < k; i++) bc.q[i] = make_dmod(c.q[i]);
-    for (int j = 0; j <= k; j++) bc.bsk[j] = make_dmod(c.bsk[j]);
+    for (int j = 0; j < kb; j++) bc.bsk[j] = make_dmod(c.bsk[j]);
     const u64 MT = 1ULL << 32;
     u64 q_mod_mt = 1;
     for (int i = 0; i < k; i++) q_mod_mt = (q_mod_mt * (c.q[i] & 0xffffffffULL)) & 0xffffffffULL;
@@ -249,16 +326,16 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
             if (l != i) pm = (pm * (c.q[l] & 0xffffffffULL)) & 0xffffffffULL;
         bc.qhat_mod_mtilde[i] = pm;
         bc.B_mod_q[i] = hm::product_mod(B, -1, qi);
-        for (int j = 0; j < k; j++) bc.bhat_mod_q[i][j] = hm::product_mod(B, j, qi);
+        for (int j = 0; j < na; j++) bc.bhat_mod_q[i][j] = hm::product_mod(B, j, qi);
     }
-    for (int j = 0; j <= k; j++) {
+    for (int j = 0; j < kb; j++) {
         const u64 bj = c.bsk[j];
         for (int i = 0; i < k; i++) bc.qhat_mod_bsk[j][i] = hm::product_mod(c.q, i, bj);
         bc.q_mod_bsk[j] = hm::product_mod(c.q, -1, bj);
         bc.inv_q_mod_bsk[j] = hm::inv(bc.q_mod_bsk[j], bj);
         bc.inv_mtilde_mod_bsk[j] = hm::inv(MT % bj, bj);
     }
-    for (int j = 0; j < k; j++) {
+    for (int j = 0; j < na; j++) {
         bc.inv_bhat_mod_b[j] = hm::inv(hm::product_mod(B, j, B[j]), B[j]);
         bc.bhat_mod_msk[j] = hm::product_mod(B, j, M_SK);
     }
@@ -271,7 +348,7 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
         Channel &ch = c.ch[ci];
         const u64 t = c.t[ci];
         ch.t = t;
-        ch.mod_id = 2 * k + 1 + ci;
+        ch.mod_id = k + kb + ci;
         PlainConst &pc = ch.pc;
         memset(&pc, 0, sizeof(pc));
         pc.t = t;
@@ -340,10 +417,15 @@ u64 *const *upload_ptrs_mut(Context &c, const std::vector<u64 *> &ptrs) {
 }
 
 // ---------------------------------------------------------------- core operations
+static int fp_range(const Context &c, int mod_base, int mod_count) {
+    for (int i = mod_base; i < mod_base + mod_count; i++)
+        if (!c.h_tabs[i].fp_ok) return 0;
+    return 1;
+}
 void op_ntt(Context &c, const u64 *src, u64 *dst, int n_polys, int mod_base, int mod_count, bool inverse) {
     PROF(inverse ? 1 : 0, 16.0 * c.N * n_polys);
-    c.check(inverse ? launch_ntt_inverse(src, dst, n_polys, c.logN, c.d_tabs, mod_base, mod_count, c.stream)
-                    : launch_ntt_forward(src, dst, n_polys, c.logN, c.d_tabs, mod_base, mod_count, c.stream),
+    c.check(inverse ? launch_ntt_inverse(src, dst, n_polys, c.logN, c.d_tabs, mod_base, mod_count, fp_range(c, mod_base, mod_count), c.stream)
+                    : launch_ntt_forward(src, dst, n_polys, c.logN, c.d_tabs, mod_base, mod_count, fp_range(c, mod_base, mod_count), c.stream),
             "ntt");
 }
 
@@ -357,20 +439,20 @@ void op_key_switch(Context &c, const u64 *target, int n, const u64 *key, const D
         u64 *acc = c.ws_alloc((size_t)m * 2 * k * N);
         {
             PROF(0, 8.0 * N * ((double)m * dm.D * k + (double)m * k));
-            c.check(launch_ntt_forward_digits(target + (size_t)c0 * k * N, digits, m, k, dm, c.logN, c.d_tabs, c.stream), "ntt_forward_digits");
+            c.check(launch_ntt_forward_digits(target + (size_t)c0 * k * N, digits, m, k, dm, c.logN, c.d_tabs, fp_range(c, 0, k), c.stream), "ntt_forward_digits");
         }
         {
             PROF(3, 8.0 * N * ((double)m * dm.D * k + (double)dm.D * 2 * k + (double)m * 2 * k));
             c.check(launch_ks_mac(digits, key, acc, m, dm.D, k, c.logN, c.d_bc, c.stream), "ks_mac");
         }
         PROF(1, 24.0 * N * m * 2 * k);
-        c.check(launch_ntt_inverse_add(acc, base + (size_t)c0 * 2 * k * N, out + (size_t)c0 * 2 * k * N, m * 2 * k, c.logN, c.d_tabs, 0, k, c.stream),
+        c.check(launch_ntt_inverse_add(acc, base + (size_t)c0 * 2 * k * N, out + (size_t)c0 * 2 * k * N, m * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream),
                 "ntt_inverse_add");
     }
 }
 
 static void multiply_chunk(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, int c0, int m, u64 *out3) {
-    const int k = c.k, kt = 2 * k + 1;
+    const int k = c.k, kt = k + c.kb;
     const size_t N = c.N;
     bool square = true;
     for (int i = 0; i < m; i++) square = square && a[c0 + i] == b[c0 + i];
@@ -382,23 +464,23 @@ static void multiply_chunk(Context &c, int ch, const std::vector<const u64 *> &a
     }
     {
         PROF(0, 16.0 * N * m * 2 * kt);
-        c.check(launch_ntt_forward(A, A, m * 2 * kt, c.logN, c.d_tabs, 0, kt, c.stream), "ntt_forward");
+        c.check(launch_ntt_forward(A, A, m * 2 * kt, c.logN, c.d_tabs, 0, kt, fp_range(c, 0, kt), c.stream), "ntt_forward");
     }
     u64 *B = A;
     if (!square) {
         std::vector<const u64 *> pb(b.begin() + c0, b.begin() + c0 + m);
         B = c.ws_alloc((size_t)m * 2 * kt * N);
         c.check(launch_behz_lift(upload_ptrs(c, pb), B, m, c.logN, c.d_bc, c.stream), "behz_lift");
-        c.check(launch_ntt_forward(B, B, m * 2 * kt, c.logN, c.d_tabs, 0, kt, c.stream), "ntt_forward");
+        c.check(launch_ntt_forward(B, B, m * 2 * kt, c.logN, c.d_tabs, 0, kt, fp_range(c, 0, kt), c.stream), "ntt_forward");
     }
     u64 *D = c.ws_alloc((size_t)m * 3 * kt * N);
     {
         PROF(2, 8.0 * N * m * kt * (square ? 5 : 7));
-        c.check(launch_behz_tensor(A, B, D, m, k, c.logN, c.d_bc, c.stream), "behz_tensor");
+        c.check(launch_behz_tensor(A, B, D, m, kt, c.logN, c.d_bc, c.stream), "behz_tensor");
     }
     {
         PROF(1, 16.0 * N * m * 3 * kt);
-        c.check(launch_ntt_inverse(D, D, m * 3 * kt, c.logN, c.d_tabs, 0, kt, c.stream), "ntt_inverse");
+        c.check(launch_ntt_inverse(D, D, m * 3 * kt, c.logN, c.d_tabs, 0, kt, fp_range(c, 0, kt), c.stream), "ntt_inverse");
     }
     PROF(2, 8.0 * N * m * 3 * (kt + k));
     c.check(launch_behz_floor(D, out3, m, c.ch[ch].t, c.logN, c.d_bc, c.stream), "behz_floor");
@@ -502,19 +584,19 @@ void op_multiply_plain_dense(Context &c, int ch, const u64 *ct, int n, const u64
     const int np = plain_per_ct ? n : 1;
     u64 *lifted = c.ws_alloc((size_t)np * k * N);
     c.check(launch_plain_lift(plain, lifted, np, (int)N, k, c.logN, c.d_bc, c.ch[ch].pc, c.stream), "plain_lift");
-    c.check(launch_ntt_forward(lifted, lifted, np * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+    c.check(launch_ntt_forward(lifted, lifted, np * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
     u64 *tmp = c.ws_alloc((size_t)n * 2 * k * N);
-    c.check(launch_ntt_forward(ct, tmp, n * 2 * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+    c.check(launch_ntt_forward(ct, tmp, n * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
     c.check(launch_dyadic_bcast(tmp, lifted, tmp, n, 2, 1, plain_per_ct ? 1 : 0, k, c.logN, c.d_bc, c.stream), "dyadic");
-    c.check(launch_ntt_inverse(tmp, out, n * 2 * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_inverse");
+    c.check(launch_ntt_inverse(tmp, out, n * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_inverse");
 }
 void op_encode(Context &c, int ch, const u64 *values, int n, int count, u64 *plain) {
     c.check(launch_encode_scatter(values, plain, n, count, c.d_index_map, c.logN, c.stream), "encode_scatter");
-    c.check(launch_ntt_inverse(plain, plain, n, c.logN, c.d_tabs, c.ch[ch].mod_id, 1, c.stream), "ntt_inverse(t)");
+    c.check(launch_ntt_inverse(plain, plain, n, c.logN, c.d_tabs, c.ch[ch].mod_id, 1, fp_range(c, c.ch[ch].mod_id, 1), c.stream), "ntt_inverse(t)");
 }
 void op_decode(Context &c, int ch, const u64 *plain, int n, u64 *values) {
     u64 *tmp = c.ws_alloc((size_t)n * c.N);
-    c.check(launch_ntt_forward(plain, tmp, n, c.logN, c.d_tabs, c.ch[ch].mod_id, 1, c.stream), "ntt_forward(t)");
+    c.check(launch_ntt_forward(plain, tmp, n, c.logN, c.d_tabs, c.ch[ch].mod_id, 1, fp_range(c, c.ch[ch].mod_id, 1), c.stream), "ntt_forward(t)");
     c.check(launch_decode_gather(tmp, values, n, c.d_index_map, c.logN, c.stream), "decode_gather");
 }
 void op_encrypt(Context &c, int chi, const u64 *plain, size_t plain_stride, int n, int coeffs, u64 nonce0, u64 *ct) {
@@ -526,10 +608,10 @@ void op_encrypt(Context &c, int chi, const u64 *plain, size_t plain_stride, int 
         const int m = std::min(4 * c.chunk, n - c0);
         u64 *u = c.ws_alloc((size_t)m * k * N);
         c.check(launch_sample(u, m, SAMPLE_TERNARY, ch.seed, stream_id(8, nonce0 + c0, 0), 1ULL << 16, k, c.logN, c.d_bc, c.stream), "sample");
-        c.check(launch_ntt_forward(u, u, m * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+        c.check(launch_ntt_forward(u, u, m * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
         u64 *dst = ct + (size_t)c0 * 2 * k * N;
         c.check(launch_dyadic_bcast(ch.pk->p, u, dst, m, 2, 0, 1, k, c.logN, c.d_bc, c.stream), "dyadic");
-        c.check(launch_ntt_inverse(dst, dst, m * 2 * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_inverse");
+        c.check(launch_ntt_inverse(dst, dst, m * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_inverse");
         c.check(launch_encrypt_finish(dst, plain ? plain + (size_t)c0 * plain_stride : nullptr, plain_stride, m, plain ? coeffs : 0, ch.seed,
                                       nonce0 + c0, k, c.logN, c.d_bc, ch.pc, c.stream),
                 "encrypt_finish");
@@ -543,9 +625,9 @@ static void dot_with_secret(Context &c, int chi, const u64 *ct, int n, u64 *x) {
     u64 *c0 = c.ws_alloc((size_t)n * kN), *c1 = c.ws_alloc((size_t)n * kN);
     CNHE_CUDA(cudaMemcpy2DAsync(c0, kN * 8, ct, 2 * kN * 8, kN * 8, n, cudaMemcpyDeviceToDevice, c.stream));
     CNHE_CUDA(cudaMemcpy2DAsync(c1, kN * 8, ct + kN, 2 * kN * 8, kN * 8, n, cudaMemcpyDeviceToDevice, c.stream));
-    c.check(launch_ntt_forward(c1, c1, n * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+    c.check(launch_ntt_forward(c1, c1, n * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
     c.check(launch_dyadic_bcast(c1, ch.sk->p, c1, n, 1, 1, 0, k, c.logN, c.d_bc, c.stream), "dyadic");
-    c.check(launch_ntt_inverse_add(c1, c0, x, n * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_inverse_add");
+    c.check(launch_ntt_inverse_add(c1, c0, x, n * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_inverse_add");
 }
 void op_decrypt(Context &c, int chi, const u64 *ct, int n, u64 *plain) {
     u64 *x = c.ws_alloc((size_t)n * c.k * c.N);
@@ -669,7 +751,7 @@ static void make_kskeys(Context &c, Channel &ch, const u64 *target_ntt, const Di
     u64 *e = c.ws_alloc((size_t)D * kN), *as = c.ws_alloc((size_t)D * kN), *a = c.ws_alloc((size_t)D * kN);
     c.check(launch_sample(a, D, SAMPLE_UNIFORM, ch.seed, stream_id(purpose_a, key_tag * 256, 0), 1ULL << 16, k, c.logN, c.d_bc, c.stream), "sample");
     c.check(launch_sample(e, D, SAMPLE_NOISE, ch.seed, stream_id(purpose_e, key_tag * 256, 0), 1ULL << 16, k, c.logN, c.d_bc, c.stream), "sample");
-    c.check(launch_ntt_forward(e, e, D * k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+    c.check(launch_ntt_forward(e, e, D * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
     c.check(launch_dyadic_bcast(a, ch.sk->p, as, D, 1, 1, 0, k, c.logN, c.d_bc, c.stream), "dyadic");
     c.check(launch_ct_add(as, e, as, (size_t)D * kN, k, c.logN, c.d_bc, 0, c.stream), "ct_add");
     c.check(launch_ct_negate(as, as, (size_t)D * kN, k, c.logN, c.d_bc, c.stream), "ct_negate");
@@ -696,14 +778,14 @@ void keys_generate(Context &c, u64 seed) {
         BufRef &sk = key_slot(c, ci, 0, 0, words, true);
         u64 *sk_coeff = c.ws_alloc(kN);
         c.check(launch_sample(sk_coeff, 1, SAMPLE_TERNARY, ch.seed, stream_id(1, 0, 0), 0, k, c.logN, c.d_bc, c.stream), "sample");
-        c.check(launch_ntt_forward(sk_coeff, sk->p, k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+        c.check(launch_ntt_forward(sk_coeff, sk->p, k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
         ch.have_sk = true;
         // public key (-(a s + e), a)
         BufRef &pk = key_slot(c, ci, 1, 0, words, true);
         u64 *e = c.ws_alloc(kN), *as = c.ws_alloc(kN);
         c.check(launch_sample(pk->p + kN, 1, SAMPLE_UNIFORM, ch.seed, stream_id(2, 0, 0), 0, k, c.logN, c.d_bc, c.stream), "sample");
         c.check(launch_sample(e, 1, SAMPLE_NOISE, ch.seed, stream_id(3, 0, 0), 0, k, c.logN, c.d_bc, c.stream), "sample");
-        c.check(launch_ntt_forward(e, e, k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+        c.check(launch_ntt_forward(e, e, k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
         c.check(launch_dyadic_bcast(pk->p + kN, sk->p, as, 1, 1, 1, 0, k, c.logN, c.d_bc, c.stream), "dyadic");
         c.check(launch_ct_add(as, e, as, kN, k, c.logN, c.d_bc, 0, c.stream), "ct_add");
         c.check(launch_ct_negate(as, pk->p, kN, k, c.logN, c.d_bc, c.stream), "ct_negate");
@@ -725,7 +807,7 @@ void keys_generate(Context &c, u64 seed) {
             CNHE_CUDA(cudaMemcpyAsync(pair, sk_coeff, kN * 8, cudaMemcpyDeviceToDevice, c.stream));
             CNHE_CUDA(cudaMemcpyAsync(pair + kN, sk_coeff, kN * 8, cudaMemcpyDeviceToDevice, c.stream));
             c.check(launch_galois(pair, base, rs, 1, einv, k, c.logN, c.d_bc, c.stream), "galois");
-            c.check(launch_ntt_forward(rs, rs, k, c.logN, c.d_tabs, 0, k, c.stream), "ntt_forward");
+            c.check(launch_ntt_forward(rs, rs, k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
             BufRef &gk = key_slot(c, ci, 3, elt, words, true);
             make_kskeys(c, ch, rs, c.dm_galois, c.dbc_galois, 6, 7, gi + 1, gk->p);
         }

@@ -46,7 +46,7 @@ struct Channel { // one plaintext modulus (one AtomicSealBfvEncryptedEnvironment
 struct Context {
     int device = 0;
     uint32_t N = 0;
-    int logN = 0, k = 0, P = 0, dbc_relin = 0, dbc_galois = 0;
+    int logN = 0, k = 0, kb = 0, P = 0, dbc_relin = 0, dbc_galois = 0; // kb: primes in the BEHZ base Bsk
     std::vector<u64> q, bsk, t;
     BehzConst h_bc;
     BehzConst *d_bc = nullptr;

@@ -100,6 +100,13 @@ extern "C" int cnhe_context_coeff_moduli(const cnhe_ctx *h, uint64_t *out) {
     for (int i = 0; i < h->c->k; i++) out[i] = h->c->q[i];
     return CNHE_OK;
 }
+extern "C" int cnhe_context_bsk_moduli(const cnhe_ctx *h, uint64_t *out, int *count) {
+    if (!h || !count) return set_err(CNHE_ERR_INVALID, "null argument");
+    *count = h->c->kb;
+    if (out)
+        for (int i = 0; i < h->c->kb; i++) out[i] = h->c->bsk[i];
+    return CNHE_OK;
+}
 extern "C" int cnhe_context_plain_moduli(const cnhe_ctx *h, uint64_t *out) {
     if (!h || !out) return set_err(CNHE_ERR_INVALID, "null argument");
     for (int i = 0; i < h->c->P; i++) out[i] = h->c->t[i];
@@ -191,7 +198,7 @@ extern "C" int cnhe_dev_download(cnhe_ctx *h, uint64_t *dst, uint64_t dptr, size
 }
 extern "C" int cnhe_raw_ntt(cnhe_ctx *h, uint64_t src, uint64_t dst, int n_polys, int mod_base, int mod_count, int inverse) {
     API_BEGIN(h)
-    if (mod_base < 0 || mod_count < 1 || mod_base + mod_count > 2 * c.k + 1 + c.P) fail("bad modulus range");
+    if (mod_base < 0 || mod_count < 1 || mod_base + mod_count > c.k + c.kb + c.P) fail("bad modulus range");
     op_ntt(c, (const u64 *)src, (u64 *)dst, n_polys, mod_base, mod_count, inverse != 0);
     API_END
 }

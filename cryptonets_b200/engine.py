@@ -104,6 +104,13 @@ class Engine:
         check(self.L.cnhe_context_coeff_moduli(self.h, _p(q)))
         self.q = [int(x) for x in q]
         self.primes = [int(x) for x in pp]
+        cnt = C.c_int()
+        check(self.L.cnhe_context_bsk_moduli(self.h, None, C.byref(cnt)))
+        b = np.zeros(cnt.value, np.uint64)
+        check(self.L.cnhe_context_bsk_moduli(self.h, _p(b), C.byref(cnt)))
+        self.bsk = [int(x) for x in b]
+        self.kb = cnt.value
+        self.plain_mod_id = self.k + self.kb  # NTT table id of plaintext modulus 0
 
     def close(self):
         if self.h:

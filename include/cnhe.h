@@ -56,6 +56,9 @@ int cnhe_context_destroy(cnhe_ctx *);
 int cnhe_context_info(const cnhe_ctx *, uint32_t *N, int *k, int *P, int *relin_digits, int *galois_digits, int *galois_elts);
 int cnhe_context_coeff_moduli(const cnhe_ctx *, uint64_t *out_k);
 int cnhe_context_plain_moduli(const cnhe_ctx *, uint64_t *out_P);
+/* the BEHZ auxiliary base Bsk (auxiliary primes, m_sk last); out may be NULL to query the count.  NTT modulus ids:
+ * 0..k-1 coefficient primes, k..k+count-1 Bsk, k+count+c plaintext modulus c */
+int cnhe_context_bsk_moduli(const cnhe_ctx *, uint64_t *out, int *count);
 int cnhe_context_galois_elts(const cnhe_ctx *, uint64_t *out);
 /* options: "behz_centered_mtilde" (0/1), "chunk" (ciphertexts per multiply/key-switch wave) */
 int cnhe_context_set_option(cnhe_ctx *, const char *name, int64_t value);
@@ -129,7 +132,7 @@ int cnhe_dev_free(cnhe_ctx *, uint64_t dptr);
 int cnhe_dev_upload(cnhe_ctx *, uint64_t dptr, const uint64_t *src, size_t words);
 int cnhe_dev_download(cnhe_ctx *, uint64_t *dst, uint64_t dptr, size_t words);
 /* n_polys residue polynomials at src; polynomial b uses modulus id mod_base + b % mod_count
- * (ids: 0..k-1 q_i, k..2k Bsk, 2k+1+c plain modulus c) */
+ * (ids: see cnhe_context_bsk_moduli) */
 int cnhe_raw_ntt(cnhe_ctx *, uint64_t src, uint64_t dst, int n_polys, int mod_base, int mod_count, int inverse);
 int cnhe_raw_multiply(cnhe_ctx *, int channel, uint64_t a, uint64_t b, int n, uint64_t out3);     /* Evaluator.Multiply, size 3 out */
 int cnhe_raw_relinearize(cnhe_ctx *, int channel, uint64_t in3, int n, uint64_t out2);

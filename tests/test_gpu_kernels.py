@@ -13,32 +13,79 @@ CONFIGS = {
 }
 
 
-@pytest.fixture(scope="module", params=list(CONFIGS))
-def pair(request):
+def _make_pair(name, aux):
+    """aux: 'fast' = 48-bit auxiliary base + FP64 butterflies (the default product configuration);
+            'seal' = SEAL 3.2's 61-bit auxiliary base (integer butterflies on those moduli), comparable stage by stage;
+            'int'  = fast base but integer butterflies everywhere (CNHE_NTT_INT)."""
+    import os
     from cryptonets_b200.engine import Engine
     from oracle.oracle_py import Oracle
-    cfg = CONFIGS[request.param]
-    eng = Engine([cfg["t"]], cfg["N"], cfg["dbc_r"], cfg["dbc_g"], cfg["count"])
+    cfg = CONFIGS[name]
+    os.environ.pop("CNHE_AUX_BASE", None)
+    os.environ.pop("CNHE_NTT_INT", None)
+    if aux == "seal":
+        os.environ["CNHE_AUX_BASE"] = "seal"
+    if aux == "int":
+        os.environ["CNHE_NTT_INT"] = "1"
+    try:
+        eng = Engine([cfg["t"]], cfg["N"], cfg["dbc_r"], cfg["dbc_g"], cfg["count"])
+    finally:
+        os.environ.pop("CNHE_AUX_BASE", None)
+        os.environ.pop("CNHE_NTT_INT", None)
     orc = Oracle(cfg["t"], cfg["N"], cfg["count"], cfg["dbc_r"], cfg["dbc_g"])
     assert eng.q == orc.q
+    if aux == "seal":
+        assert eng.bsk == orc.bsk
     eng.keygen(1234)
     orc.keygen(1234)
+    return eng, orc
+
+
+PAIRS = [(n, "fast") for n in CONFIGS] + [("default4096", "seal"), ("cryptonets8192", "seal"), ("cryptonets8192", "int")]
+
+
+@pytest.fixture(scope="module", params=PAIRS, ids=lambda p: "%s-%s" % p)
+def pair(request):
+    name, aux = request.param
+    eng, orc = _make_pair(name, aux)
+    yield eng, orc, name
+    eng.close()
+
+
+@pytest.fixture(scope="module", params=["default4096", "cryptonets8192"])
+def seal_pair(request):
+    eng, orc = _make_pair(request.param, "seal")
     yield eng, orc, request.param
     eng.close()
+
+
+def _bsk_oracle(eng, orc):
+    """an oracle whose *coefficient* moduli are the engine's Bsk primes, to check NTTs under those primes"""
+    from oracle.oracle_py import Oracle
+    return Oracle(orc.t, eng.N, custom_q=eng.bsk)
+
+
+def _mod_table(eng, orc):
+    """engine modulus id -> (modulus, oracle, oracle table id)"""
+    bo = _bsk_oracle(eng, orc)
+    tab = [(orc.q[i], orc, i) for i in range(eng.k)]
+    tab += [(eng.bsk[j], bo, j) for j in range(eng.kb)]
+    tab += [(orc.t, orc, 2 * orc.k + 1)]
+    return tab
 
 
 def test_ntt_all_moduli(pair):
     eng, orc, _ = pair
     rng = np.random.default_rng(1)
-    N, k = eng.N, eng.k
-    for which in list(range(2 * k + 1)) + [2 * k + 1]:
-        p = orc.modulus_of(which)
+    N = eng.N
+    for which, (p, o, oid) in enumerate(_mod_table(eng, orc)):
         polys = rng.integers(0, p, (3, N), dtype=np.uint64)
-        polys[0, :4] = [0, 1, p - 1, p - 2]
+        polys[0, :6] = [0, 1, p - 1, p - 2, p // 2, p // 2 + 1]
+        polys[1, :] = p - 1  # extreme magnitudes through every butterfly
         d = eng.dev_from(polys)
         eng.raw_ntt(d, d, 3, which, 1, False)
         got = eng.dev_download(d, 3 * N).reshape(3, N)
-        want = np.stack([orc.ntt(which, polys[i]) for i in range(3)])
+        want = np.stack([o.ntt(oid, polys[i]) for i in range(3)])
         assert np.array_equal(got, want), which
         eng.raw_ntt(d, d, 3, which, 1, True)
         back = eng.dev_download(d, 3 * N).reshape(3, N)
@@ -49,15 +96,19 @@ def test_ntt_all_moduli(pair):
 def test_ntt_mixed_batch(pair):
     eng, orc, _ = pair
     rng = np.random.default_rng(2)
-    N, k = eng.N, eng.k
-    kt = 2 * k + 1
-    polys = np.stack([rng.integers(0, orc.modulus_of(b % kt), N, dtype=np.uint64) for b in range(2 * kt)])
+    N = eng.N
+    tab = _mod_table(eng, orc)
+    kt = eng.k + eng.kb
+    polys = np.stack([rng.integers(0, tab[b % kt][0], N, dtype=np.uint64) for b in range(2 * kt)])
     d = eng.dev_from(polys)
     out = eng.dev_alloc(polys.size)
     eng.raw_ntt(d, out, 2 * kt, 0, kt, False)
     got = eng.dev_download(out, polys.size).reshape(polys.shape)
     for b in range(2 * kt):
-        assert np.array_equal(got[b], orc.ntt(b % kt, polys[b])), b
+        p, o, oid = tab[b % kt]
+        assert np.array_equal(got[b], o.ntt(oid, polys[b])), b
+    eng.raw_ntt(out, out, 2 * kt, 0, kt, True)
+    assert np.array_equal(eng.dev_download(out, polys.size).reshape(polys.shape), polys)
     eng.dev_free(d)
     eng.dev_free(out)
 
@@ -95,8 +146,8 @@ def test_encrypt_decrypt(pair):
     assert eng.noise_budget(v, 0, 0) == orc.noise_budget(want0)
 
 
-def test_behz_stages(pair):
-    eng, orc, _ = pair
+def test_behz_stages(seal_pair):
+    eng, orc, _ = seal_pair
     N, k = eng.N, eng.k
     kt = 2 * k + 1
     _, cts = _fresh_cts(orc, 2, 5)

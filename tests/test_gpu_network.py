@@ -28,13 +28,14 @@ def test_cryptonets_mnist_scores_equal_raw_backend(cryptonets):
     raw_net.PrepareNetwork()
     want = raw_net.GetNext().Decrypt()
     assert scores.shape == (8192, 10)
-    # the Raw backend works in doubles and the final integers need ~80 bits, so it is only accurate to 2^-52 ...
-    assert np.allclose(scores, want, rtol=1e-12, atol=0)
-    assert np.array_equal(np.argmax(scores, axis=1), np.argmax(want, axis=1))
-    assert len(set(np.argmax(scores, axis=1))) > 1
-    # ... the encrypted path is exact: compare with exact integer arithmetic on the first 48 images
+    # the encrypted path is exact: compare with exact integer arithmetic on the first 48 images
     exact = _exact_cryptonets(imgs[:48])
     assert np.array_equal(scores[:48], exact)
+    # the Raw backend works in doubles while the integers here need ~80 bits and cancel heavily, so it is only good to
+    # ~2^-45 of the largest intermediate; it still has to agree on every prediction
+    assert np.allclose(scores, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+    assert np.array_equal(np.argmax(scores, axis=1), np.argmax(want, axis=1))
+    assert len(set(np.argmax(scores, axis=1))) > 1
 
 
 def _exact_cryptonets(images):
