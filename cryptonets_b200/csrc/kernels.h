@@ -110,6 +110,10 @@ struct MacTile {
 cudaError_t launch_mac_layer(const u64 *const *in_ptrs, const int *gather, const MacTile *tiles, int n_tiles, const u64 *const *w_ptrs,
                              const u64 *bias, int K, u64 *const *out_ptrs, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
 
+// small-weight variant: wd[m*K + kk] = signed weight as an exact double (|w| < 2^17 and K*|w|*2^26 < 2^52, host-checked)
+cudaError_t launch_mac_layer_fp(const u64 *const *in_ptrs, const int *gather, const MacTile *tiles, int n_tiles, const double *wd, const u64 *bias,
+                                int K, u64 *const *out_ptrs, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
+
 // ---- K5: BEHZ multiply pieces
 // in: ct pointers (each [2][k][N]); out together layout [n][2][k+kb][N] (q residues copied, then Bsk residues)
 cudaError_t launch_behz_lift(const u64 *const *ct_ptrs, u64 *out, int n, int logn, const BehzConst *bc, cudaStream_t s);

@@ -176,6 +176,70 @@ __global__ void __launch_bounds__(128) k_mac_layer(const u64 *const *__restrict_
     }
 }
 
+// FP64 variant for small weights (|w| < 2^17, K*|w|*2^26 < 2^52 checked on the host): every ciphertext word is split into two
+// 26-bit halves and w*x is accumulated exactly in doubles -- 2 DFMA per multiply-accumulate instead of a 64x64->128 integer
+// product (mul.hi.u64 issues at 0.23 warp-instr/clk/SM on B200, DFMA at 1.94: profiles/r01_pipe_issue_rates.txt).
+// The result sum_k w_k x_k is then reduced once, so the output is the same canonical residue as the integer path.
+__device__ __forceinline__ double mac_u2d(u64 x) { return __dsub_rn(__longlong_as_double((long long)(x | 0x4330000000000000ULL)), 4503599627370496.0); }
+__device__ __forceinline__ u64 mac_signed_reduce(double lo, double hi, const DMod &q) { // value = lo + hi * 2^26, both exact integers
+    const long long a = __double2ll_rn(lo), b = __double2ll_rn(hi);
+    __int128 s = (__int128)a + ((__int128)b << 26);
+    const bool neg = s < 0;
+    unsigned __int128 mag = neg ? (unsigned __int128)(-s) : (unsigned __int128)s;
+    U128 m;
+    m.lo = (u64)mag;
+    m.hi = (u64)(mag >> 64);
+    const u64 r = barrett128(m, q);
+    return neg ? negmod(r, q.p) : r;
+}
+__global__ void __launch_bounds__(128) k_mac_layer_fp(const u64 *const *__restrict__ in_ptrs, const int *__restrict__ gather,
+                                                     const MacTile *__restrict__ tiles, const double *__restrict__ wd, const u64 *__restrict__ bias,
+                                                     int K, u64 *const *__restrict__ out_ptrs, int k, int logn, const BehzConst *__restrict__ bc,
+                                                     PlainConst pc) {
+    const int N = 1 << logn;
+    const size_t word = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const size_t ct_words = (size_t)2 * k * N;
+    if (word >= ct_words) return;
+    const MacTile tile = tiles[blockIdx.y];
+    const int l = (int)((word >> logn) % k);
+    const int *grow = gather + (size_t)tile.gather_row * K;
+    const double *wrow[MAC_TM];
+#pragma unroll
+    for (int m = 0; m < MAC_TM; m++) wrow[m] = wd + (size_t)tile.out_index[m < tile.n_out ? m : 0] * K;
+    double a0[MAC_TM][2], a1[MAC_TM][2];
+#pragma unroll
+    for (int m = 0; m < MAC_TM; m++) a0[m][0] = a0[m][1] = a1[m][0] = a1[m][1] = 0.0;
+    for (int kk = 0; kk < K; kk++) {
+        const int g = grow[kk];
+        if (g < 0) continue;
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(in_ptrs[g] + word);
+        const double x0 = mac_u2d(v.x & 0x3ffffffULL), x1 = mac_u2d(v.x >> 26);
+        const double y0 = mac_u2d(v.y & 0x3ffffffULL), y1 = mac_u2d(v.y >> 26);
+#pragma unroll
+        for (int m = 0; m < MAC_TM; m++) {
+            const double w = __ldg(wrow[m] + kk);
+            a0[m][0] = __fma_rn(w, x0, a0[m][0]);
+            a1[m][0] = __fma_rn(w, x1, a1[m][0]);
+            a0[m][1] = __fma_rn(w, y0, a0[m][1]);
+            a1[m][1] = __fma_rn(w, y1, a1[m][1]);
+        }
+    }
+    const DMod q = bc->q[l];
+    const bool c0_first = bias && word < (size_t)k * N && (word & (N - 1)) == 0;
+#pragma unroll
+    for (int m = 0; m < MAC_TM; m++) {
+        if (m < tile.n_out) {
+            const int o = tile.out_index[m];
+            u64 r0 = mac_signed_reduce(a0[m][0], a1[m][0], q), r1 = mac_signed_reduce(a0[m][1], a1[m][1], q);
+            if (c0_first) {
+                const u64 b = bias[o];
+                if (b) r0 = addmod(r0, scale_plain(b, l, q, pc), q.p);
+            }
+            *reinterpret_cast<ulonglong2 *>(out_ptrs[o] + word) = make_ulonglong2(r0, r1);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- sampling (counter-based, shared with the oracle)
 __constant__ u64 NOISE_CDF[19] = {0xff141e3023416d2ULL,  0x2e4f850f76b8d9a6ULL, 0x488c5acec8fd6db3ULL, 0x5d1ca569fc3e4ccbULL, 0x6bbb5699bdd65b9cULL,
                                   0x75291bf8371e7eccULL, 0x7aad3cf138611a69ULL, 0x7d9aa4d4ab7c76bdULL, 0x7f0368341f79807cULL, 0x7fa0f21e3a554470ULL,
@@ -315,6 +379,14 @@ cudaError_t launch_mac_layer(const u64 *const *in_ptrs, const int *gather, const
     const size_t pairs = ((size_t)2 * k << logn) / 2;
     dim3 grid(blocks_for(pairs, 128), n_tiles);
     k_mac_layer<<<grid, 128, 0, s>>>(in_ptrs, gather, tiles, w_ptrs, bias, K, out_ptrs, k, logn, bc, pc);
+    return cudaGetLastError();
+}
+cudaError_t launch_mac_layer_fp(const u64 *const *in_ptrs, const int *gather, const MacTile *tiles, int n_tiles, const double *wd, const u64 *bias,
+                                int K, u64 *const *out_ptrs, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s) {
+    if (n_tiles <= 0) return cudaSuccess;
+    const size_t pairs = ((size_t)2 * k << logn) / 2;
+    dim3 grid(blocks_for(pairs, 128), n_tiles);
+    k_mac_layer_fp<<<grid, 128, 0, s>>>(in_ptrs, gather, tiles, wd, bias, K, out_ptrs, k, logn, bc, pc);
     return cudaGetLastError();
 }
 cudaError_t launch_sample(u64 *out, int n, int kind, u64 seed, u64 stream0, u64 stream_step, int k, int logn, const BehzConst *bc, cudaStream_t s) {

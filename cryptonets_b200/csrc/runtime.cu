@@ -35,6 +35,25 @@ u64 *Context::ws_alloc(size_t words) {
 }
 void Context::ws_reserve(size_t) {}
 void Context::sync() { CNHE_CUDA(cudaStreamSynchronize(stream)); }
+void Context::h2d(void *dst, const void *src, size_t bytes) {
+    if (!bytes) return;
+    if (!stage_buf) {
+        stage_size = 32u << 20;
+        CNHE_CUDA(cudaHostAlloc((void **)&stage_buf, stage_size, cudaHostAllocDefault));
+    }
+    if (bytes > stage_size / 2) { // large: plain (staged by the driver) copy
+        CNHE_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+        return;
+    }
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (stage_off + need > stage_size) { // wrap: everything queued so far must have left the ring
+        CNHE_CUDA(cudaStreamSynchronize(stream));
+        stage_off = 0;
+    }
+    memcpy(stage_buf + stage_off, src, bytes);
+    CNHE_CUDA(cudaMemcpyAsync(dst, stage_buf + stage_off, bytes, cudaMemcpyHostToDevice, stream));
+    stage_off += need;
+}
 void Context::prof_begin(int family, double bytes) {
     if (!prof) return;
     ProfRec r;
@@ -83,6 +102,7 @@ Context::~Context() {
     if (d_index_map) cudaFree(d_index_map);
     for (auto &r : prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : prof_pool) cudaEventDestroy(e);
+    if (stage_buf) cudaFreeHost(stage_buf);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -407,12 +427,12 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
 // ---------------------------------------------------------------- pointer tables
 const u64 *const *upload_ptrs(Context &c, const std::vector<const u64 *> &ptrs) {
     u64 *d = c.ws_alloc(ptrs.size());
-    CNHE_CUDA(cudaMemcpyAsync(d, ptrs.data(), ptrs.size() * sizeof(u64 *), cudaMemcpyHostToDevice, c.stream));
+    c.h2d(d, ptrs.data(), ptrs.size() * sizeof(u64 *));
     return reinterpret_cast<const u64 *const *>(d);
 }
 u64 *const *upload_ptrs_mut(Context &c, const std::vector<u64 *> &ptrs) {
     u64 *d = c.ws_alloc(ptrs.size());
-    CNHE_CUDA(cudaMemcpyAsync(d, ptrs.data(), ptrs.size() * sizeof(u64 *), cudaMemcpyHostToDevice, c.stream));
+    c.h2d(d, ptrs.data(), ptrs.size() * sizeof(u64 *));
     return reinterpret_cast<u64 *const *>(d);
 }
 
@@ -763,7 +783,7 @@ static void make_kskeys(Context &c, Channel &ch, const u64 *target_ntt, const Di
     for (int d = 0; d < D; d++) factors[d] = hm::pw(2, (u64)dm.shift[d], c.q[dm.src[d]]);
     (void)w;
     u64 *dfac = c.ws_alloc(D);
-    CNHE_CUDA(cudaMemcpyAsync(dfac, factors.data(), D * 8, cudaMemcpyHostToDevice, c.stream));
+    c.h2d(dfac, factors.data(), D * 8);
     c.check(launch_key_add_scaled(out, target_ntt, dfac, dm, k, c.logN, c.d_bc, c.stream), "key_add_scaled");
 }
 void keys_generate(Context &c, u64 seed) {

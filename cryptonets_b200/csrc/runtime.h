@@ -80,6 +80,11 @@ struct Context {
     unsigned __int128 big_factor = 0;
     std::vector<unsigned __int128> crt_coeff;
 
+    // pinned staging ring for small host->device uploads (pointer tables, weights, tiles): truly asynchronous copies
+    unsigned char *stage_buf = nullptr;
+    size_t stage_size = 0, stage_off = 0;
+    void h2d(void *dst, const void *src, size_t bytes); // async on `stream`; `src` may be freed on return
+
     ~Context();
     size_t ct_words() const { return (size_t)2 * k * N; }
     void ws_reset() { ws_used = 0; }

@@ -5,6 +5,7 @@
 // keeps in `Ciphertext[] encData` / `Plaintext[] plainData` -- here blocks of HBM.  The functions below restate that
 // class method by method (cited inline); the arithmetic itself is in the CUDA kernels.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 
@@ -1017,9 +1018,9 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
         }
     }
     int *d_gather = (int *)c.ws_alloc((grows.size() + 1) / 2 + 1);
-    CNHE_CUDA(cudaMemcpyAsync(d_gather, grows.data(), grows.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    c.h2d(d_gather, grows.data(), grows.size() * sizeof(int));
     MacTile *d_tiles = (MacTile *)c.ws_alloc((tiles.size() * sizeof(MacTile) + 7) / 8);
-    CNHE_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(MacTile), cudaMemcpyHostToDevice, c.stream));
+    c.h2d(d_tiles, tiles.data(), tiles.size() * sizeof(MacTile));
     const double out_scale = in[0]->scale * weights[0]->scale;
     std::vector<BufRef> big(c.P);
     for (int ch = 0; ch < c.P; ch++) big[ch] = c.alloc((size_t)M * bl * c.ct_words());
@@ -1027,12 +1028,30 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
         std::vector<const u64 *> wp(M);
         for (int m = 0; m < M; m++) wp[m] = weights[m]->ptr(ch);
         const u64 *const *d_w = upload_ptrs(c, wp);
+        // signed weights as doubles for the FP64 accumulate path, when they are small enough for it to be exact
+        const u64 t = c.t[ch], thr = (t + 1) >> 1;
+        std::vector<double> wdh((size_t)M * K);
+        double wmax = 0;
+        for (int m = 0; m < M; m++)
+            for (int kk = 0; kk < K; kk++) {
+                const u64 w = weights[m]->scalars[ch][kk];
+                const double d = w >= thr ? -(double)(t - w) : (double)w;
+                wdh[(size_t)m * K + kk] = d;
+                wmax = std::max(wmax, std::fabs(d));
+            }
+        const bool fp_mac = maxbits <= 50 && wmax < 131072.0 && (double)K * wmax * 67108864.0 < 4503599627370496.0 && !getenv("CNHE_MAC_INT");
+        const double *d_wd = nullptr;
+        if (fp_mac) {
+            u64 *buf = c.ws_alloc(wdh.size());
+            c.h2d(buf, wdh.data(), wdh.size() * 8);
+            d_wd = reinterpret_cast<const double *>(buf);
+        }
         const u64 *d_bias = nullptr;
         if (bias && const_bias) {
             std::vector<u64> bv(M);
             for (int m = 0; m < M; m++) bv[m] = bias[m]->const_val[ch];
             u64 *db = c.ws_alloc(M);
-            CNHE_CUDA(cudaMemcpyAsync(db, bv.data(), (size_t)M * 8, cudaMemcpyHostToDevice, c.stream));
+            c.h2d(db, bv.data(), (size_t)M * 8);
             d_bias = db;
         }
         for (int b = 0; b < bl; b++) {
@@ -1043,9 +1062,14 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
             double used = 0;
             for (auto &t : tiles) { int kk = 0; for (int j = 0; j < K; j++) kk += grows[(size_t)t.gather_row * K + j] >= 0; used += kk + t.n_out; }
             c.prof_begin(4, used * 8.0 * c.ct_words());
-            c.check(launch_mac_layer(upload_ptrs(c, ip), d_gather, d_tiles, (int)tiles.size(), d_w, d_bias, K, upload_ptrs_mut(c, op), c.k, c.logN, c.d_bc,
-                                     c.ch[ch].pc, c.stream),
-                    "mac_layer");
+            if (fp_mac)
+                c.check(launch_mac_layer_fp(upload_ptrs(c, ip), d_gather, d_tiles, (int)tiles.size(), d_wd, d_bias, K, upload_ptrs_mut(c, op), c.k, c.logN,
+                                            c.d_bc, c.ch[ch].pc, c.stream),
+                        "mac_layer_fp");
+            else
+                c.check(launch_mac_layer(upload_ptrs(c, ip), d_gather, d_tiles, (int)tiles.size(), d_w, d_bias, K, upload_ptrs_mut(c, op), c.k, c.logN,
+                                         c.d_bc, c.ch[ch].pc, c.stream),
+                        "mac_layer");
             c.prof_end();
         }
         if (bias && !const_bias) // generic AddPlain per output
@@ -1053,7 +1077,6 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
                 u64 *o = big[ch]->p + (size_t)m * bl * c.ct_words();
                 c.check(launch_ct_add_plain(o, o, bl, 2, bias[m]->ptr(ch), c.N, (int)c.N, c.k, c.logN, c.d_bc, c.ch[ch].pc, 0, c.stream), "ct_add_plain");
             }
-        c.sync(); // host staging vectors
     }
     for (int m = 0; m < M; m++) {
         cnhe_vec *o = new_vec(c, in[0]->dim, out_scale, CNHE_DENSE, true, bl);
