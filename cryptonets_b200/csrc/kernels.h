@@ -71,6 +71,18 @@ struct BehzConst {
     u64 bhat_mod_msk[KBMAX];
     u64 inv_B_mod_msk, B_mod_q[KMAX];
 };
+// The same constants as exact doubles, centred in (-p/2, p/2], for the FP64 kernels (behz_fp.cu); valid when every
+// coefficient and Bsk prime is below 2^50.
+struct BehzConstF {
+    int k, kb, centered_mtilde, pad_;
+    double qd[KMAX], qinv[KMAX], bd[KBMAX], binv[KBMAX];
+    double inv_qhat_mod_q[KMAX], mtilde_inv_qhat_mod_q[KMAX];
+    u64 qhat_mod_mtilde[KMAX], inv_q_mod_mtilde;
+    double qhat_mod_bsk[KBMAX][KMAX];
+    double q_mod_bsk[KBMAX], inv_q_mod_bsk[KBMAX], inv_mtilde_mod_bsk[KBMAX];
+    double inv_bhat_mod_b[KBMAX], bhat_mod_q[KMAX][KBMAX], bhat_mod_msk[KBMAX];
+    double inv_B_mod_msk, msk_half, B_mod_q[KMAX];
+};
 // Per plaintext modulus t.
 struct PlainConst {
     u64 t, threshold;                 // (t+1)/2
@@ -121,6 +133,10 @@ cudaError_t launch_behz_lift(const u64 *const *ct_ptrs, u64 *out, int n, int log
 cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *d, int n, int kt, int logn, const BehzConst *bc, cudaStream_t s);
 // d (coefficient form) -> times t, fast_floor, fastbconv_sk -> out3[n][3][k][N]
 cudaError_t launch_behz_floor(const u64 *d, u64 *out3, int n, u64 t, int logn, const BehzConst *bc, cudaStream_t s);
+cudaError_t launch_behz_lift_fp(const u64 *const *ct_ptrs, u64 *out, int n, int logn, const BehzConstF *f, cudaStream_t s);
+cudaError_t launch_behz_tensor_fp(const u64 *a, const u64 *b, u64 *d, int n, int kt, int logn, const BehzConstF *f, cudaStream_t s);
+cudaError_t launch_behz_floor_fp(const u64 *d, u64 *out3, int n, u64 t, int logn, const BehzConstF *f, cudaStream_t s);
+cudaError_t launch_ks_mac_fp(const u64 *digits, const u64 *key, u64 *acc, int n, int D, int k, int logn, const BehzConstF *f, cudaStream_t s);
 // ---- K6: key-switch inner product. digits [n][D][k][N] (NTT), key [D][2][k][N] (NTT) -> acc [n][2][k][N] (NTT)
 cudaError_t launch_ks_mac(const u64 *digits, const u64 *key, u64 *acc, int n, int D, int k, int logn, const BehzConst *bc, cudaStream_t s);
 // split a size-3 array [n][3][k][N] view: base[n][2][k][N] = (c0,c1), c2[n][k][N]

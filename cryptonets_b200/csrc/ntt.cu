@@ -13,6 +13,7 @@
 // Shared-memory layout: word i is stored at i ^ (((i>>4)&7)<<1) so that the unit-stride last pass (16 consecutive
 // words per thread, 16-byte accesses) and the strided passes (gap >= 16 words) are both bank-conflict free.
 #include "kernels.h"
+#include "fparith.cuh"
 
 namespace cnhe {
 
@@ -301,26 +302,6 @@ k_ntt_inverse(const u64 *src, const u64 *base_add, u64 *dst, const NttTab *__res
 // 6 DP ops for the modular product + 2 for the butterfly, no integer corrections at all: values stay centred and small
 // (|r| <= (0.5 + 1.5|a|/2^53) p) and the host schedules a re-centring pass only where the bound could reach 2^52.
 // The transform computed is the same function as the integer path (canonical output), so results are bit-identical.
-constexpr double FP_MAGIC = 6755399441055744.0;  // 1.5 * 2^52: adding and subtracting it rounds to the nearest integer
-constexpr double FP_TWO52 = 4503599627370496.0;
-__device__ __forceinline__ double u2d(u64 x) { return __dsub_rn(__longlong_as_double((long long)(x | 0x4330000000000000ULL)), FP_TWO52); }
-__device__ __forceinline__ u64 d2u(double r) { return (u64)__double_as_longlong(__dadd_rn(r, FP_TWO52)) & 0x000FFFFFFFFFFFFFULL; }
-__device__ __forceinline__ double fmodmul(double a, double w, double p, double pinv) {
-    const double h = __dmul_rn(a, w);
-    const double l = __fma_rn(a, w, -h);
-    const double q = __dsub_rn(__fma_rn(h, pinv, FP_MAGIC), FP_MAGIC);
-    return __dadd_rn(__fma_rn(-q, p, h), l);
-}
-__device__ __forceinline__ double frecenter(double x, double p, double pinv) {
-    const double q = __dsub_rn(__fma_rn(x, pinv, FP_MAGIC), FP_MAGIC);
-    return __fma_rn(-q, p, x);
-}
-__device__ __forceinline__ double fcanon(double x, double p, double pinv) { // any |x| < 2^52 -> [0, p)
-    double r = frecenter(x, p, pinv);
-    r = r < 0.0 ? __dadd_rn(r, p) : r;
-    return r >= p ? __dsub_rn(r, p) : r;
-}
-
 template <int LOGN, int S0, int R, bool FROM_G, int PASS>
 __device__ __forceinline__ void fwd_pass_fp(double *sm, const FwdSrc &src, const NttTab &tb, int tid) {
     constexpr int T = (1 << LOGN) / 16, G = 16 >> R, E = 1 << R, LG = LOGN - S0 - R;

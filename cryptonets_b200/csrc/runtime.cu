@@ -97,6 +97,7 @@ Context::~Context() {
     g_temps.m.erase(this);
     ch.clear();
     if (d_bc) cudaFree(d_bc);
+    if (d_bf) cudaFree(d_bf);
     if (d_tabs) cudaFree(d_tabs);
     if (d_table_mem) cudaFree(d_table_mem);
     if (d_index_map) cudaFree(d_index_map);
@@ -362,6 +363,42 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
     bc.inv_B_mod_msk = hm::inv(hm::product_mod(B, -1, M_SK), M_SK);
     CNHE_CUDA(cudaMalloc((void **)&c.d_bc, sizeof(BehzConst)));
     CNHE_CUDA(cudaMemcpy(c.d_bc, &bc, sizeof(BehzConst), cudaMemcpyHostToDevice));
+    // FP64 twin of the constants (used when every q_i and Bsk prime is below 2^50)
+    {
+        BehzConstF &f = c.h_bf;
+        memset(&f, 0, sizeof(f));
+        auto cen = [](u64 v, u64 p) { return v > p / 2 ? -(double)(p - v) : (double)v; };
+        f.k = k; f.kb = kb; f.centered_mtilde = 0;
+        c.fp_elementwise = getenv("CNHE_NTT_INT") == nullptr;
+        for (int i = 0; i < k; i++) {
+            const u64 p = c.q[i];
+            c.fp_elementwise = c.fp_elementwise && hm::bit_length(p) <= 49;
+            f.qd[i] = (double)p; f.qinv[i] = 1.0 / (double)p;
+            f.inv_qhat_mod_q[i] = cen(bc.inv_qhat_mod_q[i], p);
+            f.mtilde_inv_qhat_mod_q[i] = cen(bc.mtilde_inv_qhat_mod_q[i], p);
+            f.qhat_mod_mtilde[i] = bc.qhat_mod_mtilde[i];
+            f.B_mod_q[i] = cen(bc.B_mod_q[i], p);
+            for (int j = 0; j < na; j++) f.bhat_mod_q[i][j] = cen(bc.bhat_mod_q[i][j], p);
+        }
+        f.inv_q_mod_mtilde = bc.inv_q_mod_mtilde;
+        for (int j = 0; j < kb; j++) {
+            const u64 p = c.bsk[j];
+            c.fp_elementwise = c.fp_elementwise && hm::bit_length(p) <= 48;
+            f.bd[j] = (double)p; f.binv[j] = 1.0 / (double)p;
+            for (int i = 0; i < k; i++) f.qhat_mod_bsk[j][i] = cen(bc.qhat_mod_bsk[j][i], p);
+            f.q_mod_bsk[j] = cen(bc.q_mod_bsk[j], p);
+            f.inv_q_mod_bsk[j] = cen(bc.inv_q_mod_bsk[j], p);
+            f.inv_mtilde_mod_bsk[j] = cen(bc.inv_mtilde_mod_bsk[j], p);
+        }
+        for (int j = 0; j < na; j++) {
+            f.inv_bhat_mod_b[j] = cen(bc.inv_bhat_mod_b[j], c.bsk[j]);
+            f.bhat_mod_msk[j] = cen(bc.bhat_mod_msk[j], M_SK);
+        }
+        f.inv_B_mod_msk = cen(bc.inv_B_mod_msk, M_SK);
+        f.msk_half = (double)(M_SK >> 1);
+        CNHE_CUDA(cudaMalloc((void **)&c.d_bf, sizeof(BehzConstF)));
+        CNHE_CUDA(cudaMemcpy(c.d_bf, &f, sizeof(BehzConstF), cudaMemcpyHostToDevice));
+    }
     // ---- per plaintext modulus
     c.ch.resize(P);
     for (int ci = 0; ci < P; ci++) {
@@ -463,7 +500,8 @@ void op_key_switch(Context &c, const u64 *target, int n, const u64 *key, const D
         }
         {
             PROF(3, 8.0 * N * ((double)m * dm.D * k + (double)dm.D * 2 * k + (double)m * 2 * k));
-            c.check(launch_ks_mac(digits, key, acc, m, dm.D, k, c.logN, c.d_bc, c.stream), "ks_mac");
+            if (c.fp_elementwise) c.check(launch_ks_mac_fp(digits, key, acc, m, dm.D, k, c.logN, c.d_bf, c.stream), "ks_mac_fp");
+            else c.check(launch_ks_mac(digits, key, acc, m, dm.D, k, c.logN, c.d_bc, c.stream), "ks_mac");
         }
         PROF(1, 24.0 * N * m * 2 * k);
         c.check(launch_ntt_inverse_add(acc, base + (size_t)c0 * 2 * k * N, out + (size_t)c0 * 2 * k * N, m * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream),
@@ -480,7 +518,8 @@ static void multiply_chunk(Context &c, int ch, const std::vector<const u64 *> &a
     u64 *A = c.ws_alloc((size_t)m * 2 * kt * N);
     {
         PROF(2, 8.0 * N * m * 2 * (k + kt));
-        c.check(launch_behz_lift(upload_ptrs(c, pa), A, m, c.logN, c.d_bc, c.stream), "behz_lift");
+        if (c.fp_elementwise) c.check(launch_behz_lift_fp(upload_ptrs(c, pa), A, m, c.logN, c.d_bf, c.stream), "behz_lift_fp");
+        else c.check(launch_behz_lift(upload_ptrs(c, pa), A, m, c.logN, c.d_bc, c.stream), "behz_lift");
     }
     {
         PROF(0, 16.0 * N * m * 2 * kt);
@@ -490,20 +529,23 @@ static void multiply_chunk(Context &c, int ch, const std::vector<const u64 *> &a
     if (!square) {
         std::vector<const u64 *> pb(b.begin() + c0, b.begin() + c0 + m);
         B = c.ws_alloc((size_t)m * 2 * kt * N);
-        c.check(launch_behz_lift(upload_ptrs(c, pb), B, m, c.logN, c.d_bc, c.stream), "behz_lift");
+        if (c.fp_elementwise) c.check(launch_behz_lift_fp(upload_ptrs(c, pb), B, m, c.logN, c.d_bf, c.stream), "behz_lift_fp");
+        else c.check(launch_behz_lift(upload_ptrs(c, pb), B, m, c.logN, c.d_bc, c.stream), "behz_lift");
         c.check(launch_ntt_forward(B, B, m * 2 * kt, c.logN, c.d_tabs, 0, kt, fp_range(c, 0, kt), c.stream), "ntt_forward");
     }
     u64 *D = c.ws_alloc((size_t)m * 3 * kt * N);
     {
         PROF(2, 8.0 * N * m * kt * (square ? 5 : 7));
-        c.check(launch_behz_tensor(A, B, D, m, kt, c.logN, c.d_bc, c.stream), "behz_tensor");
+        if (c.fp_elementwise) c.check(launch_behz_tensor_fp(A, B, D, m, kt, c.logN, c.d_bf, c.stream), "behz_tensor_fp");
+        else c.check(launch_behz_tensor(A, B, D, m, kt, c.logN, c.d_bc, c.stream), "behz_tensor");
     }
     {
         PROF(1, 16.0 * N * m * 3 * kt);
         c.check(launch_ntt_inverse(D, D, m * 3 * kt, c.logN, c.d_tabs, 0, kt, fp_range(c, 0, kt), c.stream), "ntt_inverse");
     }
     PROF(2, 8.0 * N * m * 3 * (kt + k));
-    c.check(launch_behz_floor(D, out3, m, c.ch[ch].t, c.logN, c.d_bc, c.stream), "behz_floor");
+    if (c.fp_elementwise) c.check(launch_behz_floor_fp(D, out3, m, c.ch[ch].t, c.logN, c.d_bf, c.stream), "behz_floor_fp");
+    else c.check(launch_behz_floor(D, out3, m, c.ch[ch].t, c.logN, c.d_bc, c.stream), "behz_floor");
 }
 void op_multiply(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out3) {
     const int n = (int)a.size();

@@ -50,6 +50,9 @@ struct Context {
     std::vector<u64> q, bsk, t;
     BehzConst h_bc;
     BehzConst *d_bc = nullptr;
+    BehzConstF h_bf;
+    BehzConstF *d_bf = nullptr;
+    bool fp_elementwise = false; // every q_i, Bsk prime small enough for the FP64 element-wise kernels
     std::vector<NttTab> h_tabs;
     NttTab *d_tabs = nullptr;
     u64 *d_table_mem = nullptr;
