@@ -192,38 +192,60 @@ __device__ __forceinline__ u64 mac_signed_reduce(double lo, double hi, const DMo
     const u64 r = barrett128(m, q);
     return neg ? negmod(r, q.p) : r;
 }
+constexpr int MAC_KC = 64; // taps staged per chunk (pointers + weights in shared memory)
+constexpr int MAC_U = 8;   // loads in flight per thread
 __global__ void __launch_bounds__(128) k_mac_layer_fp(const u64 *const *__restrict__ in_ptrs, const int *__restrict__ gather,
                                                      const MacTile *__restrict__ tiles, const double *__restrict__ wd, const u64 *__restrict__ bias,
                                                      int K, u64 *const *__restrict__ out_ptrs, int k, int logn, const BehzConst *__restrict__ bc,
                                                      PlainConst pc) {
+    __shared__ const u64 *sptr[MAC_KC];
+    __shared__ double sw[MAC_KC][MAC_TM];
     const int N = 1 << logn;
     const size_t word = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     const size_t ct_words = (size_t)2 * k * N;
-    if (word >= ct_words) return;
+    const bool active = word < ct_words;
+    const size_t w_off = active ? word : 0;
     const MacTile tile = tiles[blockIdx.y];
-    const int l = (int)((word >> logn) % k);
+    const int l = (int)((w_off >> logn) % k);
     const int *grow = gather + (size_t)tile.gather_row * K;
-    const double *wrow[MAC_TM];
-#pragma unroll
-    for (int m = 0; m < MAC_TM; m++) wrow[m] = wd + (size_t)tile.out_index[m < tile.n_out ? m : 0] * K;
     double a0[MAC_TM][2], a1[MAC_TM][2];
 #pragma unroll
     for (int m = 0; m < MAC_TM; m++) a0[m][0] = a0[m][1] = a1[m][0] = a1[m][1] = 0.0;
-    for (int kk = 0; kk < K; kk++) {
-        const int g = grow[kk];
-        if (g < 0) continue;
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(in_ptrs[g] + word);
-        const double x0 = mac_u2d(v.x & 0x3ffffffULL), x1 = mac_u2d(v.x >> 26);
-        const double y0 = mac_u2d(v.y & 0x3ffffffULL), y1 = mac_u2d(v.y >> 26);
+    for (int k0 = 0; k0 < K; k0 += MAC_KC) {
+        const int kc = min(MAC_KC, K - k0);
+        __syncthreads();
+        // stage this chunk: padded taps (gather < 0) become a valid pointer with zero weights, so the inner loop is branch free
+        for (int i = threadIdx.x; i < MAC_KC; i += blockDim.x) {
+            const int g = i < kc ? grow[k0 + i] : -1;
+            sptr[i] = in_ptrs[g < 0 ? 0 : g];
+        }
+        for (int i = threadIdx.x; i < MAC_KC * MAC_TM; i += blockDim.x) {
+            const int kk = i / MAC_TM, m = i % MAC_TM;
+            const bool live = kk < kc && m < tile.n_out && grow[k0 + kk] >= 0;
+            sw[kk][m] = live ? wd[(size_t)tile.out_index[m] * K + k0 + kk] : 0.0;
+        }
+        __syncthreads();
+        for (int kk = 0; kk < MAC_KC; kk += MAC_U) {
+            if (kk >= kc) break;
+            ulonglong2 v[MAC_U];
 #pragma unroll
-        for (int m = 0; m < MAC_TM; m++) {
-            const double w = __ldg(wrow[m] + kk);
-            a0[m][0] = __fma_rn(w, x0, a0[m][0]);
-            a1[m][0] = __fma_rn(w, x1, a1[m][0]);
-            a0[m][1] = __fma_rn(w, y0, a0[m][1]);
-            a1[m][1] = __fma_rn(w, y1, a1[m][1]);
+            for (int u = 0; u < MAC_U; u++) v[u] = *reinterpret_cast<const ulonglong2 *>(sptr[kk + u] + w_off);
+#pragma unroll
+            for (int u = 0; u < MAC_U; u++) {
+                const double x0 = mac_u2d(v[u].x & 0x3ffffffULL), x1 = mac_u2d(v[u].x >> 26);
+                const double y0 = mac_u2d(v[u].y & 0x3ffffffULL), y1 = mac_u2d(v[u].y >> 26);
+#pragma unroll
+                for (int m = 0; m < MAC_TM; m++) {
+                    const double w = sw[kk + u][m];
+                    a0[m][0] = __fma_rn(w, x0, a0[m][0]);
+                    a1[m][0] = __fma_rn(w, x1, a1[m][0]);
+                    a0[m][1] = __fma_rn(w, y0, a0[m][1]);
+                    a1[m][1] = __fma_rn(w, y1, a1[m][1]);
+                }
+            }
         }
     }
+    if (!active) return;
     const DMod q = bc->q[l];
     const bool c0_first = bias && word < (size_t)k * N && (word & (N - 1)) == 0;
 #pragma unroll
