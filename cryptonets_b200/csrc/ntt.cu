@@ -12,6 +12,8 @@
 // written back is canonical, which is what makes the kernel bit-comparable with the CPU oracle.
 // Shared-memory layout: word i is stored at i ^ (((i>>4)&7)<<1) so that the unit-stride last pass (16 consecutive
 // words per thread, 16-byte accesses) and the strided passes (gap >= 16 words) are both bank-conflict free.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "fparith.cuh"
 
@@ -302,15 +304,75 @@ k_ntt_inverse(const u64 *src, const u64 *base_add, u64 *dst, const NttTab *__res
 // 6 DP ops for the modular product + 2 for the butterfly, no integer corrections at all: values stay centred and small
 // (|r| <= (0.5 + 1.5|a|/2^53) p) and the host schedules a re-centring pass only where the bound could reach 2^52.
 // The transform computed is the same function as the integer path (canonical output), so results are bit-identical.
+// twiddles with table index < TWC are served from a per-CTA shared-memory copy (loaded once, under the first data loads)
+constexpr int TWC = 512;
+__device__ __forceinline__ void load_twiddle_cache(double *twc, const double *tw, int tid, int nthreads) {
+    for (int i = tid; i < TWC; i += nthreads) twc[i] = __ldg(tw + i);
+}
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a thread moves its 16 consecutive words as four full 32-byte sectors
+__device__ __forceinline__ void ldg256(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) {
+    asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+__device__ __forceinline__ void stg256(u64 *p, u64 a, u64 b, u64 c, u64 d) {
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+// Shared-memory round trips are what keeps the FP64 pipe idle (tools/dp_pass_bench.cu: 96 % utilisation on registers, ~62 %
+// with an LDS/STS round trip every 3 stages), so the FP64 transform uses as few, as fat passes as the register file allows:
+// N=8192 is 5+4+4 stages (was 3+3+3+4), the first pass reads HBM directly, the last one writes HBM directly.
+// A pass over stages [S0, S0+R) is executed by "virtual threads": N/32 of them for R=5 (32 coefficients each), N/16 otherwise
+// (16 coefficients: one radix-16 group, or two adjacent columns of radix-8 / four of radix-4 with 16-byte accesses).
 template <int LOGN, int S0, int R, bool FROM_G, int PASS>
-__device__ __forceinline__ void fwd_pass_fp(double *sm, const FwdSrc &src, const NttTab &tb, int tid) {
-    constexpr int T = (1 << LOGN) / 16, G = 16 >> R, E = 1 << R, LG = LOGN - S0 - R;
+__device__ __forceinline__ void fwd_pass_fp(double *sm, const double *twc, const FwdSrc &src, const NttTab &tb, int vt) {
+    constexpr int E = 1 << R, LG = LOGN - S0 - R;
+    constexpr bool CACHED = (S0 + R) <= 9; // every twiddle index of this pass is below TWC
     const double p = tb.pd, pinv = tb.pinv;
     const bool rc = (tb.fwd_recenter >> PASS) & 1;
+    if constexpr (R <= 3) {
+        constexpr int T = (1 << LOGN) / 16, G = 16 >> R;
 #pragma unroll
-    for (int gg = 0; gg < G; gg++) {
-        const int gid = tid + gg * T;
-        const int c = gid & ((1 << LG) - 1), j = gid >> LG;
+        for (int gg = 0; gg < G / 2; gg++) {
+            const int gid = vt + gg * T;
+            const int c2 = gid & ((1 << (LG - 1)) - 1), j = gid >> (LG - 1);
+            const int base = (j << (LG + R)) + 2 * c2;
+            double x[E], y[E];
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                const int idx = base + (e << LG);
+                if constexpr (FROM_G) {
+                    x[e] = u2d(fwd_load(src, idx, tb.mod));
+                    y[e] = u2d(fwd_load(src, idx + 1, tb.mod));
+                } else {
+                    const double2 v = *reinterpret_cast<const double2 *>(sm + swz(idx));
+                    x[e] = v.x;
+                    y[e] = v.y;
+                }
+            }
+            if (rc) {
+#pragma unroll
+                for (int e = 0; e < E; e++) { x[e] = frecenter(x[e], p, pinv); y[e] = frecenter(y[e], p, pinv); }
+            }
+#pragma unroll
+            for (int u = 0; u < R; u++) {
+                const int h = E >> (u + 1);
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    if (e & h) continue;
+                    const int ti = (1 << (S0 + u)) + (j << u) + (e >> (R - u));
+                    const double w = CACHED ? twc[ti] : __ldg(tb.wd + ti);
+                    const double t0 = fmodmul(x[e + h], w, p, pinv), t1 = fmodmul(y[e + h], w, p, pinv);
+                    const double a0 = x[e], a1 = y[e];
+                    x[e] = __dadd_rn(a0, t0);
+                    x[e + h] = __dsub_rn(a0, t0);
+                    y[e] = __dadd_rn(a1, t1);
+                    y[e + h] = __dsub_rn(a1, t1);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < E; e++) *reinterpret_cast<double2 *>(sm + swz(base + (e << LG))) = make_double2(x[e], y[e]);
+        }
+    } else {
+        const int c = vt & ((1 << LG) - 1), j = vt >> LG;
         const int base = (j << (LG + R)) + c;
         double x[E];
 #pragma unroll
@@ -325,7 +387,8 @@ __device__ __forceinline__ void fwd_pass_fp(double *sm, const FwdSrc &src, const
 #pragma unroll
             for (int e = 0; e < E; e++) {
                 if (e & h) continue;
-                const double w = __ldg(tb.wd + ((1 << (S0 + u)) + (j << u) + (e >> (R - u))));
+                const int ti = (1 << (S0 + u)) + (j << u) + (e >> (R - u));
+                const double w = CACHED ? twc[ti] : __ldg(tb.wd + ti);
                 const double t = fmodmul(x[e + h], w, p, pinv);
                 const double a = x[e];
                 x[e] = __dadd_rn(a, t);
@@ -336,13 +399,14 @@ __device__ __forceinline__ void fwd_pass_fp(double *sm, const FwdSrc &src, const
         for (int e = 0; e < E; e++) sm[swz(base + (e << LG))] = x[e];
     }
 }
+// Last forward pass: stages [LOGN-4, LOGN) on 16 consecutive words; canonical result goes straight to HBM.
 template <int LOGN, int PASS>
-__device__ __forceinline__ void fwd_last_fp(double *sm, const NttTab &tb, int tid) {
+__device__ __forceinline__ void fwd_last_fp(const double *sm, u64 *dst, const NttTab &tb, int j) {
     constexpr int S0 = LOGN - 4;
     const double p = tb.pd, pinv = tb.pinv;
     const bool rc = (tb.fwd_recenter >> PASS) & 1;
-    double2 *smv = reinterpret_cast<double2 *>(sm);
-    const int j = tid, xr = j & 7;
+    const double2 *smv = reinterpret_cast<const double2 *>(sm);
+    const int xr = j & 7;
     double x[16];
 #pragma unroll
     for (int ch = 0; ch < 8; ch++) {
@@ -354,53 +418,87 @@ __device__ __forceinline__ void fwd_last_fp(double *sm, const NttTab &tb, int ti
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = frecenter(x[e], p, pinv);
     }
+    // twiddles of this pass: 1 + 2 + 4 + 8 consecutive doubles per thread, fetched as 16-byte loads up front
+    double tw[15];
+    tw[0] = __ldg(tb.wd + ((1 << S0) + j));
+    {
+        const double2 a = __ldg(reinterpret_cast<const double2 *>(tb.wd + ((1 << (S0 + 1)) + (j << 1))));
+        tw[1] = a.x; tw[2] = a.y;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const double2 b = __ldg(reinterpret_cast<const double2 *>(tb.wd + ((1 << (S0 + 2)) + (j << 2) + 2 * i)));
+            tw[3 + 2 * i] = b.x; tw[4 + 2 * i] = b.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const double2 c = __ldg(reinterpret_cast<const double2 *>(tb.wd + ((1 << (S0 + 3)) + (j << 3) + 2 * i)));
+            tw[7 + 2 * i] = c.x; tw[8 + 2 * i] = c.y;
+        }
+    }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
         const int h = 8 >> u;
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             if (e & h) continue;
-            const double w = __ldg(tb.wd + ((1 << (S0 + u)) + (j << u) + (e >> (4 - u))));
+            const double w = tw[(1 << u) - 1 + (e >> (4 - u))];
             const double t = fmodmul(x[e + h], w, p, pinv);
             const double a = x[e];
             x[e] = __dadd_rn(a, t);
             x[e + h] = __dsub_rn(a, t);
         }
     }
-    ulonglong2 *smu = reinterpret_cast<ulonglong2 *>(sm);
+    u64 *o = dst + 16 * j;
 #pragma unroll
-    for (int ch = 0; ch < 8; ch++)
-        smu[j * 8 + (ch ^ xr)] = make_ulonglong2(d2u(fcanon(x[2 * ch], p, pinv)), d2u(fcanon(x[2 * ch + 1], p, pinv)));
+    for (int g = 0; g < 4; g++)
+        stg256(o + 4 * g, fcanon_u(x[4 * g], p, pinv), fcanon_u(x[4 * g + 1], p, pinv), fcanon_u(x[4 * g + 2], p, pinv), fcanon_u(x[4 * g + 3], p, pinv));
 }
+
+#define CNHE_VTN(COUNT, stmt) _Pragma("unroll") for (int vt = tid; vt < (COUNT); vt += TR) { stmt; }
+__host__ __device__ constexpr int fp_threads(int logn) { return logn >= 13 ? (1 << logn) / 32 : (1 << logn) / 16; }
+__host__ __device__ constexpr int fp_min_blocks(int logn) { return logn >= 14 ? 1 : (logn == 13 ? 2 : 3); }
+
+// Ask L2 for the polynomial that the CTA taking this one's place will read (CTAs are dispatched in blockIdx order, so that
+// is about `resident` blocks ahead): its first-pass loads then hit L2 instead of waiting on HBM with the FP64 pipe idle.
 template <int LOGN>
-__device__ __forceinline__ void fwd_body_fp(double *sm, const FwdSrc &src, const NttTab &tb, int tid) {
-    if constexpr (LOGN == 10) {
-        fwd_pass_fp<10, 0, 2, true, 0>(sm, src, tb, tid); __syncthreads();
-        fwd_pass_fp<10, 2, 4, false, 1>(sm, src, tb, tid); __syncthreads();
-        fwd_last_fp<10, 2>(sm, tb, tid);
-    } else if constexpr (LOGN == 11) {
-        fwd_pass_fp<11, 0, 3, true, 0>(sm, src, tb, tid); __syncthreads();
-        fwd_pass_fp<11, 3, 4, false, 1>(sm, src, tb, tid); __syncthreads();
-        fwd_last_fp<11, 2>(sm, tb, tid);
-    } else if constexpr (LOGN == 12) {
-        fwd_pass_fp<12, 0, 4, true, 0>(sm, src, tb, tid); __syncthreads();
-        fwd_pass_fp<12, 4, 4, false, 1>(sm, src, tb, tid); __syncthreads();
-        fwd_last_fp<12, 2>(sm, tb, tid);
-    } else if constexpr (LOGN == 13) {
-        fwd_pass_fp<13, 0, 3, true, 0>(sm, src, tb, tid); __syncthreads();
-        fwd_pass_fp<13, 3, 3, false, 1>(sm, src, tb, tid); __syncthreads();
-        fwd_pass_fp<13, 6, 3, false, 2>(sm, src, tb, tid); __syncthreads();
-        fwd_last_fp<13, 3>(sm, tb, tid);
-    } else {
-        fwd_pass_fp<14, 0, 3, true, 0>(sm, src, tb, tid); __syncthreads();
-        fwd_pass_fp<14, 3, 3, false, 1>(sm, src, tb, tid); __syncthreads();
-        fwd_pass_fp<14, 6, 4, false, 2>(sm, src, tb, tid); __syncthreads();
-        fwd_last_fp<14, 3>(sm, tb, tid);
+__device__ __forceinline__ void prefetch_next_poly(const u64 *src_base, int b, int n_polys, int tid) {
+    constexpr int N = 1 << LOGN, TR = fp_threads(LOGN);
+    const int ahead = b + 148 * fp_min_blocks(LOGN);
+    if (ahead < n_polys) {
+        const char *p = reinterpret_cast<const char *>(src_base + (size_t)ahead * N);
+        for (int i = tid * 128; i < N * 8; i += TR * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i));
     }
-    __syncthreads();
 }
 template <int LOGN>
-__global__ void __launch_bounds__((1 << LOGN) / 16, min_blocks(LOGN))
+__device__ __forceinline__ void fwd_body_fp(double *sm, const FwdSrc &src, u64 *dst, const NttTab &tb, int tid) {
+    constexpr int N = 1 << LOGN, TR = fp_threads(LOGN);
+    double *twc = sm + N;
+    load_twiddle_cache(twc, tb.wd, tid, TR);
+    __syncthreads();
+    if constexpr (LOGN == 10) {
+        CNHE_VTN(N / 16, (fwd_pass_fp<10, 0, 2, true, 0>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_pass_fp<10, 2, 4, false, 1>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_last_fp<10, 2>(sm, dst, tb, vt)));
+    } else if constexpr (LOGN == 11) {
+        CNHE_VTN(N / 16, (fwd_pass_fp<11, 0, 3, true, 0>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_pass_fp<11, 3, 4, false, 1>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_last_fp<11, 2>(sm, dst, tb, vt)));
+    } else if constexpr (LOGN == 12) {
+        CNHE_VTN(N / 16, (fwd_pass_fp<12, 0, 4, true, 0>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_pass_fp<12, 4, 4, false, 1>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_last_fp<12, 2>(sm, dst, tb, vt)));
+    } else if constexpr (LOGN == 13) {
+        CNHE_VTN(N / 32, (fwd_pass_fp<13, 0, 5, true, 0>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_pass_fp<13, 5, 4, false, 1>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_last_fp<13, 2>(sm, dst, tb, vt)));
+    } else {
+        CNHE_VTN(N / 32, (fwd_pass_fp<14, 0, 5, true, 0>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 32, (fwd_pass_fp<14, 5, 5, false, 1>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_last_fp<14, 2>(sm, dst, tb, vt)));
+    }
+}
+template <int LOGN>
+__global__ void __launch_bounds__(fp_threads(LOGN), fp_min_blocks(LOGN))
 k_ntt_forward_fp(const u64 *src, u64 *dst, const NttTab *__restrict__ tabs, int mod_base, int mod_count) {
     extern __shared__ __align__(16) u64 sm[];
     constexpr int N = 1 << LOGN;
@@ -409,11 +507,11 @@ k_ntt_forward_fp(const u64 *src, u64 *dst, const NttTab *__restrict__ tabs, int 
     FwdSrc fs;
     fs.src = src + (size_t)b * N;
     fs.digit = false; fs.need_reduce = false; fs.shift = 0; fs.mask = 0;
-    fwd_body_fp<LOGN>(reinterpret_cast<double *>(sm), fs, tb, tid);
-    smem_to_global<LOGN>(sm, dst + (size_t)b * N, tid);
+    prefetch_next_poly<LOGN>(src, b, gridDim.x, tid);
+    fwd_body_fp<LOGN>(reinterpret_cast<double *>(sm), fs, dst + (size_t)b * N, tb, tid);
 }
 template <int LOGN>
-__global__ void __launch_bounds__((1 << LOGN) / 16, min_blocks(LOGN))
+__global__ void __launch_bounds__(fp_threads(LOGN), fp_min_blocks(LOGN))
 k_ntt_forward_digits_fp(const u64 *target, u64 *dst, const NttTab *__restrict__ tabs, int k, DigitMap dm) {
     extern __shared__ __align__(16) u64 sm[];
     constexpr int N = 1 << LOGN;
@@ -426,25 +524,42 @@ k_ntt_forward_digits_fp(const u64 *target, u64 *dst, const NttTab *__restrict__ 
     fs.shift = dm.shift[d];
     fs.mask = dm.mask;
     fs.need_reduce = dm.mask >= tb.mod.p;
-    fwd_body_fp<LOGN>(reinterpret_cast<double *>(sm), fs, tb, tid);
-    smem_to_global<LOGN>(sm, dst + (size_t)b * N, tid);
+    fwd_body_fp<LOGN>(reinterpret_cast<double *>(sm), fs, dst + (size_t)b * N, tb, tid);
 }
 
-// ---- inverse, FP64
+// ---- inverse, FP64: first pass reads 16 consecutive words per virtual thread straight from HBM (256-bit loads)
 template <int LOGN>
-__device__ __forceinline__ void inv_first_fp(u64 *smraw, const NttTab &tb, int tid) {
+__device__ __forceinline__ void inv_first_fp(double *sm, const u64 *src, const NttTab &tb, int j) {
     constexpr int N = 1 << LOGN;
     const double p = tb.pd, pinv = tb.pinv;
-    ulonglong2 *smu = reinterpret_cast<ulonglong2 *>(smraw);
-    double2 *smv = reinterpret_cast<double2 *>(smraw);
-    const int j = tid, xr = j & 7;
-    const u64 half = tb.mod.p >> 1;
+    double2 *smv = reinterpret_cast<double2 *>(sm);
+    const int xr = j & 7;
     double x[16];
 #pragma unroll
-    for (int ch = 0; ch < 8; ch++) { // centred load: |x| <= p/2
-        ulonglong2 v = smu[j * 8 + (ch ^ xr)];
-        x[2 * ch] = v.x > half ? __dsub_rn(u2d(v.x), p) : u2d(v.x);
-        x[2 * ch + 1] = v.y > half ? __dsub_rn(u2d(v.y), p) : u2d(v.y);
+    for (int g = 0; g < 4; g++) {
+        u64 v0, v1, v2, v3;
+        ldg256(src + 16 * j + 4 * g, v0, v1, v2, v3);
+        x[4 * g] = u2d(v0);
+        x[4 * g + 1] = u2d(v1);
+        x[4 * g + 2] = u2d(v2);
+        x[4 * g + 3] = u2d(v3);
+    }
+    // stage u uses 8 >> u consecutive inverse twiddles: 8 + 4 + 2 + 1 doubles per thread, 16-byte loads
+    double tw[15];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double2 a = __ldg(reinterpret_cast<const double2 *>(tb.iwd + ((N >> 1) + (j << 3) + 2 * i)));
+        tw[2 * i] = a.x; tw[2 * i + 1] = a.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const double2 a = __ldg(reinterpret_cast<const double2 *>(tb.iwd + ((N >> 2) + (j << 2) + 2 * i)));
+        tw[8 + 2 * i] = a.x; tw[9 + 2 * i] = a.y;
+    }
+    {
+        const double2 a = __ldg(reinterpret_cast<const double2 *>(tb.iwd + ((N >> 3) + (j << 1))));
+        tw[12] = a.x; tw[13] = a.y;
+        tw[14] = __ldg(tb.iwd + ((N >> 4) + j));
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
@@ -453,24 +568,82 @@ __device__ __forceinline__ void inv_first_fp(u64 *smraw, const NttTab &tb, int t
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             if (e & h) continue;
-            const double w = __ldg(tb.iwd + ((N >> (u + 1)) + (j << (3 - u)) + (e >> (u + 1))));
+            const double w = tw[(16 - (16 >> u)) + (e >> (u + 1))];
             const double a = x[e], bq = x[e + h];
-            const double sum = __dadd_rn(a, bq);
-            x[e] = rc ? frecenter(sum, p, pinv) : sum;
+            x[e] = __dadd_rn(a, bq);
             x[e + h] = fmodmul(__dsub_rn(a, bq), w, p, pinv);
+        }
+        if (rc) { // uniform branch: the host schedules a re-centring of the sums on very few stages
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                if (!(e & h)) x[e] = frecenter(x[e], p, pinv);
         }
     }
 #pragma unroll
     for (int ch = 0; ch < 8; ch++) smv[j * 8 + (ch ^ xr)] = make_double2(x[2 * ch], x[2 * ch + 1]);
 }
-template <int LOGN, int V0, int R, bool LAST, int PASS>
-__device__ __forceinline__ void inv_pass_fp(double *sm, u64 *dst, const u64 *base_add, const NttTab &tb, int tid) {
-    constexpr int N = 1 << LOGN, T = N / 16, G = 16 >> R, E = 1 << R;
+template <int LOGN, int V0, int R, bool LAST>
+__device__ __forceinline__ void inv_pass_fp(double *sm, const double *twc, u64 *dst, const u64 *base_add, const NttTab &tb, int vt) {
+    constexpr int N = 1 << LOGN, E = 1 << R;
+    constexpr bool CACHED = (N >> V0) <= TWC; // stage v reads indices [N>>(v+1), N>>v)
     const double p = tb.pd, pinv = tb.pinv;
+    auto finish = [&](double v, int idx) {
+        double r = fmodmul(v, tb.inv_n_d, p, pinv); // |v| < 2^52 (host-checked); r in (-1.3p, 1.3p)
+        r = r < 0.0 ? __dadd_rn(r, p) : r;
+        r = r < 0.0 ? __dadd_rn(r, p) : r;
+        r = r >= p ? __dsub_rn(r, p) : r;
+        u64 o = d2u(r);
+        if (base_add) o = addmod(o, base_add[idx], tb.mod.p);
+        return o;
+    };
+    if constexpr (R <= 3) {
+        constexpr int T = N / 16, G = 16 >> R;
 #pragma unroll
-    for (int gg = 0; gg < G; gg++) {
-        const int gid = tid + gg * T;
-        const int c = gid & ((1 << V0) - 1), j = gid >> V0;
+        for (int gg = 0; gg < G / 2; gg++) {
+            const int gid = vt + gg * T;
+            const int c2 = gid & ((1 << (V0 - 1)) - 1), j = gid >> (V0 - 1);
+            const int base = (j << (V0 + R)) + 2 * c2;
+            double x[E], y[E];
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                const double2 v = *reinterpret_cast<const double2 *>(sm + swz(base + (e << V0)));
+                x[e] = v.x;
+                y[e] = v.y;
+            }
+#pragma unroll
+            for (int u = 0; u < R; u++) {
+                const int h = 1 << u;
+                const bool rc = (tb.inv_recenter >> (V0 + u)) & 1;
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    if (e & h) continue;
+                    const int ti = (N >> (V0 + u + 1)) + (j << (R - 1 - u)) + (e >> (u + 1));
+                    const double w = CACHED ? twc[ti] : __ldg(tb.iwd + ti);
+                    const double a0 = x[e], b0 = x[e + h], a1 = y[e], b1 = y[e + h];
+                    x[e] = __dadd_rn(a0, b0);
+                    y[e] = __dadd_rn(a1, b1);
+                    x[e + h] = fmodmul(__dsub_rn(a0, b0), w, p, pinv);
+                    y[e + h] = fmodmul(__dsub_rn(a1, b1), w, p, pinv);
+                }
+                if (rc) {
+#pragma unroll
+                    for (int e = 0; e < E; e++)
+                        if (!(e & h)) { x[e] = frecenter(x[e], p, pinv); y[e] = frecenter(y[e], p, pinv); }
+                }
+            }
+            if constexpr (LAST) {
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const int idx = base + (e << V0);
+                    *reinterpret_cast<ulonglong2 *>(dst + idx) = make_ulonglong2(finish(x[e], idx), finish(y[e], idx + 1));
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; e++) *reinterpret_cast<double2 *>(sm + swz(base + (e << V0))) = make_double2(x[e], y[e]);
+            }
+        }
+    } else {
+        const int c = vt & ((1 << V0) - 1), j = vt >> V0;
         const int base = (j << (V0 + R)) + c;
         double x[E];
 #pragma unroll
@@ -478,28 +651,27 @@ __device__ __forceinline__ void inv_pass_fp(double *sm, u64 *dst, const u64 *bas
 #pragma unroll
         for (int u = 0; u < R; u++) {
             const int h = 1 << u;
-            const bool rc = (tb.inv_recenter >> (V0 + u)) & 1; // re-centre the sums of stage V0+u (host-scheduled)
+            const bool rc = (tb.inv_recenter >> (V0 + u)) & 1;
 #pragma unroll
             for (int e = 0; e < E; e++) {
                 if (e & h) continue;
-                const double w = __ldg(tb.iwd + ((N >> (V0 + u + 1)) + (j << (R - 1 - u)) + (e >> (u + 1))));
+                const int ti = (N >> (V0 + u + 1)) + (j << (R - 1 - u)) + (e >> (u + 1));
+                const double w = CACHED ? twc[ti] : __ldg(tb.iwd + ti);
                 const double a = x[e], bq = x[e + h];
-                const double sum = __dadd_rn(a, bq);
-                x[e] = rc ? frecenter(sum, p, pinv) : sum;
+                x[e] = __dadd_rn(a, bq);
                 x[e + h] = fmodmul(__dsub_rn(a, bq), w, p, pinv);
+            }
+            if (rc) {
+#pragma unroll
+                for (int e = 0; e < E; e++)
+                    if (!(e & h)) x[e] = frecenter(x[e], p, pinv);
             }
         }
         if constexpr (LAST) {
 #pragma unroll
             for (int e = 0; e < E; e++) {
-                double r = fmodmul(x[e], tb.inv_n_d, p, pinv); // |x| < 2^52 (host-checked); r in (-1.3p, 1.3p)
-                r = r < 0.0 ? __dadd_rn(r, p) : r;
-                r = r < 0.0 ? __dadd_rn(r, p) : r;
-                r = r >= p ? __dsub_rn(r, p) : r;
-                u64 v = d2u(r);
                 const int idx = base + (e << V0);
-                if (base_add) v = addmod(v, base_add[idx], tb.mod.p);
-                dst[idx] = v;
+                dst[idx] = finish(x[e], idx);
             }
         } else {
 #pragma unroll
@@ -508,42 +680,42 @@ __device__ __forceinline__ void inv_pass_fp(double *sm, u64 *dst, const u64 *bas
     }
 }
 template <int LOGN>
-__global__ void __launch_bounds__((1 << LOGN) / 16, min_blocks(LOGN))
+__global__ void __launch_bounds__(fp_threads(LOGN), fp_min_blocks(LOGN))
 k_ntt_inverse_fp(const u64 *src, const u64 *base_add, u64 *dst, const NttTab *__restrict__ tabs, int mod_base, int mod_count) {
-    extern __shared__ __align__(16) u64 sm[];
-    constexpr int N = 1 << LOGN;
+    extern __shared__ __align__(16) u64 smraw[];
+    constexpr int N = 1 << LOGN, TR = fp_threads(LOGN);
     const int b = blockIdx.x, tid = threadIdx.x;
     const NttTab tb = tabs[mod_base + b % mod_count];
-    global_to_smem<LOGN>(sm, src + (size_t)b * N, tid);
-    __syncthreads();
-    inv_first_fp<LOGN>(sm, tb, tid);
-    __syncthreads();
-    double *smd = reinterpret_cast<double *>(sm);
+    double *sm = reinterpret_cast<double *>(smraw);
+    double *twc = sm + N;
+    load_twiddle_cache(twc, tb.iwd, tid, TR);
+    prefetch_next_poly<LOGN>(src, b, gridDim.x, tid);
+    const u64 *s = src + (size_t)b * N;
     u64 *d = dst + (size_t)b * N;
     const u64 *ba = base_add ? base_add + (size_t)b * N : nullptr;
+    CNHE_VTN(N / 16, (inv_first_fp<LOGN>(sm, s, tb, vt)));
+    __syncthreads();
     if constexpr (LOGN == 10) {
-        inv_pass_fp<10, 4, 4, false, 1>(smd, d, ba, tb, tid); __syncthreads();
-        inv_pass_fp<10, 8, 2, true, 2>(smd, d, ba, tb, tid);
+        CNHE_VTN(N / 16, (inv_pass_fp<10, 4, 4, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (inv_pass_fp<10, 8, 2, true>(sm, twc, d, ba, tb, vt)));
     } else if constexpr (LOGN == 11) {
-        inv_pass_fp<11, 4, 4, false, 1>(smd, d, ba, tb, tid); __syncthreads();
-        inv_pass_fp<11, 8, 3, true, 2>(smd, d, ba, tb, tid);
+        CNHE_VTN(N / 16, (inv_pass_fp<11, 4, 4, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (inv_pass_fp<11, 8, 3, true>(sm, twc, d, ba, tb, vt)));
     } else if constexpr (LOGN == 12) {
-        inv_pass_fp<12, 4, 4, false, 1>(smd, d, ba, tb, tid); __syncthreads();
-        inv_pass_fp<12, 8, 4, true, 2>(smd, d, ba, tb, tid);
+        CNHE_VTN(N / 16, (inv_pass_fp<12, 4, 4, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (inv_pass_fp<12, 8, 4, true>(sm, twc, d, ba, tb, vt)));
     } else if constexpr (LOGN == 13) {
-        inv_pass_fp<13, 4, 3, false, 1>(smd, d, ba, tb, tid); __syncthreads();
-        inv_pass_fp<13, 7, 3, false, 2>(smd, d, ba, tb, tid); __syncthreads();
-        inv_pass_fp<13, 10, 3, true, 3>(smd, d, ba, tb, tid);
+        CNHE_VTN(N / 16, (inv_pass_fp<13, 4, 4, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 32, (inv_pass_fp<13, 8, 5, true>(sm, twc, d, ba, tb, vt)));
     } else {
-        inv_pass_fp<14, 4, 4, false, 1>(smd, d, ba, tb, tid); __syncthreads();
-        inv_pass_fp<14, 8, 3, false, 2>(smd, d, ba, tb, tid); __syncthreads();
-        inv_pass_fp<14, 11, 3, true, 3>(smd, d, ba, tb, tid);
+        CNHE_VTN(N / 32, (inv_pass_fp<14, 4, 5, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 32, (inv_pass_fp<14, 9, 5, true>(sm, twc, d, ba, tb, vt)));
     }
 }
 
 int ntt_pass_radices(int logn, int inverse, int *r) {
-    static const int F[5][4] = {{2, 4, 4, 0}, {3, 4, 4, 0}, {4, 4, 4, 0}, {3, 3, 3, 4}, {3, 3, 4, 4}};
-    static const int I[5][4] = {{4, 4, 2, 0}, {4, 4, 3, 0}, {4, 4, 4, 0}, {4, 3, 3, 3}, {4, 4, 3, 3}};
+    static const int F[5][4] = {{2, 4, 4, 0}, {3, 4, 4, 0}, {4, 4, 4, 0}, {5, 4, 4, 0}, {5, 5, 4, 0}};
+    static const int I[5][4] = {{4, 4, 2, 0}, {4, 4, 3, 0}, {4, 4, 4, 0}, {4, 4, 5, 0}, {4, 5, 5, 0}};
     if (logn < 10 || logn > 14) return 0;
     int n = 0;
     for (int i = 0; i < 4; i++) {
@@ -554,7 +726,7 @@ int ntt_pass_radices(int logn, int inverse, int *r) {
 }
 
 // ---------------------------------------------------------------- launchers
-int ntt_kernel_smem_bytes(int logn) { return (1 << logn) * 8; }
+int ntt_kernel_smem_bytes(int logn) { return (1 << logn) * 8 + TWC * 8; } // polynomial + twiddle cache (FP64 path)
 
 template <class K>
 static cudaError_t prep(K kern, int logn) {
@@ -578,7 +750,7 @@ cudaError_t launch_ntt_forward(const u64 *src, u64 *dst, int n_polys, int logn, 
         CNHE_DISPATCH_LOGN(logn, {
             cudaError_t e = prep(k_ntt_forward_fp<L>, L);
             if (e != cudaSuccess) return e;
-            k_ntt_forward_fp<L><<<n_polys, (1 << L) / 16, ntt_kernel_smem_bytes(L), s>>>(src, dst, tabs, mod_base, mod_count);
+            k_ntt_forward_fp<L><<<n_polys, fp_threads(L), ntt_kernel_smem_bytes(L), s>>>(src, dst, tabs, mod_base, mod_count);
         });
         return cudaGetLastError();
     }
@@ -596,7 +768,7 @@ cudaError_t launch_ntt_forward_digits(const u64 *target, u64 *dst, int n_ct, int
         CNHE_DISPATCH_LOGN(logn, {
             cudaError_t e = prep(k_ntt_forward_digits_fp<L>, L);
             if (e != cudaSuccess) return e;
-            k_ntt_forward_digits_fp<L><<<n_ct * dm.D * k, (1 << L) / 16, ntt_kernel_smem_bytes(L), s>>>(target, dst, tabs, k, dm);
+            k_ntt_forward_digits_fp<L><<<n_ct * dm.D * k, fp_threads(L), ntt_kernel_smem_bytes(L), s>>>(target, dst, tabs, k, dm);
         });
         return cudaGetLastError();
     }
@@ -614,7 +786,7 @@ static cudaError_t launch_inv(const u64 *src, const u64 *base, u64 *dst, int n_p
         CNHE_DISPATCH_LOGN(logn, {
             cudaError_t e = prep(k_ntt_inverse_fp<L>, L);
             if (e != cudaSuccess) return e;
-            k_ntt_inverse_fp<L><<<n_polys, (1 << L) / 16, ntt_kernel_smem_bytes(L), s>>>(src, base, dst, tabs, mod_base, mod_count);
+            k_ntt_inverse_fp<L><<<n_polys, fp_threads(L), ntt_kernel_smem_bytes(L), s>>>(src, base, dst, tabs, mod_base, mod_count);
         });
         return cudaGetLastError();
     }

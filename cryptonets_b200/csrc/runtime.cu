@@ -159,8 +159,8 @@ static void fp_schedule(NttTab &tb, int logN, bool force_int) {
             if (i == 0) return;  // the first pass reads straight from global memory: no re-centring slot
         }
     }
-    // inverse: centred input (0.5); sums double every stage; bit v re-centres the sums produced by stage v
-    A = 0.5;
+    // inverse: canonical input (1.0); sums double every stage; bit v re-centres the sums produced by stage v
+    A = 1.0;
     for (int v = 0; v < logN; v++) {
         if (2 * A >= L) return;
         const double y = c(2 * A);
