@@ -296,7 +296,8 @@ def run_b200(args):
         fam = prof["ntt_forward"]
         # dominant family: forward NTT (incl. the digit-decomposing variant of relinearisation)
         achieved = fam["bytes"] / (fam["ms"] * 1e-3) / 1e9 if fam["ms"] > 0 else 0.0
-        roof = {"bound": "hbm", "kernel": "k_ntt_forward / k_ntt_forward_digits (N=8192)", "achieved": achieved, "peak": peaks["hbm_gbs"],
+        roof = {"bound": "hbm", "kernel": "k_ntt_forward_fp / k_ntt_forward_digits_fp (N=8192), 16*N algorithmic bytes per transform", "achieved": achieved,
+                "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)",
                 "traffic": None, "launches_timed": fam["launches"], "share_of_step": fam["ms"] / ms if ms else None,
                 "families_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}

@@ -495,7 +495,7 @@ void op_key_switch(Context &c, const u64 *target, int n, const u64 *key, const D
         u64 *digits = c.ws_alloc((size_t)m * dm.D * k * N);
         u64 *acc = c.ws_alloc((size_t)m * 2 * k * N);
         {
-            PROF(0, 8.0 * N * ((double)m * dm.D * k + (double)m * k));
+            PROF(0, 16.0 * N * (double)m * dm.D * k); // 16N bytes per transform (8N digit source read + 8N written)
             c.check(launch_ntt_forward_digits(target + (size_t)c0 * k * N, digits, m, k, dm, c.logN, c.d_tabs, fp_range(c, 0, k), c.stream), "ntt_forward_digits");
         }
         {
