@@ -652,6 +652,23 @@ void op_multiply_plain_dense(Context &c, int ch, const u64 *ct, int n, const u64
     c.check(launch_dyadic_bcast(tmp, lifted, tmp, n, 2, 1, plain_per_ct ? 1 : 0, k, c.logN, c.d_bc, c.stream), "dyadic");
     c.check(launch_ntt_inverse(tmp, out, n * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_inverse");
 }
+// one ciphertext times n dense plaintexts: out[i] = ct * plain[i]   (row-major matrix x vector: every row against the same input)
+void op_multiply_plain_dense_bcast(Context &c, int ch, const u64 *ct, const u64 *plains, int n, u64 *out) {
+    const int k = c.k;
+    const size_t N = c.N;
+    u64 *ctn = c.ws_alloc((size_t)2 * k * N);
+    c.check(launch_ntt_forward(ct, ctn, 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
+    for (int c0 = 0; c0 < n; c0 += 4 * c.chunk) {
+        WsScope scope(c);
+        const int m = std::min(4 * c.chunk, n - c0);
+        u64 *lifted = c.ws_alloc((size_t)m * k * N);
+        c.check(launch_plain_lift(plains + (size_t)c0 * N, lifted, m, (int)N, k, c.logN, c.d_bc, c.ch[ch].pc, c.stream), "plain_lift");
+        c.check(launch_ntt_forward(lifted, lifted, m * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
+        u64 *dst = out + (size_t)c0 * 2 * k * N;
+        c.check(launch_dyadic_bcast(ctn, lifted, dst, m, 2, 0, 1, k, c.logN, c.d_bc, c.stream), "dyadic");
+        c.check(launch_ntt_inverse(dst, dst, m * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_inverse");
+    }
+}
 void op_encode(Context &c, int ch, const u64 *values, int n, int count, u64 *plain) {
     c.check(launch_encode_scatter(values, plain, n, count, c.d_index_map, c.logN, c.stream), "encode_scatter");
     c.check(launch_ntt_inverse(plain, plain, n, c.logN, c.d_tabs, c.ch[ch].mod_id, 1, fp_range(c, c.ch[ch].mod_id, 1), c.stream), "ntt_inverse(t)");

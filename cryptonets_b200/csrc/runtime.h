@@ -131,6 +131,7 @@ void op_rotate_columns(Context &c, int ch, const u64 *in, int n, u64 *out);
 u64 galois_elt_from_step(const Context &c, int steps);
 // dense plaintext (coefficient form mod t, [n or 1][N]) times ciphertexts [n][2kN]
 void op_multiply_plain_dense(Context &c, int ch, const u64 *ct, int n, const u64 *plain, bool plain_per_ct, u64 *out);
+void op_multiply_plain_dense_bcast(Context &c, int ch, const u64 *ct, const u64 *plains, int n, u64 *out);
 // values [n][count] (mod t, device) -> plain [n][N] coefficient form
 void op_encode(Context &c, int ch, const u64 *values, int n, int count, u64 *plain);
 void op_decode(Context &c, int ch, const u64 *plain, int n, u64 *values);

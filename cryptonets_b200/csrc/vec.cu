@@ -1141,6 +1141,78 @@ extern "C" int cnhe_mat_mul_colmajor_sparse(cnhe_ctx *h, const cnhe_vec *const *
     }
     API_END
 }
+// Batched SumAllSlots (AtomicSealBfvVector.cs:888-955) on n single-block ciphertexts in place: the same rotate-and-add ladder,
+// one key-switch wave per step for all n.
+static uint64_t sum_slots_batched(Context &c, int ch, u64 *cts, int n, uint64_t length) {
+    const size_t N = c.N, words = (size_t)n * c.ct_words();
+    uint64_t len = length;
+    u64 *tmp = c.ws_alloc(words);
+    if (len >= N / 2) {
+        op_rotate_columns(c, ch, cts, n, tmp);
+        c.check(launch_ct_add(cts, tmp, cts, words, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+        len = N / 2;
+    }
+    for (uint64_t steps = 1; steps < len; steps *= 2) {
+        op_rotate_rows(c, ch, cts, n, -(int)steps, tmp);
+        c.check(launch_ct_add(cts, tmp, cts, words, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+    }
+    return len;
+}
+// RowMajor matrix x vector (EncryptedSealBfvMatrix.cs:79-120): per row DotProduct(row, v) = PointwiseMultiply + SumAllSlots, then
+// GenerateSparseOfArray, or (ForceDenseFormat) a one-hot mask per row and the sum of all rows.  All rows go through each stage
+// together instead of one DotProduct per row.
+extern "C" int cnhe_mat_mul_rowmajor(cnhe_ctx *h, const cnhe_vec *const *rows, int n_rows, const cnhe_vec *v, int force_dense, cnhe_vec **out) {
+    API_BEGIN(h)
+    if (n_rows < 1) fail("empty matrix");
+    same_ctx(c, v);
+    if (!v->enc) fail("at least one parameter has to be encrypted");
+    if (v->format != CNHE_DENSE) fail("Expecting dense vector format");
+    if (v->blocks != 1) fail("row-major multiplication expects a single-block vector");
+    for (int r = 0; r < n_rows; r++) {
+        same_ctx(c, rows[r]);
+        if (rows[r]->enc) fail("encrypted rows are not supported by the batched row-major product");
+        if (rows[r]->dim != v->dim) fail("Dimensions do not match");
+        if (rows[r]->format != v->format) fail("Format mismatch");
+        if (rows[r]->scale != rows[0]->scale) fail("row scales differ");
+    }
+    const size_t N = c.N, ctw = c.ct_words();
+    if (force_dense && (size_t)n_rows > N) fail("column out of range");
+    const int out_blocks = force_dense ? 1 : n_rows;
+    cnhe_vec *o = new_vec(c, (uint64_t)n_rows, v->scale * rows[0]->scale, force_dense ? CNHE_DENSE : CNHE_SPARSE, true, out_blocks);
+    std::unique_ptr<cnhe_vec> guard(o);
+    alloc_channels(o);
+    const int RC = 1024; // rows per wave
+    for (int ch = 0; ch < c.P; ch++) {
+        bool first = true;
+        for (int r0 = 0; r0 < n_rows; r0 += RC) {
+            WsScope scope(c);
+            const int m = std::min(RC, n_rows - r0);
+            u64 *plains = c.ws_alloc((size_t)m * N);
+            for (int i = 0; i < m; i++)
+                CNHE_CUDA(cudaMemcpyAsync(plains + (size_t)i * N, rows[r0 + i]->ptr(ch), N * 8, cudaMemcpyDeviceToDevice, c.stream));
+            u64 *prod = force_dense ? c.ws_alloc((size_t)m * ctw) : o->block(ch, r0);
+            op_multiply_plain_dense_bcast(c, ch, v->ptr(ch), plains, m, prod);
+            sum_slots_batched(c, ch, prod, m, CNHE_ALL_SLOTS);
+            if (force_dense) {
+                // one-hot masks for columns r0..r0+m (EncryptedSealBfvMatrix.cs:96, AtomicSealBfvVector.cs:936-945)
+                std::vector<u64> onehot((size_t)m * N, 0);
+                for (int i = 0; i < m; i++) onehot[(size_t)i * N + (r0 + i)] = 1;
+                u64 *dv = c.ws_alloc((size_t)m * N), *masks = c.ws_alloc((size_t)m * N);
+                CNHE_CUDA(cudaMemcpyAsync(dv, onehot.data(), onehot.size() * 8, cudaMemcpyHostToDevice, c.stream));
+                op_encode(c, ch, dv, m, (int)N, masks);
+                op_multiply_plain_dense(c, ch, prod, m, masks, true, prod);
+                std::vector<const u64 *> terms;
+                if (!first) terms.push_back(o->ptr(ch));
+                for (int i = 0; i < m; i++) terms.push_back(prod + (size_t)i * ctw);
+                c.check(launch_ct_add_many(upload_ptrs(c, terms), (int)terms.size(), o->ptr(ch), ctw, c.k, c.logN, c.d_bc, c.stream), "ct_add_many");
+                c.sync();
+            }
+            first = false;
+        }
+    }
+    *out = guard.release();
+    API_END
+}
 // SquareActivation over a whole matrix: every column PointwiseMultiply'd with itself in one wave per channel
 extern "C" int cnhe_layer_square(cnhe_ctx *h, const cnhe_vec *const *in, int n, cnhe_vec **out) {
     API_BEGIN(h)

@@ -304,6 +304,11 @@ class Engine:
         check(self.L.cnhe_mat_mul_colmajor_sparse(self.h, _vec_array(cols), len(cols), sparse.h, C.byref(out)))
         return Vec(self, out)
 
+    def mat_mul_rowmajor(self, rows, v, force_dense=False):
+        out = VECP()
+        check(self.L.cnhe_mat_mul_rowmajor(self.h, _vec_array(rows), len(rows), v.h, int(force_dense), C.byref(out)))
+        return Vec(self, out)
+
     def layer_conv_dense(self, inputs, gather, weights, bias, M, K):
         g = None
         if gather is not None:

@@ -91,6 +91,7 @@ class B200BfvMatrix:
         self.vectors = [factory.CopyVector(v) for v in vectors] if CopyVectors else list(vectors)
         self.Format = fmt
         self.DataDisposedExternaly = False
+        self.Batched = True  # False replays the reference's per-row call sequence
 
     eng = property(lambda s: s.factory.engine)
     RowCount = property(lambda s: len(s.vectors) if s.Format == EMatrixFormat.RowMajor else s.vectors[0].Dim)
@@ -121,6 +122,9 @@ class B200BfvMatrix:
             if ForceDenseFormat:
                 raise Exception("Forcing dense format is available only in RowMajor mode")
             return B200BfvVector(f, self.eng.mat_mul_colmajor_sparse([c.vec for c in self.vectors], v.vec))
+        if self.Batched and v.IsEncrypted and not self.IsEncrypted and v.vec.blocks == 1:
+            # all rows through each stage together (same ciphertexts as the per-row loop below)
+            return B200BfvVector(f, self.eng.mat_mul_rowmajor([r.vec for r in self.vectors], v.vec, ForceDenseFormat))
         if not ForceDenseFormat:  # EncryptedSealBfvMatrix.cs:79-89
             tmp = [row.DotProduct(v, env) for row in self.vectors]
             res = B200BfvVector(f, self.eng.generate_sparse_of_array([t.vec for t in tmp]))

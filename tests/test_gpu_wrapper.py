@@ -157,3 +157,25 @@ def test_errors_mirror_reference(F, objs):
         objs["enc1"].Add(short)
     with pytest.raises(CnheError, match="multiplying two plaintexts"):
         objs["plain2"].PointwiseMultiply(objs["plain2"])
+
+
+@pytest.mark.parametrize("force_dense", [False, True])
+def test_rowmajor_matrix_vector_batched_equals_per_row(F, force_dense):
+    """LLDenseLayer's product (EncryptedSealBfvMatrix.cs:79-120): the batched device routine must give the very ciphertexts of the
+    reference's per-row DotProduct loop, and the plain result."""
+    from cryptonets_b200.interfaces import EMatrixFormat, EVectorFormat
+    rng = np.random.default_rng(8)
+    W = rng.integers(-9, 10, (7, 40)).astype(np.float64)
+    x = rng.integers(-20, 21, 40).astype(np.float64)
+    M = F.GetPlainMatrix(W, EMatrixFormat.RowMajor, 4)
+    v = F.GetEncryptedVector(x, EVectorFormat.dense, 2)
+    M.Batched = True
+    a = M.Mul(v, None, force_dense)
+    M.Batched = False
+    b = M.Mul(v, None, force_dense)
+    assert a.Dim == b.Dim == 7 and a.Scale == b.Scale == 8 and a.Format == b.Format
+    got = a.Decrypt()
+    assert np.array_equal(got[:7], W @ x)
+    for ch in range(F.engine.P):
+        for blk in range(a.vec.blocks):
+            assert np.array_equal(a.vec.export_raw(ch, blk), b.vec.export_raw(ch, blk)), (ch, blk)
