@@ -34,7 +34,20 @@ u64 *Context::ws_alloc(size_t words) {
     return b->p;
 }
 void Context::ws_reserve(size_t) {}
-void Context::sync() { CNHE_CUDA(cudaStreamSynchronize(stream)); }
+void Context::sync() {
+    for (cudaStream_t s : streams) CNHE_CUDA(cudaStreamSynchronize(s));
+}
+void Context::join_streams() {
+    for (size_t i = 1; i < streams.size(); i++) {
+        CNHE_CUDA(cudaEventRecord(ev_join, streams[i]));
+        CNHE_CUDA(cudaStreamWaitEvent(streams[0], ev_join, 0));
+    }
+}
+void Context::fork_streams() {
+    if (streams.size() < 2) return;
+    CNHE_CUDA(cudaEventRecord(ev_join, streams[0]));
+    for (size_t i = 1; i < streams.size(); i++) CNHE_CUDA(cudaStreamWaitEvent(streams[i], ev_join, 0));
+}
 void Context::h2d(void *dst, const void *src, size_t bytes) {
     if (!bytes) return;
     if (!stage_buf) {
@@ -46,8 +59,8 @@ void Context::h2d(void *dst, const void *src, size_t bytes) {
         return;
     }
     const size_t need = (bytes + 255) & ~(size_t)255;
-    if (stage_off + need > stage_size) { // wrap: everything queued so far must have left the ring
-        CNHE_CUDA(cudaStreamSynchronize(stream));
+    if (stage_off + need > stage_size) { // wrap: everything queued so far (on any channel stream) must have left the ring
+        sync();
         stage_off = 0;
     }
     memcpy(stage_buf + stage_off, src, bytes);
@@ -73,7 +86,7 @@ void Context::prof_end() {
 }
 void Context::prof_flush() {
     if (prof_recs.empty()) return;
-    CNHE_CUDA(cudaStreamSynchronize(stream));
+    sync();
     for (auto &r : prof_recs) {
         float ms = 0;
         CNHE_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
@@ -93,7 +106,7 @@ struct ProfScope {
 #define PROF(family, bytes) ProfScope prof_scope_##__LINE__(c, family, bytes)
 Context::~Context() {
     cudaSetDevice(device);
-    if (stream) cudaStreamSynchronize(stream);
+    for (cudaStream_t s : streams) cudaStreamSynchronize(s);
     g_temps.m.erase(this);
     ch.clear();
     if (d_bc) cudaFree(d_bc);
@@ -106,7 +119,8 @@ Context::~Context() {
     if (stage_buf) cudaFreeHost(stage_buf);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
-    if (stream) cudaStreamDestroy(stream);
+    if (ev_join) cudaEventDestroy(ev_join);
+    for (cudaStream_t s : streams) cudaStreamDestroy(s);
 }
 // free the temporaries of the previous operation (stream ordered, so kernels still in flight keep their memory)
 void ws_release_all(Context &c) {
@@ -257,7 +271,10 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
     const int kb = (int)c.bsk.size();
     const u64 M_SK = c.bsk[kb - 1];
     c.kb = kb;
-    CNHE_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.streams.resize(P);
+    for (int i = 0; i < P; i++) CNHE_CUDA(cudaStreamCreateWithFlags(&c.streams[i], cudaStreamNonBlocking));
+    c.stream = c.streams[0];
+    CNHE_CUDA(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     CNHE_CUDA(cudaEventCreate(&c.ev0));
     CNHE_CUDA(cudaEventCreate(&c.ev1));
     {
@@ -849,6 +866,7 @@ void keys_generate(Context &c, u64 seed) {
     const int k = c.k;
     const size_t N = c.N, kN = (size_t)k * N;
     for (int ci = 0; ci < c.P; ci++) {
+        c.set_channel(ci);
         Channel &ch = c.ch[ci];
         ch.seed = seed + (u64)ci;
         ch.nonce = 1;

@@ -25,7 +25,15 @@ void cuda_check(cudaError_t e, const char *what);
 struct DevBuf {
     u64 *p = nullptr;
     size_t words = 0;
+    // one CUDA stream per plaintext-modulus channel (the reference runs one Task per prime, EncryptedSealBfvVector.cs:225-236):
+    // channels are independent until decryption, so their kernels and host<->device copies overlap.  `stream` is the stream of the
+    // channel currently being issued (set_channel).
+    std::vector<cudaStream_t> streams;
     cudaStream_t stream = nullptr;
+    bool multi_stream = true;
+    void set_channel(int ch) { stream = streams[multi_stream ? ch : 0]; }
+    void join_streams(); // stream 0 waits for the tail of every other stream
+    void fork_streams(); // every other stream waits for the tail of stream 0
     DevBuf(size_t w, cudaStream_t s);
     ~DevBuf();
     DevBuf(const DevBuf &) = delete;
@@ -61,8 +69,16 @@ struct Context {
     DigitMap dm_relin, dm_galois;
     std::vector<u64> galois_elts;
     std::vector<Channel> ch;
+    // one CUDA stream per plaintext-modulus channel (the reference runs one Task per prime, EncryptedSealBfvVector.cs:225-236):
+    // channels are independent until decryption, so their kernels and host<->device copies overlap.  `stream` is the stream of the
+    // channel currently being issued (set_channel).
+    std::vector<cudaStream_t> streams;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool multi_stream = true;
+    void set_channel(int ch) { stream = streams[multi_stream ? ch : 0]; }
+    void join_streams(); // stream 0 waits for the tail of every other stream
+    void fork_streams(); // every other stream waits for the tail of stream 0
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_join = nullptr;
     std::recursive_mutex mu;
     int chunk = 128;
     uint64_t launches = 0;

@@ -52,6 +52,7 @@ extern "C" const char *cnhe_version(void) { return "cnhe-b200 0.1 (sm_100a)"; }
     try {                                                                                                              \
         std::lock_guard<std::recursive_mutex> lock(c.mu);                                                              \
         CNHE_CUDA(cudaSetDevice(c.device));                                                                            \
+        c.set_channel(0);                                                                                              \
         ws_release_all(c);
 #define API_END                                                                                                        \
     }                                                                                                                  \
@@ -127,6 +128,9 @@ extern "C" int cnhe_context_set_option(cnhe_ctx *h, const char *name, int64_t va
         CNHE_CUDA(cudaMemcpyAsync(c.d_bc, &c.h_bc, sizeof(BehzConst), cudaMemcpyHostToDevice, c.stream));
         CNHE_CUDA(cudaMemcpyAsync(c.d_bf, &c.h_bf, sizeof(BehzConstF), cudaMemcpyHostToDevice, c.stream));
         c.sync();
+    } else if (n == "multi_stream") {
+        c.sync();
+        c.multi_stream = value != 0;
     } else if (n == "chunk") {
         if (value < 1 || value > 4096) fail("chunk must be in [1,4096]");
         c.chunk = (int)value;
@@ -212,26 +216,36 @@ static std::vector<const u64 *> strided(uint64_t base, int n, size_t words) {
 }
 extern "C" int cnhe_raw_multiply(cnhe_ctx *h, int channel, uint64_t a, uint64_t b, int n, uint64_t out3) {
     API_BEGIN(h)
+    if (channel < 0 || channel >= c.P) fail("bad channel");
+    c.set_channel(channel);
     op_multiply(c, channel, strided(a, n, c.ct_words()), strided(b, n, c.ct_words()), (u64 *)out3);
     API_END
 }
 extern "C" int cnhe_raw_relinearize(cnhe_ctx *h, int channel, uint64_t in3, int n, uint64_t out2) {
     API_BEGIN(h)
+    if (channel < 0 || channel >= c.P) fail("bad channel");
+    c.set_channel(channel);
     op_relinearize(c, channel, (const u64 *)in3, n, (u64 *)out2);
     API_END
 }
 extern "C" int cnhe_raw_multiply_relin(cnhe_ctx *h, int channel, uint64_t a, uint64_t b, int n, uint64_t out2) {
     API_BEGIN(h)
+    if (channel < 0 || channel >= c.P) fail("bad channel");
+    c.set_channel(channel);
     op_multiply_relin(c, channel, strided(a, n, c.ct_words()), strided(b, n, c.ct_words()), (u64 *)out2);
     API_END
 }
 extern "C" int cnhe_raw_apply_galois(cnhe_ctx *h, int channel, uint64_t in, int n, uint64_t elt, uint64_t out) {
     API_BEGIN(h)
+    if (channel < 0 || channel >= c.P) fail("bad channel");
+    c.set_channel(channel);
     op_apply_galois(c, channel, (const u64 *)in, n, elt, (u64 *)out);
     API_END
 }
 extern "C" int cnhe_raw_rotate_rows(cnhe_ctx *h, int channel, uint64_t in, int n, int steps, uint64_t out) {
     API_BEGIN(h)
+    if (channel < 0 || channel >= c.P) fail("bad channel");
+    c.set_channel(channel);
     op_rotate_rows(c, channel, (const u64 *)in, n, steps, (u64 *)out);
     API_END
 }
@@ -244,6 +258,8 @@ extern "C" int cnhe_raw_behz_lift(cnhe_ctx *h, uint64_t in_cts, int n, uint64_t 
 }
 extern "C" int cnhe_raw_behz_floor(cnhe_ctx *h, int channel, uint64_t d, int n, uint64_t out3) {
     API_BEGIN(h)
+    if (channel < 0 || channel >= c.P) fail("bad channel");
+    c.set_channel(channel);
     if (c.fp_elementwise) c.check(launch_behz_floor_fp((const u64 *)d, (u64 *)out3, n, c.ch[channel].t, c.logN, c.d_bf, c.stream), "behz_floor_fp");
     else c.check(launch_behz_floor((const u64 *)d, (u64 *)out3, n, c.ch[channel].t, c.logN, c.d_bc, c.stream), "behz_floor");
     API_END
@@ -271,7 +287,14 @@ extern "C" int cnhe_prof_collect(cnhe_ctx *h, int family, double *total_ms, uint
 }
 extern "C" int cnhe_raw_event_timing(cnhe_ctx *h, int start) {
     API_BEGIN(h)
-    CNHE_CUDA(cudaEventRecord(start ? c.ev0 : c.ev1, c.stream));
+    if (start) {
+        c.join_streams();
+        CNHE_CUDA(cudaEventRecord(c.ev0, c.streams[0]));
+        c.fork_streams();
+    } else {
+        c.join_streams();
+        CNHE_CUDA(cudaEventRecord(c.ev1, c.streams[0]));
+    }
     API_END
 }
 extern "C" int cnhe_raw_elapsed_ms(cnhe_ctx *h, float *ms) {
@@ -295,7 +318,10 @@ static cnhe_vec *new_vec(Context &c, uint64_t dim, double scale, int format, boo
     return v;
 }
 static void alloc_channels(cnhe_vec *v) {
-    for (int ch = 0; ch < v->ctx->P; ch++) v->buf[ch] = v->ctx->alloc((size_t)v->blocks * v->unit());
+    for (int ch = 0; ch < v->ctx->P; ch++) {
+        v->ctx->set_channel(ch);
+        v->buf[ch] = v->ctx->alloc((size_t)v->blocks * v->unit());
+    }
 }
 static cnhe_vec *alias_of(const cnhe_vec *a) { return new cnhe_vec(*a); } // shares the reference-counted buffers
 static void same_ctx(Context &c, const cnhe_vec *v) {
@@ -353,6 +379,7 @@ static cnhe_vec *make_vector(Context &c, const double *v, uint64_t dim, double s
     if (format == CNHE_SPARSE && !encrypt) {
         out->scalars = split;
         for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
             out->buf[ch] = c.alloc(dim);
             CNHE_CUDA(cudaMemcpyAsync(out->buf[ch]->p, split[ch].data(), dim * 8, cudaMemcpyHostToDevice, c.stream));
         }
@@ -361,6 +388,7 @@ static cnhe_vec *make_vector(Context &c, const double *v, uint64_t dim, double s
     }
     alloc_channels(out);
     for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         if (format == CNHE_DENSE) {
             // BatchEncoder.Encode per N-slot chunk (AtomicSealBfvVector.cs:1123-1133); a short last chunk is zero padded
             std::vector<u64> padded((size_t)blocks * N, 0);
@@ -413,6 +441,7 @@ extern "C" int cnhe_vecs_encrypt(cnhe_ctx *h, const double *v, int n, uint64_t d
     split_values(c, v, (uint64_t)n * dim, scale, split);
     std::vector<BufRef> big(c.P);
     for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         std::vector<u64> padded((size_t)n * bl * N, 0);
         for (int i = 0; i < n; i++) memcpy(&padded[(size_t)i * bl * N], &split[ch][(size_t)i * dim], dim * 8);
         u64 *dvals = c.ws_alloc(padded.size()), *plain = c.ws_alloc(padded.size());
@@ -426,6 +455,7 @@ extern "C" int cnhe_vecs_encrypt(cnhe_ctx *h, const double *v, int n, uint64_t d
     for (int i = 0; i < n; i++) {
         cnhe_vec *o = new_vec(c, dim, scale, CNHE_DENSE, true, bl);
         for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
             o->buf[ch] = big[ch];
             o->off[ch] = (size_t)i * bl * c.ct_words();
         }
@@ -465,7 +495,10 @@ extern "C" int cnhe_vec_decrypt(cnhe_ctx *h, const cnhe_vec *v, double *out, uin
     same_ctx(c, v);
     if (cap < v->dim) fail("destination too small");
     std::vector<std::vector<u64>> split(c.P);
-    for (int ch = 0; ch < c.P; ch++) decrypt_channel(c, v, ch, split[ch]);
+    for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
+        decrypt_channel(c, v, ch, split[ch]);
+    }
     join_values(c, split, v->dim, v->scale, out);
     API_END
 }
@@ -475,7 +508,10 @@ extern "C" int cnhe_vecs_decrypt(cnhe_ctx *h, const cnhe_vec *const *vecs, int n
         same_ctx(c, vecs[i]);
         if (vecs[i]->dim != dim) fail("all vectors must have the same dimension");
         std::vector<std::vector<u64>> split(c.P);
-        for (int ch = 0; ch < c.P; ch++) decrypt_channel(c, vecs[i], ch, split[ch]);
+        for (int ch = 0; ch < c.P; ch++) {
+            c.set_channel(ch);
+            decrypt_channel(c, vecs[i], ch, split[ch]);
+        }
         join_values(c, split, dim, vecs[i]->scale, out + (size_t)i * dim);
     }
     API_END
@@ -485,6 +521,7 @@ extern "C" int cnhe_vec_copy(cnhe_ctx *h, const cnhe_vec *v, cnhe_vec **out) {
     same_ctx(c, v);
     cnhe_vec *o = new cnhe_vec(*v);
     for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         const size_t words = (size_t)v->blocks * v->unit();
         o->buf[ch] = c.alloc(words);
         o->off[ch] = 0;
@@ -550,12 +587,17 @@ extern "C" int cnhe_vecs_import_raw(cnhe_ctx *h, const uint64_t *src, int n, int
     const size_t per = (size_t)blocks * c.ct_words(), words = (size_t)n * per;
     std::vector<BufRef> big(c.P);
     for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         big[ch] = c.alloc(words);
+        // one channel after the other over PCIe, each on its own stream: channel 0 computes while channel 1 is still uploading
+        if (ch > 0) CNHE_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
         CNHE_CUDA(cudaMemcpyAsync(big[ch]->p, src + (size_t)ch * words, words * 8, cudaMemcpyHostToDevice, c.stream));
+        if (ch + 1 < c.P) CNHE_CUDA(cudaEventRecord(c.ev_join, c.stream));
     }
     for (int i = 0; i < n; i++) {
         cnhe_vec *o = new_vec(c, dim, scale, format, true, blocks);
-        for (int ch = 0; ch < c.P; ch++) { o->buf[ch] = big[ch]; o->off[ch] = (size_t)i * per; }
+        for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch); o->buf[ch] = big[ch]; o->off[ch] = (size_t)i * per; }
         out[i] = o;
     }
     API_END
@@ -607,6 +649,7 @@ static cnhe_vec *addsub(Context &c, const cnhe_vec *a, const cnhe_vec *b, bool s
     cnhe_vec *o = new_vec(c, a->dim, a->scale, a->format, true, e->blocks);
     alloc_channels(o);
     for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         if (p->enc) {
             c.check(launch_ct_add(a->ptr(ch), b->ptr(ch), o->ptr(ch), (size_t)e->blocks * c.ct_words(), c.k, c.logN, c.d_bc, sub, c.stream), "ct_add");
         } else {
@@ -643,6 +686,7 @@ static cnhe_vec *mul_sparse_dim_one(Context &c, const cnhe_vec *self, const cnhe
     std::unique_ptr<cnhe_vec> guard(o);
     alloc_channels(o);
     for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         if (self->enc && s->enc) {
             op_multiply_relin(c, ch, block_ptrs(s, ch, self->blocks), block_ptrs(self, ch), o->ptr(ch));
         } else if (self->enc) { // constant plaintext times every block
@@ -674,6 +718,7 @@ static cnhe_vec *pointwise_multiply(Context &c, const cnhe_vec *a, const cnhe_ve
     alloc_channels(o);
     const cnhe_vec *e = a->enc ? a : b, *p = a->enc ? b : a;
     for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         if (a->enc && b->enc) {
             op_multiply_relin(c, ch, block_ptrs(b, ch), block_ptrs(a, ch), o->ptr(ch)); // evaluator.Multiply(ev.encData[i], encData[i])
         } else if (p->format == CNHE_DENSE) {
@@ -706,6 +751,7 @@ static cnhe_vec *sum_all_slots(Context &c, const cnhe_vec *a, uint64_t length, i
     std::unique_ptr<cnhe_vec> guard(o);
     alloc_channels(o);
     for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         len = length;
         u64 *sum = o->ptr(ch);
         if (a->blocks > 1) { // AddMany over the blocks
@@ -762,7 +808,10 @@ extern "C" int cnhe_vec_rotate(cnhe_ctx *h, const cnhe_vec *a, int amount, cnhe_
     cnhe_vec *o = new_vec(c, a->dim, a->scale, CNHE_DENSE, true, 1);
     std::unique_ptr<cnhe_vec> guard(o);
     alloc_channels(o);
-    for (int ch = 0; ch < c.P; ch++) op_rotate_rows(c, ch, a->ptr(ch), 1, amount, o->ptr(ch));
+    for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
+        op_rotate_rows(c, ch, a->ptr(ch), 1, amount, o->ptr(ch));
+    }
     *out = guard.release();
     API_END
 }
@@ -780,6 +829,7 @@ extern "C" int cnhe_vec_duplicate(cnhe_ctx *h, const cnhe_vec *a, uint64_t count
     std::unique_ptr<cnhe_vec> guard(o);
     alloc_channels(o);
     for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         u64 *res = o->ptr(ch), *rotator = c.ws_alloc(ctw), *tmp = c.ws_alloc(ctw);
         CNHE_CUDA(cudaMemcpyAsync(res, a->ptr(ch), ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
         const u64 *rot_src = a->ptr(ch);
@@ -825,6 +875,7 @@ extern "C" int cnhe_vec_permute(cnhe_ctx *h, const cnhe_vec *a, const cnhe_vec *
     std::unique_ptr<cnhe_vec> guard(o);
     alloc_channels(o);
     for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         u64 *t = c.ws_alloc(ctw), *r = c.ws_alloc(ctw);
         bool have = false;
         for (int i = 0; i < n; i++) {
@@ -935,7 +986,10 @@ static cnhe_vec *interleave(Context &c, const cnhe_vec *const *vecs, int n, int 
     cnhe_vec *o = new_vec(c, vv[0]->dim, vv[0]->scale, CNHE_DENSE, true, out_blocks);
     std::unique_ptr<cnhe_vec> guard(o);
     alloc_channels(o);
-    for (int ch = 0; ch < c.P; ch++) interleave_channel(c, ch, vv, shift, out_blocks, o->ptr(ch));
+    for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
+        interleave_channel(c, ch, vv, shift, out_blocks, o->ptr(ch));
+    }
     return guard.release();
 }
 extern "C" int cnhe_vecs_interleave(cnhe_ctx *h, const cnhe_vec *const *vecs, int n, int shift, cnhe_vec **out) {
@@ -1026,10 +1080,15 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
     c.h2d(d_gather, grows.data(), grows.size() * sizeof(int));
     MacTile *d_tiles = (MacTile *)c.ws_alloc((tiles.size() * sizeof(MacTile) + 7) / 8);
     c.h2d(d_tiles, tiles.data(), tiles.size() * sizeof(MacTile));
+    c.fork_streams(); // the gather table and the tiles were uploaded on channel 0's stream and are read by every channel
     const double out_scale = in[0]->scale * weights[0]->scale;
     std::vector<BufRef> big(c.P);
-    for (int ch = 0; ch < c.P; ch++) big[ch] = c.alloc((size_t)M * bl * c.ct_words());
     for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
+        big[ch] = c.alloc((size_t)M * bl * c.ct_words());
+    }
+    for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         std::vector<const u64 *> wp(M);
         for (int m = 0; m < M; m++) wp[m] = weights[m]->ptr(ch);
         const u64 *const *d_w = upload_ptrs(c, wp);
@@ -1086,6 +1145,7 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
     for (int m = 0; m < M; m++) {
         cnhe_vec *o = new_vec(c, in[0]->dim, out_scale, CNHE_DENSE, true, bl);
         for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
             o->buf[ch] = big[ch];
             o->off[ch] = (size_t)m * bl * c.ct_words();
         }
@@ -1116,6 +1176,7 @@ extern "C" int cnhe_mat_mul_colmajor_sparse(cnhe_ctx *h, const cnhe_vec *const *
         std::unique_ptr<cnhe_vec> guard(o);
         alloc_channels(o);
         for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
             u64 *prod = c.ws_alloc((size_t)K * bl * ctw);
             if (cols[0]->enc) { // both encrypted: Multiply + Relinearize per (k, block)
                 std::vector<const u64 *> a, b;
@@ -1183,6 +1244,7 @@ extern "C" int cnhe_mat_mul_rowmajor(cnhe_ctx *h, const cnhe_vec *const *rows, i
     alloc_channels(o);
     const int RC = 1024; // rows per wave
     for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         bool first = true;
         for (int r0 = 0; r0 < n_rows; r0 += RC) {
             WsScope scope(c);
@@ -1226,6 +1288,7 @@ extern "C" int cnhe_layer_square(cnhe_ctx *h, const cnhe_vec *const *in, int n, 
     const int total = first[n];
     std::vector<BufRef> big(c.P);
     for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         big[ch] = c.alloc((size_t)total * c.ct_words());
         std::vector<const u64 *> ptrs;
         for (int i = 0; i < n; i++)
@@ -1235,6 +1298,7 @@ extern "C" int cnhe_layer_square(cnhe_ctx *h, const cnhe_vec *const *in, int n, 
     for (int i = 0; i < n; i++) {
         cnhe_vec *o = new_vec(c, in[i]->dim, in[i]->scale * in[i]->scale, in[i]->format, true, in[i]->blocks);
         for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
             o->buf[ch] = big[ch];
             o->off[ch] = (size_t)first[i] * c.ct_words();
         }

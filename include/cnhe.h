@@ -60,7 +60,8 @@ int cnhe_context_plain_moduli(const cnhe_ctx *, uint64_t *out_P);
  * 0..k-1 coefficient primes, k..k+count-1 Bsk, k+count+c plaintext modulus c */
 int cnhe_context_bsk_moduli(const cnhe_ctx *, uint64_t *out, int *count);
 int cnhe_context_galois_elts(const cnhe_ctx *, uint64_t *out);
-/* options: "behz_centered_mtilde" (0/1), "chunk" (ciphertexts per multiply/key-switch wave) */
+/* options: "behz_centered_mtilde" (0/1), "chunk" (ciphertexts per multiply/key-switch wave), "multi_stream" (1: one CUDA
+ * stream per plaintext modulus, default; 0: everything on one stream) */
 int cnhe_context_set_option(cnhe_ctx *, const char *name, int64_t value);
 int cnhe_context_sync(cnhe_ctx *);
 /* EncryptedSealBfvEnvironment.GenerateEncryptionKeys ("EncryptedSealBfvVector.cs:92-102") -> KeyGenerator, RelinKeys(dbc),
