@@ -25,15 +25,7 @@ void cuda_check(cudaError_t e, const char *what);
 struct DevBuf {
     u64 *p = nullptr;
     size_t words = 0;
-    // one CUDA stream per plaintext-modulus channel (the reference runs one Task per prime, EncryptedSealBfvVector.cs:225-236):
-    // channels are independent until decryption, so their kernels and host<->device copies overlap.  `stream` is the stream of the
-    // channel currently being issued (set_channel).
-    std::vector<cudaStream_t> streams;
-    cudaStream_t stream = nullptr;
-    bool multi_stream = true;
-    void set_channel(int ch) { stream = streams[multi_stream ? ch : 0]; }
-    void join_streams(); // stream 0 waits for the tail of every other stream
-    void fork_streams(); // every other stream waits for the tail of stream 0
+    cudaStream_t stream = nullptr; // allocation (and release) stream: the channel the buffer belongs to
     DevBuf(size_t w, cudaStream_t s);
     ~DevBuf();
     DevBuf(const DevBuf &) = delete;

@@ -575,8 +575,10 @@ extern "C" int cnhe_vec_import_raw(cnhe_ctx *h, const uint64_t *src, int blocks,
     cnhe_vec *o = new_vec(c, dim, scale, format, true, blocks);
     alloc_channels(o);
     const size_t words = (size_t)blocks * c.ct_words();
-    for (int ch = 0; ch < c.P; ch++)
+    for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         CNHE_CUDA(cudaMemcpyAsync(o->ptr(ch), src + (size_t)ch * words, words * 8, cudaMemcpyHostToDevice, c.stream));
+    }
     c.sync();
     *out = o;
     API_END
@@ -611,8 +613,10 @@ extern "C" int cnhe_vecs_export_raw(cnhe_ctx *h, const cnhe_vec *const *vecs, in
     for (int i = 0; i < n; i++) {
         same_ctx(c, vecs[i]);
         if (!vecs[i]->enc || vecs[i]->blocks != blocks) fail("expecting encrypted vectors with equal block counts");
-        for (int ch = 0; ch < c.P; ch++)
+        for (int ch = 0; ch < c.P; ch++) {
+            c.set_channel(ch);
             CNHE_CUDA(cudaMemcpyAsync(dst + ((size_t)ch * n + i) * per, vecs[i]->ptr(ch), per * 8, cudaMemcpyDeviceToHost, c.stream));
+        }
     }
     c.sync();
     API_END
@@ -897,9 +901,11 @@ extern "C" int cnhe_vecs_generate_sparse_of_array(cnhe_ctx *h, const cnhe_vec *c
     for (int i = 0; i < n; i++) { same_ctx(c, vecs[i]); if (!vecs[i]->enc) fail("expecting encrypted vectors"); }
     cnhe_vec *o = new_vec(c, (uint64_t)n, vecs[0]->scale, CNHE_SPARSE, true, n);
     alloc_channels(o);
-    for (int ch = 0; ch < c.P; ch++)
+    for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
         for (int i = 0; i < n; i++)
             CNHE_CUDA(cudaMemcpyAsync(o->block(ch, i), vecs[i]->block(ch, 0), c.ct_words() * 8, cudaMemcpyDeviceToDevice, c.stream));
+    }
     *out = o;
     API_END
 }
@@ -1076,11 +1082,6 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
             }
         }
     }
-    int *d_gather = (int *)c.ws_alloc((grows.size() + 1) / 2 + 1);
-    c.h2d(d_gather, grows.data(), grows.size() * sizeof(int));
-    MacTile *d_tiles = (MacTile *)c.ws_alloc((tiles.size() * sizeof(MacTile) + 7) / 8);
-    c.h2d(d_tiles, tiles.data(), tiles.size() * sizeof(MacTile));
-    c.fork_streams(); // the gather table and the tiles were uploaded on channel 0's stream and are read by every channel
     const double out_scale = in[0]->scale * weights[0]->scale;
     std::vector<BufRef> big(c.P);
     for (int ch = 0; ch < c.P; ch++) {
@@ -1089,6 +1090,11 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
     }
     for (int ch = 0; ch < c.P; ch++) {
         c.set_channel(ch);
+        // every temporary lives on this channel's stream (stream-ordered frees must not overtake another channel's kernels)
+        int *d_gather = (int *)c.ws_alloc((grows.size() + 1) / 2 + 1);
+        c.h2d(d_gather, grows.data(), grows.size() * sizeof(int));
+        MacTile *d_tiles = (MacTile *)c.ws_alloc((tiles.size() * sizeof(MacTile) + 7) / 8);
+        c.h2d(d_tiles, tiles.data(), tiles.size() * sizeof(MacTile));
         std::vector<const u64 *> wp(M);
         for (int m = 0; m < M; m++) wp[m] = weights[m]->ptr(ch);
         const u64 *const *d_w = upload_ptrs(c, wp);
