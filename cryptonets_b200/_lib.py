@@ -35,6 +35,7 @@ _SIGS = {
     "cnhe_vecs_decrypt": [C.c_void_p, C.POINTER(VECP), i32, DBLP, u64],
     "cnhe_vec_copy": [C.c_void_p, VECP, C.POINTER(VECP)],
     "cnhe_vec_destroy": [VECP],
+    "cnhe_vecs_destroy": [C.POINTER(VECP), i32],
     "cnhe_vec_meta": [VECP, U64P, DBLP, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), U64P],
     "cnhe_vec_register_scale": [VECP, C.c_double],
     "cnhe_vec_register_dim": [VECP, u64],

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) k_behz_floor(const u64 *__restrict__ d, u
     }
 }
 
-// ---- key-switch inner product: acc{0,1}[c][l][x] = sum_d digits[c][d][l][x] * key[d][{0,1}][l][x]
+// ---- key-switch inner product: acc{0,1}[c][l][x] = sum_d digits[c][l][d][x] * key[d][{0,1}][l][x]
 __global__ void __launch_bounds__(256) k_ks_mac(const u64 *__restrict__ digits, const u64 *__restrict__ key, u64 *__restrict__ acc, int n, int D,
                                                int logn, const BehzConst *__restrict__ gbc) {
     __shared__ BehzConst bc;
@@ -158,9 +158,9 @@ __global__ void __launch_bounds__(256) k_ks_mac(const u64 *__restrict__ digits, 
     const int x = (int)(gid & (N - 1));
     const int l = (int)((gid >> logn) % k), c = (int)((gid >> logn) / k);
     const DMod m = bc.q[l];
-    const u64 *dg = digits + ((size_t)c * D * k + l) * N + x;
+    const u64 *dg = digits + ((size_t)c * k + l) * D * N + x;
     const u64 *k0 = key + (size_t)l * N + x;
-    const size_t dstride = (size_t)k * N, kstride = (size_t)2 * k * N;
+    const size_t dstride = (size_t)N, kpoly = (size_t)k * N, kstride = (size_t)2 * k * N;
     U128 a0 = {0, 0}, a1 = {0, 0};
     for (int d0 = 0; d0 < D; d0 += 8) { // at most 8 products of 62x62 bits between reductions
         U128 s0 = {0, 0}, s1 = {0, 0};
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) k_ks_mac(const u64 *__restrict__ digits, 
         for (int dd = d0; dd < dend; dd++) {
             const u64 v = dg[(size_t)dd * dstride];
             mac128(s0, v, __ldg(k0 + (size_t)dd * kstride));
-            mac128(s1, v, __ldg(k0 + (size_t)dd * kstride + dstride));
+            mac128(s1, v, __ldg(k0 + (size_t)dd * kstride + kpoly));
         }
         add128(a0, barrett128(s0, m));
         add128(a1, barrett128(s1, m));

@@ -5,24 +5,20 @@
 // 128-bit integer product (4 mul.hi.u64 + 6 mul.lo.u64, the slowest instructions on the B200 integer pipe).  Wherever SEAL's
 // algorithm depends on the *representative* of a residue (the fast base conversions sum [x c]_p * c' over the integers),
 // the canonical representative in [0,p) is formed first, exactly as in behz.cu.
+#include <cstdlib>
 #include "fparith.cuh"
 #include "kernels.h"
 
 namespace cnhe {
 
-__device__ __forceinline__ void load_consts_f(BehzConstF *dst, const BehzConstF *src) {
-    const int words = sizeof(BehzConstF) / 8;
-    const u64 *s = reinterpret_cast<const u64 *>(src);
-    u64 *d = reinterpret_cast<u64 *>(dst);
-    for (int i = threadIdx.x; i < words; i += blockDim.x) d[i] = s[i];
-    __syncthreads();
-}
-static_assert(sizeof(BehzConstF) % 8 == 0, "BehzConstF must be a whole number of words");
+// The conversion constants travel as a __grid_constant__ kernel parameter (3 KB, constant bank): with the loops over residues fully
+// unrolled every constant is an immediate c[bank][offset] operand of its DFMA -- no shared-memory copy, no LDS per product.
+static_assert(sizeof(BehzConstF) % 8 == 0 && sizeof(BehzConstF) <= 3584, "BehzConstF must fit the kernel parameter space");
 
+// LAZY (all kernels below): buffers exchanged with the NTT kernels hold lazy doubles (fparith.cuh) instead of canonical words
+template <bool LAZY>
 __global__ void __launch_bounds__(256) k_behz_lift_fp(const u64 *const *__restrict__ ct_ptrs, u64 *__restrict__ out, int n_polys, int logn,
-                                                     const BehzConstF *__restrict__ gf) {
-    __shared__ BehzConstF F;
-    load_consts_f(&F, gf);
+                                                     const __grid_constant__ BehzConstF F) {
     const int N = 1 << logn, k = F.k, kb = F.kb, kt = k + kb;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)n_polys << logn) return;
@@ -35,28 +31,31 @@ __global__ void __launch_bounds__(256) k_behz_lift_fp(const u64 *const *__restri
     for (int i = 0; i < KMAX; i++)
         if (i < k) {
             const u64 v = src[(size_t)i * N];
-            dst[(size_t)i * N] = v;
-            tmp[i] = fcanon(fmodmul(u2d(v), F.mtilde_inv_qhat_mod_q[i], F.qd[i], F.qinv[i]), F.qd[i], F.qinv[i]);
+            const double vd = u2d(v);
+            dst[(size_t)i * N] = LAZY ? lazy_bits(vd) : v;
+            tmp[i] = fcanon(fmodmul(vd, F.mtilde_inv_qhat_mod_q[i], F.qd[i], F.qinv[i]), F.qd[i], F.qinv[i]);
             sm += d2u(tmp[i]) * F.qhat_mod_mtilde[i];
         }
     sm &= 0xffffffffULL;
     const u64 r = ((1ULL << 32) - ((sm * F.inv_q_mod_mtilde) & 0xffffffffULL)) & 0xffffffffULL;
     double rr = u2d(r);
     if (F.centered_mtilde && r >= (1ULL << 31)) rr -= 4294967296.0;
-    for (int j = 0; j < kb; j++) {
+#pragma unroll
+    for (int j = 0; j < KBMAX; j++) {
+        if (j >= kb) break;
         const double p = F.bd[j], pinv = F.binv[j];
         double acc = fmodmul(rr, F.q_mod_bsk[j], p, pinv);
 #pragma unroll
         for (int i = 0; i < KMAX; i++)
             if (i < k) acc = __dadd_rn(acc, fmodmul(tmp[i], F.qhat_mod_bsk[j][i], p, pinv));
-        dst[(size_t)(k + j) * N] = fcanon_u(fmodmul(acc, F.inv_mtilde_mod_bsk[j], p, pinv), p, pinv);
+        const double r = fmodmul(acc, F.inv_mtilde_mod_bsk[j], p, pinv); // fresh product: |r| <= 0.51 p
+        dst[(size_t)(k + j) * N] = LAZY ? lazy_bits(r) : fsmall_u(r, F.b_u[j]);
     }
 }
 
+template <bool LAZY>
 __global__ void __launch_bounds__(256) k_behz_tensor_fp(const u64 *a, const u64 *b, u64 *__restrict__ d, int n, int logn,
-                                                       const BehzConstF *__restrict__ gf) {
-    __shared__ BehzConstF F;
-    load_consts_f(&F, gf);
+                                                       const __grid_constant__ BehzConstF F) {
     const int N = 1 << logn, k = F.k, kt = k + F.kb;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= ((size_t)n * kt) << logn) return;
@@ -64,7 +63,7 @@ __global__ void __launch_bounds__(256) k_behz_tensor_fp(const u64 *a, const u64 
     const int l = (int)((gid >> logn) % kt), c = (int)((gid >> logn) / kt);
     const double p = l < k ? F.qd[l] : F.bd[l - k], pinv = l < k ? F.qinv[l] : F.binv[l - k];
     const size_t in0 = ((size_t)(c * 2 + 0) * kt + l) * N + x, in1 = ((size_t)(c * 2 + 1) * kt + l) * N + x;
-    const double a0 = u2d(a[in0]), a1 = u2d(a[in1]);
+    const double a0 = LAZY ? ld_lazy(a + in0) : u2d(a[in0]), a1 = LAZY ? ld_lazy(a + in1) : u2d(a[in1]);
     double d0, d1, d2;
     if (a == b) {
         d0 = fmodmul(a0, a0, p, pinv);
@@ -72,21 +71,26 @@ __global__ void __launch_bounds__(256) k_behz_tensor_fp(const u64 *a, const u64 
         const double cross = fmodmul(a0, a1, p, pinv);
         d1 = __dadd_rn(cross, cross);
     } else {
-        const double b0 = u2d(b[in0]), b1 = u2d(b[in1]);
+        const double b0 = LAZY ? ld_lazy(b + in0) : u2d(b[in0]), b1 = LAZY ? ld_lazy(b + in1) : u2d(b[in1]);
         d0 = fmodmul(a0, b0, p, pinv);
         d2 = fmodmul(a1, b1, p, pinv);
         d1 = __dadd_rn(fmodmul(a0, b1, p, pinv), fmodmul(a1, b0, p, pinv));
     }
     const size_t o = ((size_t)(c * 3) * kt + l) * N + x;
-    d[o] = fcanon_u(d0, p, pinv);
-    d[o + (size_t)kt * N] = fcanon_u(d1, p, pinv);
-    d[o + (size_t)2 * kt * N] = fcanon_u(d2, p, pinv);
+    if (LAZY) { // |d0|, |d2| <= 0.51 p, |d1| <= 1.02 p: within the inverse transform's input bound (1.25 p)
+        d[o] = lazy_bits(d0);
+        d[o + (size_t)kt * N] = lazy_bits(d1);
+        d[o + (size_t)2 * kt * N] = lazy_bits(d2);
+    } else {
+        d[o] = fcanon_u(d0, p, pinv);
+        d[o + (size_t)kt * N] = fcanon_u(d1, p, pinv);
+        d[o + (size_t)2 * kt * N] = fcanon_u(d2, p, pinv);
+    }
 }
 
+template <bool LAZY>
 __global__ void __launch_bounds__(256) k_behz_floor_fp(const u64 *__restrict__ d, u64 *__restrict__ out, int n_polys, double t, int logn,
-                                                      const BehzConstF *__restrict__ gf) {
-    __shared__ BehzConstF F;
-    load_consts_f(&F, gf);
+                                                      const __grid_constant__ BehzConstF F) {
     const int N = 1 << logn, k = F.k, kb = F.kb, kt = k + kb, na = kb - 1;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)n_polys << logn) return;
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(256) k_behz_floor_fp(const u64 *__restrict__ d
     for (int i = 0; i < KMAX; i++)
         if (i < k) {
             const double p = F.qd[i], pinv = F.qinv[i];
-            const double v = fmodmul(u2d(src[(size_t)i * N]), t, p, pinv);
+            const double v = fmodmul(LAZY ? ld_lazy(src + (size_t)i * N) : u2d(src[(size_t)i * N]), t, p, pinv);
             tmp[i] = fcanon(fmodmul(v, F.inv_qhat_mod_q[i], p, pinv), p, pinv);
         }
 #pragma unroll
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(256) k_behz_floor_fp(const u64 *__restrict__ d
 #pragma unroll
             for (int i = 0; i < KMAX; i++)
                 if (i < k) conv = __dadd_rn(conv, fmodmul(tmp[i], F.qhat_mod_bsk[j][i], p, pinv));
-            const double xb = fmodmul(u2d(src[(size_t)(k + j) * N]), t, p, pinv);
+            const double xb = fmodmul(LAZY ? ld_lazy(src + (size_t)(k + j) * N) : u2d(src[(size_t)(k + j) * N]), t, p, pinv);
             fl[j] = fmodmul(frecenter(__dsub_rn(xb, conv), p, pinv), F.inv_q_mod_bsk[j], p, pinv);
         }
     const double pm = F.bd[na], pminv = F.binv[na];
@@ -120,10 +124,16 @@ __global__ void __launch_bounds__(256) k_behz_floor_fp(const u64 *__restrict__ d
             tmp[j] = fcanon(fmodmul(fl[j], F.inv_bhat_mod_b[j], F.bd[j], F.binv[j]), F.bd[j], F.binv[j]);
             am = __dadd_rn(am, fmodmul(tmp[j], F.bhat_mod_msk[j], pm, pminv));
         }
-    const double alpha = fcanon(fmodmul(frecenter(__dsub_rn(am, fl[na]), pm, pminv), F.inv_B_mod_msk, pm, pminv), pm, pminv);
+    double fl_sk = 0.0; // fl[na] without a runtime-indexed (local-memory) array access
+#pragma unroll
+    for (int j = 0; j < KBMAX; j++)
+        if (j == na) fl_sk = fl[j];
+    const double alpha = fcanon(fmodmul(frecenter(__dsub_rn(am, fl_sk), pm, pminv), F.inv_B_mod_msk, pm, pminv), pm, pminv);
     // centred alpha: alpha > m_sk/2 means alpha - m_sk (negative)
     const double alpha_c = alpha > F.msk_half ? __dsub_rn(alpha, pm) : alpha;
-    for (int i = 0; i < k; i++) {
+#pragma unroll
+    for (int i = 0; i < KMAX; i++) {
+        if (i >= k) break;
         const double p = F.qd[i], pinv = F.qinv[i];
         double v = 0.0;
 #pragma unroll
@@ -134,55 +144,85 @@ __global__ void __launch_bounds__(256) k_behz_floor_fp(const u64 *__restrict__ d
     }
 }
 
+// One thread: two adjacent coefficients of residue l of one ciphertext, walking the D digit transforms (adjacent polynomials in the
+// [c][l][d][N] layout) with 16-byte loads, UNR digits in flight: the kernel is bound by the digit stream out of HBM (8 MB per
+// ciphertext at N=8192, D=25), the key (16 MB per channel) is re-read out of L2 by every ciphertext.
+__device__ __forceinline__ ulonglong2 ldcs2(const u64 *p) { // streaming (evict-first): each digit word is read exactly once
+    ulonglong2 v;
+    asm volatile("ld.global.cs.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
+template <bool LAZY, int UNR>
 __global__ void __launch_bounds__(256) k_ks_mac_fp(const u64 *__restrict__ digits, const u64 *__restrict__ key, u64 *__restrict__ acc, int n, int D,
-                                                  int logn, const BehzConstF *__restrict__ gf) {
-    __shared__ BehzConstF F;
-    load_consts_f(&F, gf);
+                                                  int logn, const __grid_constant__ BehzConstF F) {
     const int N = 1 << logn, k = F.k;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= ((size_t)n * k) << logn) return;
-    const int x = (int)(gid & (N - 1));
-    const int l = (int)((gid >> logn) % k), c = (int)((gid >> logn) / k);
+    if (gid >= ((size_t)n * k) << (logn - 1)) return;
+    const int x = (int)(gid & (N / 2 - 1)) * 2;
+    const int l = (int)((gid >> (logn - 1)) % k), c = (int)((gid >> (logn - 1)) / k);
     const double p = F.qd[l], pinv = F.qinv[l];
-    const u64 *dg = digits + ((size_t)c * D * k + l) * N + x;
+    const size_t kpoly = (size_t)k * N, kstride = (size_t)2 * k * N;
+    const u64 *dg = digits + ((size_t)c * k + l) * D * N + x;
     const u64 *k0 = key + (size_t)l * N + x;
-    const size_t dstride = (size_t)k * N, kstride = (size_t)2 * k * N;
-    double a0 = 0.0, a1 = 0.0;
-    for (int d0 = 0; d0 < D; d0 += 8) {
-        const int dend = min(D, d0 + 8);
-        for (int dd = d0; dd < dend; dd++) {
-            const double v = u2d(dg[(size_t)dd * dstride]);
-            a0 = __dadd_rn(a0, fmodmul(v, u2d(__ldg(k0 + (size_t)dd * kstride)), p, pinv));
-            a1 = __dadd_rn(a1, fmodmul(v, u2d(__ldg(k0 + (size_t)dd * kstride + dstride)), p, pinv));
+    double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0; // a<key poly><coefficient>
+#pragma unroll UNR
+    for (int dd = 0; dd < D; dd++) {
+        const ulonglong2 vu = ldcs2(dg + (size_t)dd * N);
+        const ulonglong2 w0u = __ldg(reinterpret_cast<const ulonglong2 *>(k0 + (size_t)dd * kstride));
+        const ulonglong2 w1u = __ldg(reinterpret_cast<const ulonglong2 *>(k0 + (size_t)dd * kstride + kpoly));
+        const double v0 = LAZY ? __longlong_as_double((long long)vu.x) : u2d(vu.x), v1 = LAZY ? __longlong_as_double((long long)vu.y) : u2d(vu.y);
+        a00 = __dadd_rn(a00, fmodmul(v0, u2d(w0u.x), p, pinv));
+        a01 = __dadd_rn(a01, fmodmul(v1, u2d(w0u.y), p, pinv));
+        a10 = __dadd_rn(a10, fmodmul(v0, u2d(w1u.x), p, pinv));
+        a11 = __dadd_rn(a11, fmodmul(v1, u2d(w1u.y), p, pinv));
+        if ((dd & 7) == 7) { // sums of 8 fresh products stay below 4.1 p; re-centre before they could leave the exact range
+            a00 = frecenter(a00, p, pinv); a01 = frecenter(a01, p, pinv);
+            a10 = frecenter(a10, p, pinv); a11 = frecenter(a11, p, pinv);
         }
-        a0 = frecenter(a0, p, pinv);
-        a1 = frecenter(a1, p, pinv);
     }
+    a00 = frecenter(a00, p, pinv); a01 = frecenter(a01, p, pinv);
+    a10 = frecenter(a10, p, pinv); a11 = frecenter(a11, p, pinv);
     const size_t o = ((size_t)(c * 2) * k + l) * N + x;
-    acc[o] = fcanon_u(a0, p, pinv);
-    acc[o + (size_t)k * N] = fcanon_u(a1, p, pinv);
+    if (LAZY) {
+        *reinterpret_cast<ulonglong2 *>(acc + o) = make_ulonglong2(lazy_bits(a00), lazy_bits(a01));
+        *reinterpret_cast<ulonglong2 *>(acc + o + kpoly) = make_ulonglong2(lazy_bits(a10), lazy_bits(a11));
+    } else {
+        *reinterpret_cast<ulonglong2 *>(acc + o) = make_ulonglong2(fsmall_u(a00, F.q_u[l]), fsmall_u(a01, F.q_u[l]));
+        *reinterpret_cast<ulonglong2 *>(acc + o + kpoly) = make_ulonglong2(fsmall_u(a10, F.q_u[l]), fsmall_u(a11, F.q_u[l]));
+    }
 }
 
 static inline unsigned blocks_for(size_t threads) { return (unsigned)((threads + 255) / 256); }
 
-cudaError_t launch_behz_lift_fp(const u64 *const *ct_ptrs, u64 *out, int n, int logn, const BehzConstF *f, cudaStream_t s) {
+// `f` is the HOST copy of the constants (passed by value into the kernel's parameter space)
+cudaError_t launch_behz_lift_fp(const u64 *const *ct_ptrs, u64 *out, int n, int logn, const BehzConstF *f, int lazy, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    k_behz_lift_fp<<<blocks_for((size_t)n * 2 << logn), 256, 0, s>>>(ct_ptrs, out, n * 2, logn, f);
+    if (lazy) k_behz_lift_fp<true><<<blocks_for((size_t)n * 2 << logn), 256, 0, s>>>(ct_ptrs, out, n * 2, logn, *f);
+    else k_behz_lift_fp<false><<<blocks_for((size_t)n * 2 << logn), 256, 0, s>>>(ct_ptrs, out, n * 2, logn, *f);
     return cudaGetLastError();
 }
-cudaError_t launch_behz_tensor_fp(const u64 *a, const u64 *b, u64 *d, int n, int kt, int logn, const BehzConstF *f, cudaStream_t s) {
+cudaError_t launch_behz_tensor_fp(const u64 *a, const u64 *b, u64 *d, int n, int kt, int logn, const BehzConstF *f, int lazy, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    k_behz_tensor_fp<<<blocks_for(((size_t)n * kt) << logn), 256, 0, s>>>(a, b, d, n, logn, f);
+    if (lazy) k_behz_tensor_fp<true><<<blocks_for(((size_t)n * kt) << logn), 256, 0, s>>>(a, b, d, n, logn, *f);
+    else k_behz_tensor_fp<false><<<blocks_for(((size_t)n * kt) << logn), 256, 0, s>>>(a, b, d, n, logn, *f);
     return cudaGetLastError();
 }
-cudaError_t launch_behz_floor_fp(const u64 *d, u64 *out3, int n, u64 t, int logn, const BehzConstF *f, cudaStream_t s) {
+cudaError_t launch_behz_floor_fp(const u64 *d, u64 *out3, int n, u64 t, int logn, const BehzConstF *f, int lazy, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    k_behz_floor_fp<<<blocks_for((size_t)n * 3 << logn), 256, 0, s>>>(d, out3, n * 3, (double)t, logn, f);
+    if (lazy) k_behz_floor_fp<true><<<blocks_for((size_t)n * 3 << logn), 256, 0, s>>>(d, out3, n * 3, (double)t, logn, *f);
+    else k_behz_floor_fp<false><<<blocks_for((size_t)n * 3 << logn), 256, 0, s>>>(d, out3, n * 3, (double)t, logn, *f);
     return cudaGetLastError();
 }
-cudaError_t launch_ks_mac_fp(const u64 *digits, const u64 *key, u64 *acc, int n, int D, int k, int logn, const BehzConstF *f, cudaStream_t s) {
+cudaError_t launch_ks_mac_fp(const u64 *digits, const u64 *key, u64 *acc, int n, int D, int k, int logn, const BehzConstF *f, int lazy,
+                             cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    k_ks_mac_fp<<<blocks_for(((size_t)n * k) << logn), 256, 0, s>>>(digits, key, acc, n, D, logn, f);
+    static const int unr = getenv("CNHE_KSMAC") ? atoi(getenv("CNHE_KSMAC")) : 1; // tuning knob: digits in flight per thread
+    const unsigned blocks = blocks_for(((size_t)n * k) << (logn - 1));
+    if (!lazy) k_ks_mac_fp<false, 4><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+    else if (unr == 1) k_ks_mac_fp<true, 1><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+    else if (unr == 2) k_ks_mac_fp<true, 2><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+    else if (unr == 8) k_ks_mac_fp<true, 8><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+    else k_ks_mac_fp<true, 4><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
     return cudaGetLastError();
 }
 

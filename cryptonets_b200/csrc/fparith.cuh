@@ -26,7 +26,24 @@ __device__ __forceinline__ double fcanon(double x, double p, double pinv) { // a
 }
 
 
-// canonical u64 residue of (sum) for a double holding any integer |x| < 2^52
-__device__ __forceinline__ u64 fcanon_u(double x, double p, double pinv) { return d2u(fcanon(x, p, pinv)); }
+// exact signed integer value of a double holding an integer |x| < 2^51 (one FP64 add; the rest runs on the integer pipe)
+__device__ __forceinline__ long long d2i(double r) { return __double_as_longlong(__dadd_rn(r, FP_MAGIC)) - 0x4338000000000000LL; }
+// canonical u64 residue of a double holding any integer |x| < 2^52: re-centre on the FP64 pipe (3 instructions), fix the sign
+// on the integer pipe -- half the FP64 work of fcanon() + d2u()
+__device__ __forceinline__ u64 fcanon_u(double x, double p, double pinv) {
+    long long v = d2i(frecenter(x, p, pinv)); // |v| <= p/2 (+1)
+    v += (v >> 63) & (long long)p;
+    return (u64)v;
+}
+// same for a value already known to lie in (-p, p)
+__device__ __forceinline__ u64 fsmall_u(double r, u64 p) {
+    long long v = d2i(r);
+    v += (v >> 63) & (long long)p;
+    return (u64)v;
+}
+// "lazy" residues: internal buffers between the kernels of one multiply / key switch hold IEEE doubles with integer values
+// |x| <= A*p (A host-checked), so producers skip the canonicalisation and consumers skip the u64 -> double conversion
+__device__ __forceinline__ double ld_lazy(const u64 *p) { return __longlong_as_double((long long)*p); }
+__device__ __forceinline__ u64 lazy_bits(double x) { return (u64)__double_as_longlong(x); }
 
 } // namespace cnhe

@@ -15,8 +15,11 @@ struct NttTab {
     // FP64 butterfly path (p < 2^50): the same twiddles as exact doubles, centred in (-p/2, p/2]
     const double *wd, *iwd;
     double pd, pinv, inv_n_d;
+    double inv_n_w_d;                   // iw[1] * N^-1 mod p, centred: the last inverse stage carries the N^-1 scaling
     int fp_ok;                          // 1 when the FP64 path is exact for this modulus and N
     unsigned fwd_recenter, inv_recenter; // forward: bit i = re-centre at the start of pass i; inverse: bit v = re-centre the sums of stage v
+    int fwd_out_rc;                     // lazy forward output must be re-centred (its bound squared would overflow the consumer's product)
+    double fwd_out_bound;               // |forward lazy output| <= fwd_out_bound * p
 };
 
 // Base-2^w digit decomposition used by relinearisation / Galois key switching: digit d comes from residue
@@ -28,6 +31,8 @@ struct DigitMap {
     u64 mask;
 };
 
+// `fp` argument of the NTT launchers
+enum NttFormat { NTT_FP = 1, NTT_IN_F = 2, NTT_OUT_F = 4 };
 enum NttLoad { NTT_LOAD_PLAIN = 0, NTT_LOAD_DIGIT = 1 };
 enum NttStore { NTT_STORE_PLAIN = 0, NTT_STORE_ADD = 1 };
 
@@ -38,12 +43,13 @@ cudaError_t launch_ntt_forward(const u64 *src, u64 *dst, int n_polys, int logn, 
                                cudaStream_t s);
 cudaError_t launch_ntt_inverse(const u64 *src, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base, int mod_count, int fp,
                                cudaStream_t s);
-// dst[((c*D + d)*k + l)] = NTT_l( digit d of target[c] )   target: [n_ct][k][N] coefficient form
-cudaError_t launch_ntt_forward_digits(const u64 *target, u64 *dst, int n_ct, int k, const DigitMap &dm, int logn, const NttTab *tabs, int fp,
-                                      cudaStream_t s);
-// dst[b] = INTT(src[b]) + base[b]  (mod p)
-cudaError_t launch_ntt_inverse_add(const u64 *src, const u64 *base, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base,
-                                   int mod_count, int fp, cudaStream_t s);
+// dst[((c*k + l)*D + d)] = NTT_l( digit d of target[c] )   target: [n_ct][k][N] coefficient form
+// ciphertext c's k-residue target polynomial starts at target + c * ct_stride (words)
+cudaError_t launch_ntt_forward_digits(const u64 *target, size_t ct_stride, u64 *dst, int n_ct, int k, const DigitMap &dm, int logn,
+                                      const NttTab *tabs, int fp, cudaStream_t s);
+// dst[b] = INTT(src[b]) + base[(b / base_group) * base_stride + (b % base_group) * N]  (mod p)
+cudaError_t launch_ntt_inverse_add(const u64 *src, const u64 *base, int base_group, size_t base_stride, u64 *dst, int n_polys, int logn,
+                                   const NttTab *tabs, int mod_base, int mod_count, int fp, cudaStream_t s);
 // pass structure shared by host (re-centring masks) and device: radix (log2) of each pass, forward and inverse
 int ntt_pass_radices(int logn, int inverse, int *radices /*4*/);
 int ntt_kernel_smem_bytes(int logn);
@@ -82,6 +88,7 @@ struct BehzConstF {
     double q_mod_bsk[KBMAX], inv_q_mod_bsk[KBMAX], inv_mtilde_mod_bsk[KBMAX];
     double inv_bhat_mod_b[KBMAX], bhat_mod_q[KMAX][KBMAX], bhat_mod_msk[KBMAX];
     double inv_B_mod_msk, msk_half, B_mod_q[KMAX];
+    u64 q_u[KMAX], b_u[KBMAX]; // the moduli as integers (sign fix-up of canonical outputs on the integer pipe)
 };
 // Per plaintext modulus t.
 struct PlainConst {
@@ -133,10 +140,13 @@ cudaError_t launch_behz_lift(const u64 *const *ct_ptrs, u64 *out, int n, int log
 cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *d, int n, int kt, int logn, const BehzConst *bc, cudaStream_t s);
 // d (coefficient form) -> times t, fast_floor, fastbconv_sk -> out3[n][3][k][N]
 cudaError_t launch_behz_floor(const u64 *d, u64 *out3, int n, u64 t, int logn, const BehzConst *bc, cudaStream_t s);
-cudaError_t launch_behz_lift_fp(const u64 *const *ct_ptrs, u64 *out, int n, int logn, const BehzConstF *f, cudaStream_t s);
-cudaError_t launch_behz_tensor_fp(const u64 *a, const u64 *b, u64 *d, int n, int kt, int logn, const BehzConstF *f, cudaStream_t s);
-cudaError_t launch_behz_floor_fp(const u64 *d, u64 *out3, int n, u64 t, int logn, const BehzConstF *f, cudaStream_t s);
-cudaError_t launch_ks_mac_fp(const u64 *digits, const u64 *key, u64 *acc, int n, int D, int k, int logn, const BehzConstF *f, cudaStream_t s);
+// lazy = 1: the buffers exchanged with the NTT kernels (lift output, tensor input/output, floor input, digit input, accumulator
+// output) hold lazy doubles (fparith.cuh) -- pair with NTT_IN_F / NTT_OUT_F on the transforms in between
+cudaError_t launch_behz_lift_fp(const u64 *const *ct_ptrs, u64 *out, int n, int logn, const BehzConstF *f, int lazy, cudaStream_t s);
+cudaError_t launch_behz_tensor_fp(const u64 *a, const u64 *b, u64 *d, int n, int kt, int logn, const BehzConstF *f, int lazy, cudaStream_t s);
+cudaError_t launch_behz_floor_fp(const u64 *d, u64 *out3, int n, u64 t, int logn, const BehzConstF *f, int lazy, cudaStream_t s);
+cudaError_t launch_ks_mac_fp(const u64 *digits, const u64 *key, u64 *acc, int n, int D, int k, int logn, const BehzConstF *f, int lazy,
+                             cudaStream_t s);
 // ---- K6: key-switch inner product. digits [n][D][k][N] (NTT), key [D][2][k][N] (NTT) -> acc [n][2][k][N] (NTT)
 cudaError_t launch_ks_mac(const u64 *digits, const u64 *key, u64 *acc, int n, int D, int k, int logn, const BehzConst *bc, cudaStream_t s);
 // split a size-3 array [n][3][k][N] view: base[n][2][k][N] = (c0,c1), c2[n][k][N]

@@ -179,20 +179,20 @@ k_ntt_forward(const u64 *src, u64 *dst, const NttTab *__restrict__ tabs, int mod
 
 template <int LOGN>
 __global__ void __launch_bounds__((1 << LOGN) / 16, min_blocks(LOGN))
-k_ntt_forward_digits(const u64 *target, u64 *dst, const NttTab *__restrict__ tabs, int k, DigitMap dm) {
+k_ntt_forward_digits(const u64 *target, size_t ct_stride, u64 *dst, const NttTab *__restrict__ tabs, int k, DigitMap dm) {
     extern __shared__ __align__(16) u64 sm[];
     constexpr int N = 1 << LOGN;
     const int b = blockIdx.x, tid = threadIdx.x;
     const int l = b % k, d = (b / k) % dm.D, c = b / (k * dm.D);
     const NttTab tb = tabs[l];
     FwdSrc fs;
-    fs.src = target + ((size_t)c * k + dm.src[d]) * N;
+    fs.src = target + (size_t)c * ct_stride + (size_t)dm.src[d] * N;
     fs.digit = true;
     fs.shift = dm.shift[d];
     fs.mask = dm.mask;
     fs.need_reduce = dm.mask >= tb.mod.p;
     fwd_body<LOGN>(sm, fs, tb, tid);
-    smem_to_global<LOGN>(sm, dst + (size_t)b * N, tid);
+    smem_to_global<LOGN>(sm, dst + (((size_t)c * k + l) * dm.D + d) * N, tid); // [c][l][d]: the layout the key MAC streams
 }
 
 // ---------------------------------------------------------------- inverse
@@ -264,7 +264,8 @@ __device__ __forceinline__ void inv_pass(u64 *sm, u64 *dst, const u64 *base_add,
 
 template <int LOGN>
 __global__ void __launch_bounds__((1 << LOGN) / 16, min_blocks(LOGN))
-k_ntt_inverse(const u64 *src, const u64 *base_add, u64 *dst, const NttTab *__restrict__ tabs, int mod_base, int mod_count) {
+k_ntt_inverse(const u64 *src, const u64 *base_add, int base_group, size_t base_stride, u64 *dst, const NttTab *__restrict__ tabs, int mod_base,
+              int mod_count) {
     extern __shared__ __align__(16) u64 sm[];
     constexpr int N = 1 << LOGN;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -274,7 +275,7 @@ k_ntt_inverse(const u64 *src, const u64 *base_add, u64 *dst, const NttTab *__res
     inv_first<LOGN>(sm, tb, tid);
     __syncthreads();
     u64 *d = dst + (size_t)b * N;
-    const u64 *ba = base_add ? base_add + (size_t)b * N : nullptr;
+    const u64 *ba = base_add ? base_add + (size_t)(b / base_group) * base_stride + (size_t)(b % base_group) * N : nullptr;
     if constexpr (LOGN == 10) {
         inv_pass<10, 4, 4, false>(sm, d, ba, tb, tid); __syncthreads();
         inv_pass<10, 8, 2, true>(sm, d, ba, tb, tid);
@@ -322,7 +323,19 @@ __device__ __forceinline__ void stg256(u64 *p, u64 a, u64 b, u64 c, u64 d) {
 // N=8192 is 5+4+4 stages (was 3+3+3+4), the first pass reads HBM directly, the last one writes HBM directly.
 // A pass over stages [S0, S0+R) is executed by "virtual threads": N/32 of them for R=5 (32 coefficients each), N/16 otherwise
 // (16 coefficients: one radix-16 group, or two adjacent columns of radix-8 / four of radix-4 with 16-byte accesses).
-template <int LOGN, int S0, int R, bool FROM_G, int PASS>
+// first-pass load: canonical u64 word, a digit of it, or (IN_F) a lazy double written by the producing kernel
+template <bool IN_F>
+__device__ __forceinline__ double fwd_load_fp(const FwdSrc &s, int idx, double p, double pinv) {
+    if constexpr (IN_F) return ld_lazy(s.src + idx);
+    u64 v = s.src[idx];
+    if (s.digit) {
+        v = (v >> s.shift) & s.mask; // source residue < 2^50, so every digit converts exactly
+        const double x = u2d(v);
+        return s.need_reduce ? frecenter(x, p, pinv) : x;
+    }
+    return u2d(v);
+}
+template <int LOGN, int S0, int R, bool FROM_G, int PASS, bool IN_F>
 __device__ __forceinline__ void fwd_pass_fp(double *sm, const double *twc, const FwdSrc &src, const NttTab &tb, int vt) {
     constexpr int E = 1 << R, LG = LOGN - S0 - R;
     constexpr bool CACHED = (S0 + R) <= 9; // every twiddle index of this pass is below TWC
@@ -340,8 +353,8 @@ __device__ __forceinline__ void fwd_pass_fp(double *sm, const double *twc, const
             for (int e = 0; e < E; e++) {
                 const int idx = base + (e << LG);
                 if constexpr (FROM_G) {
-                    x[e] = u2d(fwd_load(src, idx, tb.mod));
-                    y[e] = u2d(fwd_load(src, idx + 1, tb.mod));
+                    x[e] = fwd_load_fp<IN_F>(src, idx, p, pinv);
+                    y[e] = fwd_load_fp<IN_F>(src, idx + 1, p, pinv);
                 } else {
                     const double2 v = *reinterpret_cast<const double2 *>(sm + swz(idx));
                     x[e] = v.x;
@@ -376,7 +389,10 @@ __device__ __forceinline__ void fwd_pass_fp(double *sm, const double *twc, const
         const int base = (j << (LG + R)) + c;
         double x[E];
 #pragma unroll
-        for (int e = 0; e < E; e++) x[e] = FROM_G ? u2d(fwd_load(src, base + (e << LG), tb.mod)) : sm[swz(base + (e << LG))];
+        for (int e = 0; e < E; e++) {
+            if constexpr (FROM_G) x[e] = fwd_load_fp<IN_F>(src, base + (e << LG), p, pinv);
+            else x[e] = sm[swz(base + (e << LG))];
+        }
         if (rc) {
 #pragma unroll
             for (int e = 0; e < E; e++) x[e] = frecenter(x[e], p, pinv);
@@ -400,7 +416,7 @@ __device__ __forceinline__ void fwd_pass_fp(double *sm, const double *twc, const
     }
 }
 // Last forward pass: stages [LOGN-4, LOGN) on 16 consecutive words; canonical result goes straight to HBM.
-template <int LOGN, int PASS>
+template <int LOGN, int PASS, bool OUT_F>
 __device__ __forceinline__ void fwd_last_fp(const double *sm, u64 *dst, const NttTab &tb, int j) {
     constexpr int S0 = LOGN - 4;
     const double p = tb.pd, pinv = tb.pinv;
@@ -449,9 +465,18 @@ __device__ __forceinline__ void fwd_last_fp(const double *sm, u64 *dst, const Nt
         }
     }
     u64 *o = dst + 16 * j;
+    if constexpr (OUT_F) { // lazy doubles: |x| <= fwd bound * p; re-centred only where the consumer's product could overflow (host flag)
+        if (tb.fwd_out_rc) {
 #pragma unroll
-    for (int g = 0; g < 4; g++)
-        stg256(o + 4 * g, fcanon_u(x[4 * g], p, pinv), fcanon_u(x[4 * g + 1], p, pinv), fcanon_u(x[4 * g + 2], p, pinv), fcanon_u(x[4 * g + 3], p, pinv));
+            for (int e = 0; e < 16; e++) x[e] = frecenter(x[e], p, pinv);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; g++) stg256(o + 4 * g, lazy_bits(x[4 * g]), lazy_bits(x[4 * g + 1]), lazy_bits(x[4 * g + 2]), lazy_bits(x[4 * g + 3]));
+    } else {
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+            stg256(o + 4 * g, fcanon_u(x[4 * g], p, pinv), fcanon_u(x[4 * g + 1], p, pinv), fcanon_u(x[4 * g + 2], p, pinv), fcanon_u(x[4 * g + 3], p, pinv));
+    }
 }
 
 #define CNHE_VTN(COUNT, stmt) _Pragma("unroll") for (int vt = tid; vt < (COUNT); vt += TR) { stmt; }
@@ -469,35 +494,35 @@ __device__ __forceinline__ void prefetch_next_poly(const u64 *src_base, int b, i
         for (int i = tid * 128; i < N * 8; i += TR * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i));
     }
 }
-template <int LOGN>
+template <int LOGN, bool IN_F, bool OUT_F>
 __device__ __forceinline__ void fwd_body_fp(double *sm, const FwdSrc &src, u64 *dst, const NttTab &tb, int tid) {
     constexpr int N = 1 << LOGN, TR = fp_threads(LOGN);
     double *twc = sm + N;
     load_twiddle_cache(twc, tb.wd, tid, TR);
     __syncthreads();
     if constexpr (LOGN == 10) {
-        CNHE_VTN(N / 16, (fwd_pass_fp<10, 0, 2, true, 0>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (fwd_pass_fp<10, 2, 4, false, 1>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (fwd_last_fp<10, 2>(sm, dst, tb, vt)));
+        CNHE_VTN(N / 16, (fwd_pass_fp<10, 0, 2, true, 0, IN_F>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_pass_fp<10, 2, 4, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_last_fp<10, 2, OUT_F>(sm, dst, tb, vt)));
     } else if constexpr (LOGN == 11) {
-        CNHE_VTN(N / 16, (fwd_pass_fp<11, 0, 3, true, 0>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (fwd_pass_fp<11, 3, 4, false, 1>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (fwd_last_fp<11, 2>(sm, dst, tb, vt)));
+        CNHE_VTN(N / 16, (fwd_pass_fp<11, 0, 3, true, 0, IN_F>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_pass_fp<11, 3, 4, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_last_fp<11, 2, OUT_F>(sm, dst, tb, vt)));
     } else if constexpr (LOGN == 12) {
-        CNHE_VTN(N / 16, (fwd_pass_fp<12, 0, 4, true, 0>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (fwd_pass_fp<12, 4, 4, false, 1>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (fwd_last_fp<12, 2>(sm, dst, tb, vt)));
+        CNHE_VTN(N / 16, (fwd_pass_fp<12, 0, 4, true, 0, IN_F>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_pass_fp<12, 4, 4, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_last_fp<12, 2, OUT_F>(sm, dst, tb, vt)));
     } else if constexpr (LOGN == 13) {
-        CNHE_VTN(N / 32, (fwd_pass_fp<13, 0, 5, true, 0>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (fwd_pass_fp<13, 5, 4, false, 1>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (fwd_last_fp<13, 2>(sm, dst, tb, vt)));
+        CNHE_VTN(N / 32, (fwd_pass_fp<13, 0, 5, true, 0, IN_F>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_pass_fp<13, 5, 4, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_last_fp<13, 2, OUT_F>(sm, dst, tb, vt)));
     } else {
-        CNHE_VTN(N / 32, (fwd_pass_fp<14, 0, 5, true, 0>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 32, (fwd_pass_fp<14, 5, 5, false, 1>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (fwd_last_fp<14, 2>(sm, dst, tb, vt)));
+        CNHE_VTN(N / 32, (fwd_pass_fp<14, 0, 5, true, 0, IN_F>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 32, (fwd_pass_fp<14, 5, 5, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_last_fp<14, 2, OUT_F>(sm, dst, tb, vt)));
     }
 }
-template <int LOGN>
+template <int LOGN, bool IN_F, bool OUT_F>
 __global__ void __launch_bounds__(fp_threads(LOGN), fp_min_blocks(LOGN))
 k_ntt_forward_fp(const u64 *src, u64 *dst, const NttTab *__restrict__ tabs, int mod_base, int mod_count) {
     extern __shared__ __align__(16) u64 sm[];
@@ -508,27 +533,28 @@ k_ntt_forward_fp(const u64 *src, u64 *dst, const NttTab *__restrict__ tabs, int 
     fs.src = src + (size_t)b * N;
     fs.digit = false; fs.need_reduce = false; fs.shift = 0; fs.mask = 0;
     prefetch_next_poly<LOGN>(src, b, gridDim.x, tid);
-    fwd_body_fp<LOGN>(reinterpret_cast<double *>(sm), fs, dst + (size_t)b * N, tb, tid);
+    fwd_body_fp<LOGN, IN_F, OUT_F>(reinterpret_cast<double *>(sm), fs, dst + (size_t)b * N, tb, tid);
 }
-template <int LOGN>
+// target: ciphertext c's polynomial with `k` residues starts at target + c * ct_stride (words)
+template <int LOGN, bool OUT_F>
 __global__ void __launch_bounds__(fp_threads(LOGN), fp_min_blocks(LOGN))
-k_ntt_forward_digits_fp(const u64 *target, u64 *dst, const NttTab *__restrict__ tabs, int k, DigitMap dm) {
+k_ntt_forward_digits_fp(const u64 *target, size_t ct_stride, u64 *dst, const NttTab *__restrict__ tabs, int k, DigitMap dm) {
     extern __shared__ __align__(16) u64 sm[];
     constexpr int N = 1 << LOGN;
     const int b = blockIdx.x, tid = threadIdx.x;
     const int l = b % k, d = (b / k) % dm.D, c = b / (k * dm.D);
     const NttTab tb = tabs[l];
     FwdSrc fs;
-    fs.src = target + ((size_t)c * k + dm.src[d]) * N;
+    fs.src = target + (size_t)c * ct_stride + (size_t)dm.src[d] * N;
     fs.digit = true;
     fs.shift = dm.shift[d];
     fs.mask = dm.mask;
     fs.need_reduce = dm.mask >= tb.mod.p;
-    fwd_body_fp<LOGN>(reinterpret_cast<double *>(sm), fs, dst + (size_t)b * N, tb, tid);
+    fwd_body_fp<LOGN, false, OUT_F>(reinterpret_cast<double *>(sm), fs, dst + (((size_t)c * k + l) * dm.D + d) * N, tb, tid); // [c][l][d]
 }
 
 // ---- inverse, FP64: first pass reads 16 consecutive words per virtual thread straight from HBM (256-bit loads)
-template <int LOGN>
+template <int LOGN, bool IN_F>
 __device__ __forceinline__ void inv_first_fp(double *sm, const u64 *src, const NttTab &tb, int j) {
     constexpr int N = 1 << LOGN;
     const double p = tb.pd, pinv = tb.pinv;
@@ -539,10 +565,17 @@ __device__ __forceinline__ void inv_first_fp(double *sm, const u64 *src, const N
     for (int g = 0; g < 4; g++) {
         u64 v0, v1, v2, v3;
         ldg256(src + 16 * j + 4 * g, v0, v1, v2, v3);
-        x[4 * g] = u2d(v0);
-        x[4 * g + 1] = u2d(v1);
-        x[4 * g + 2] = u2d(v2);
-        x[4 * g + 3] = u2d(v3);
+        if constexpr (IN_F) {
+            x[4 * g] = __longlong_as_double((long long)v0);
+            x[4 * g + 1] = __longlong_as_double((long long)v1);
+            x[4 * g + 2] = __longlong_as_double((long long)v2);
+            x[4 * g + 3] = __longlong_as_double((long long)v3);
+        } else {
+            x[4 * g] = u2d(v0);
+            x[4 * g + 1] = u2d(v1);
+            x[4 * g + 2] = u2d(v2);
+            x[4 * g + 3] = u2d(v3);
+        }
     }
     // stage u uses 8 >> u consecutive inverse twiddles: 8 + 4 + 2 + 1 doubles per thread, 16-byte loads
     double tw[15];
@@ -582,17 +615,16 @@ __device__ __forceinline__ void inv_first_fp(double *sm, const u64 *src, const N
 #pragma unroll
     for (int ch = 0; ch < 8; ch++) smv[j * 8 + (ch ^ xr)] = make_double2(x[2 * ch], x[2 * ch + 1]);
 }
-template <int LOGN, int V0, int R, bool LAST>
+// The last stage (one twiddle, iw[1]) carries N^-1: sums are multiplied by N^-1, differences by iw[1]*N^-1, so every output is a
+// fresh modular product in (-0.51p, 0.51p): written as is (OUT_F, lazy double) or sign-fixed on the integer pipe (canonical).
+template <int LOGN, int V0, int R, bool LAST, bool OUT_F>
 __device__ __forceinline__ void inv_pass_fp(double *sm, const double *twc, u64 *dst, const u64 *base_add, const NttTab &tb, int vt) {
     constexpr int N = 1 << LOGN, E = 1 << R;
     constexpr bool CACHED = (N >> V0) <= TWC; // stage v reads indices [N>>(v+1), N>>v)
     const double p = tb.pd, pinv = tb.pinv;
     auto finish = [&](double v, int idx) {
-        double r = fmodmul(v, tb.inv_n_d, p, pinv); // |v| < 2^52 (host-checked); r in (-1.3p, 1.3p)
-        r = r < 0.0 ? __dadd_rn(r, p) : r;
-        r = r < 0.0 ? __dadd_rn(r, p) : r;
-        r = r >= p ? __dsub_rn(r, p) : r;
-        u64 o = d2u(r);
+        if constexpr (OUT_F) return lazy_bits(v);
+        u64 o = fsmall_u(v, tb.mod.p);
         if (base_add) o = addmod(o, base_add[idx], tb.mod.p);
         return o;
     };
@@ -620,12 +652,19 @@ __device__ __forceinline__ void inv_pass_fp(double *sm, const double *twc, u64 *
                     const int ti = (N >> (V0 + u + 1)) + (j << (R - 1 - u)) + (e >> (u + 1));
                     const double w = CACHED ? twc[ti] : __ldg(tb.iwd + ti);
                     const double a0 = x[e], b0 = x[e + h], a1 = y[e], b1 = y[e + h];
-                    x[e] = __dadd_rn(a0, b0);
-                    y[e] = __dadd_rn(a1, b1);
-                    x[e + h] = fmodmul(__dsub_rn(a0, b0), w, p, pinv);
-                    y[e + h] = fmodmul(__dsub_rn(a1, b1), w, p, pinv);
+                    if (LAST && u == R - 1) {
+                        x[e] = fmodmul(__dadd_rn(a0, b0), tb.inv_n_d, p, pinv);
+                        y[e] = fmodmul(__dadd_rn(a1, b1), tb.inv_n_d, p, pinv);
+                        x[e + h] = fmodmul(__dsub_rn(a0, b0), tb.inv_n_w_d, p, pinv);
+                        y[e + h] = fmodmul(__dsub_rn(a1, b1), tb.inv_n_w_d, p, pinv);
+                    } else {
+                        x[e] = __dadd_rn(a0, b0);
+                        y[e] = __dadd_rn(a1, b1);
+                        x[e + h] = fmodmul(__dsub_rn(a0, b0), w, p, pinv);
+                        y[e + h] = fmodmul(__dsub_rn(a1, b1), w, p, pinv);
+                    }
                 }
-                if (rc) {
+                if (rc && !(LAST && u == R - 1)) {
 #pragma unroll
                     for (int e = 0; e < E; e++)
                         if (!(e & h)) { x[e] = frecenter(x[e], p, pinv); y[e] = frecenter(y[e], p, pinv); }
@@ -658,10 +697,15 @@ __device__ __forceinline__ void inv_pass_fp(double *sm, const double *twc, u64 *
                 const int ti = (N >> (V0 + u + 1)) + (j << (R - 1 - u)) + (e >> (u + 1));
                 const double w = CACHED ? twc[ti] : __ldg(tb.iwd + ti);
                 const double a = x[e], bq = x[e + h];
-                x[e] = __dadd_rn(a, bq);
-                x[e + h] = fmodmul(__dsub_rn(a, bq), w, p, pinv);
+                if (LAST && u == R - 1) {
+                    x[e] = fmodmul(__dadd_rn(a, bq), tb.inv_n_d, p, pinv);
+                    x[e + h] = fmodmul(__dsub_rn(a, bq), tb.inv_n_w_d, p, pinv);
+                } else {
+                    x[e] = __dadd_rn(a, bq);
+                    x[e + h] = fmodmul(__dsub_rn(a, bq), w, p, pinv);
+                }
             }
-            if (rc) {
+            if (rc && !(LAST && u == R - 1)) {
 #pragma unroll
                 for (int e = 0; e < E; e++)
                     if (!(e & h)) x[e] = frecenter(x[e], p, pinv);
@@ -679,9 +723,11 @@ __device__ __forceinline__ void inv_pass_fp(double *sm, const double *twc, u64 *
         }
     }
 }
-template <int LOGN>
+// base_add (optional): polynomial b is added to base_add[(b / base_group) * base_stride + (b % base_group) * N] (canonical output only)
+template <int LOGN, bool IN_F, bool OUT_F>
 __global__ void __launch_bounds__(fp_threads(LOGN), fp_min_blocks(LOGN))
-k_ntt_inverse_fp(const u64 *src, const u64 *base_add, u64 *dst, const NttTab *__restrict__ tabs, int mod_base, int mod_count) {
+k_ntt_inverse_fp(const u64 *src, const u64 *base_add, int base_group, size_t base_stride, u64 *dst, const NttTab *__restrict__ tabs, int mod_base,
+                 int mod_count) {
     extern __shared__ __align__(16) u64 smraw[];
     constexpr int N = 1 << LOGN, TR = fp_threads(LOGN);
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -692,24 +738,28 @@ k_ntt_inverse_fp(const u64 *src, const u64 *base_add, u64 *dst, const NttTab *__
     prefetch_next_poly<LOGN>(src, b, gridDim.x, tid);
     const u64 *s = src + (size_t)b * N;
     u64 *d = dst + (size_t)b * N;
-    const u64 *ba = base_add ? base_add + (size_t)b * N : nullptr;
-    CNHE_VTN(N / 16, (inv_first_fp<LOGN>(sm, s, tb, vt)));
+    const u64 *ba = base_add ? base_add + (size_t)(b / base_group) * base_stride + (size_t)(b % base_group) * N : nullptr;
+    if (ba) { // the base polynomial is consumed by the epilogue, ~20k cycles from now: have it waiting in L2
+        const char *pb = reinterpret_cast<const char *>(ba);
+        for (int i = tid * 128; i < N * 8; i += TR * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + i));
+    }
+    CNHE_VTN(N / 16, (inv_first_fp<LOGN, IN_F>(sm, s, tb, vt)));
     __syncthreads();
     if constexpr (LOGN == 10) {
-        CNHE_VTN(N / 16, (inv_pass_fp<10, 4, 4, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (inv_pass_fp<10, 8, 2, true>(sm, twc, d, ba, tb, vt)));
+        CNHE_VTN(N / 16, (inv_pass_fp<10, 4, 4, false, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (inv_pass_fp<10, 8, 2, true, OUT_F>(sm, twc, d, ba, tb, vt)));
     } else if constexpr (LOGN == 11) {
-        CNHE_VTN(N / 16, (inv_pass_fp<11, 4, 4, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (inv_pass_fp<11, 8, 3, true>(sm, twc, d, ba, tb, vt)));
+        CNHE_VTN(N / 16, (inv_pass_fp<11, 4, 4, false, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (inv_pass_fp<11, 8, 3, true, OUT_F>(sm, twc, d, ba, tb, vt)));
     } else if constexpr (LOGN == 12) {
-        CNHE_VTN(N / 16, (inv_pass_fp<12, 4, 4, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (inv_pass_fp<12, 8, 4, true>(sm, twc, d, ba, tb, vt)));
+        CNHE_VTN(N / 16, (inv_pass_fp<12, 4, 4, false, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (inv_pass_fp<12, 8, 4, true, OUT_F>(sm, twc, d, ba, tb, vt)));
     } else if constexpr (LOGN == 13) {
-        CNHE_VTN(N / 16, (inv_pass_fp<13, 4, 4, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 32, (inv_pass_fp<13, 8, 5, true>(sm, twc, d, ba, tb, vt)));
+        CNHE_VTN(N / 16, (inv_pass_fp<13, 4, 4, false, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 32, (inv_pass_fp<13, 8, 5, true, OUT_F>(sm, twc, d, ba, tb, vt)));
     } else {
-        CNHE_VTN(N / 32, (inv_pass_fp<14, 4, 5, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 32, (inv_pass_fp<14, 9, 5, true>(sm, twc, d, ba, tb, vt)));
+        CNHE_VTN(N / 32, (inv_pass_fp<14, 4, 5, false, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 32, (inv_pass_fp<14, 9, 5, true, OUT_F>(sm, twc, d, ba, tb, vt)));
     }
 }
 
@@ -743,14 +793,24 @@ static cudaError_t prep(K kern, int logn) {
     default: return cudaErrorInvalidValue;                                                                              \
     }
 
+// `fp`: 0 = integer Harvey butterflies; NTT_FP = FP64 butterflies, optionally | NTT_IN_F (source holds lazy doubles) | NTT_OUT_F
+// (destination receives lazy doubles instead of canonical words)
 cudaError_t launch_ntt_forward(const u64 *src, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base, int mod_count, int fp,
                                cudaStream_t s) {
     if (n_polys <= 0) return cudaSuccess;
-    if (fp) {
+    if (fp & NTT_FP) {
+        const bool lazy = (fp & (NTT_IN_F | NTT_OUT_F)) == (NTT_IN_F | NTT_OUT_F);
+        if (!lazy && (fp & (NTT_IN_F | NTT_OUT_F))) return cudaErrorInvalidValue; // only canonical->canonical and lazy->lazy are built
         CNHE_DISPATCH_LOGN(logn, {
-            cudaError_t e = prep(k_ntt_forward_fp<L>, L);
-            if (e != cudaSuccess) return e;
-            k_ntt_forward_fp<L><<<n_polys, fp_threads(L), ntt_kernel_smem_bytes(L), s>>>(src, dst, tabs, mod_base, mod_count);
+            if (lazy) {
+                cudaError_t e = prep(k_ntt_forward_fp<L, true, true>, L);
+                if (e != cudaSuccess) return e;
+                k_ntt_forward_fp<L, true, true><<<n_polys, fp_threads(L), ntt_kernel_smem_bytes(L), s>>>(src, dst, tabs, mod_base, mod_count);
+            } else {
+                cudaError_t e = prep(k_ntt_forward_fp<L, false, false>, L);
+                if (e != cudaSuccess) return e;
+                k_ntt_forward_fp<L, false, false><<<n_polys, fp_threads(L), ntt_kernel_smem_bytes(L), s>>>(src, dst, tabs, mod_base, mod_count);
+            }
         });
         return cudaGetLastError();
     }
@@ -761,49 +821,69 @@ cudaError_t launch_ntt_forward(const u64 *src, u64 *dst, int n_polys, int logn, 
     });
     return cudaGetLastError();
 }
-cudaError_t launch_ntt_forward_digits(const u64 *target, u64 *dst, int n_ct, int k, const DigitMap &dm, int logn, const NttTab *tabs, int fp,
-                                      cudaStream_t s) {
+cudaError_t launch_ntt_forward_digits(const u64 *target, size_t ct_stride, u64 *dst, int n_ct, int k, const DigitMap &dm, int logn,
+                                      const NttTab *tabs, int fp, cudaStream_t s) {
     if (n_ct <= 0) return cudaSuccess;
-    if (fp) {
+    if (fp & NTT_FP) {
+        if (fp & NTT_IN_F) return cudaErrorInvalidValue; // digits are cut from canonical words
         CNHE_DISPATCH_LOGN(logn, {
-            cudaError_t e = prep(k_ntt_forward_digits_fp<L>, L);
-            if (e != cudaSuccess) return e;
-            k_ntt_forward_digits_fp<L><<<n_ct * dm.D * k, fp_threads(L), ntt_kernel_smem_bytes(L), s>>>(target, dst, tabs, k, dm);
+            if (fp & NTT_OUT_F) {
+                cudaError_t e = prep(k_ntt_forward_digits_fp<L, true>, L);
+                if (e != cudaSuccess) return e;
+                k_ntt_forward_digits_fp<L, true><<<n_ct * dm.D * k, fp_threads(L), ntt_kernel_smem_bytes(L), s>>>(target, ct_stride, dst, tabs, k, dm);
+            } else {
+                cudaError_t e = prep(k_ntt_forward_digits_fp<L, false>, L);
+                if (e != cudaSuccess) return e;
+                k_ntt_forward_digits_fp<L, false><<<n_ct * dm.D * k, fp_threads(L), ntt_kernel_smem_bytes(L), s>>>(target, ct_stride, dst, tabs, k, dm);
+            }
         });
         return cudaGetLastError();
     }
     CNHE_DISPATCH_LOGN(logn, {
         cudaError_t e = prep(k_ntt_forward_digits<L>, L);
         if (e != cudaSuccess) return e;
-        k_ntt_forward_digits<L><<<n_ct * dm.D * k, (1 << L) / 16, ntt_kernel_smem_bytes(L), s>>>(target, dst, tabs, k, dm);
+        k_ntt_forward_digits<L><<<n_ct * dm.D * k, (1 << L) / 16, ntt_kernel_smem_bytes(L), s>>>(target, ct_stride, dst, tabs, k, dm);
     });
     return cudaGetLastError();
 }
-static cudaError_t launch_inv(const u64 *src, const u64 *base, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base,
-                              int mod_count, int fp, cudaStream_t s) {
+template <int L, bool IN_F, bool OUT_F>
+static cudaError_t launch_inv_fp(const u64 *src, const u64 *base, int base_group, size_t base_stride, u64 *dst, int n_polys, const NttTab *tabs,
+                                 int mod_base, int mod_count, cudaStream_t s) {
+    cudaError_t e = prep(k_ntt_inverse_fp<L, IN_F, OUT_F>, L);
+    if (e != cudaSuccess) return e;
+    k_ntt_inverse_fp<L, IN_F, OUT_F><<<n_polys, fp_threads(L), ntt_kernel_smem_bytes(L), s>>>(src, base, base_group, base_stride, dst, tabs, mod_base,
+                                                                                            mod_count);
+    return cudaSuccess;
+}
+static cudaError_t launch_inv(const u64 *src, const u64 *base, int base_group, size_t base_stride, u64 *dst, int n_polys, int logn,
+                              const NttTab *tabs, int mod_base, int mod_count, int fp, cudaStream_t s) {
     if (n_polys <= 0) return cudaSuccess;
-    if (fp) {
+    if (base_group < 1) base_group = 1;
+    if (fp & NTT_FP) {
+        const bool in_f = fp & NTT_IN_F, out_f = fp & NTT_OUT_F;
+        if (out_f && (!in_f || base)) return cudaErrorInvalidValue; // built: canonical->canonical, lazy->lazy, lazy->canonical(+base)
         CNHE_DISPATCH_LOGN(logn, {
-            cudaError_t e = prep(k_ntt_inverse_fp<L>, L);
+            cudaError_t e = out_f  ? launch_inv_fp<L, true, true>(src, base, base_group, base_stride, dst, n_polys, tabs, mod_base, mod_count, s)
+                            : in_f ? launch_inv_fp<L, true, false>(src, base, base_group, base_stride, dst, n_polys, tabs, mod_base, mod_count, s)
+                                   : launch_inv_fp<L, false, false>(src, base, base_group, base_stride, dst, n_polys, tabs, mod_base, mod_count, s);
             if (e != cudaSuccess) return e;
-            k_ntt_inverse_fp<L><<<n_polys, fp_threads(L), ntt_kernel_smem_bytes(L), s>>>(src, base, dst, tabs, mod_base, mod_count);
         });
         return cudaGetLastError();
     }
     CNHE_DISPATCH_LOGN(logn, {
         cudaError_t e = prep(k_ntt_inverse<L>, L);
         if (e != cudaSuccess) return e;
-        k_ntt_inverse<L><<<n_polys, (1 << L) / 16, ntt_kernel_smem_bytes(L), s>>>(src, base, dst, tabs, mod_base, mod_count);
+        k_ntt_inverse<L><<<n_polys, (1 << L) / 16, ntt_kernel_smem_bytes(L), s>>>(src, base, base_group, base_stride, dst, tabs, mod_base, mod_count);
     });
     return cudaGetLastError();
 }
 cudaError_t launch_ntt_inverse(const u64 *src, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base, int mod_count, int fp,
                                cudaStream_t s) {
-    return launch_inv(src, nullptr, dst, n_polys, logn, tabs, mod_base, mod_count, fp, s);
+    return launch_inv(src, nullptr, 1, 0, dst, n_polys, logn, tabs, mod_base, mod_count, fp, s);
 }
-cudaError_t launch_ntt_inverse_add(const u64 *src, const u64 *base, u64 *dst, int n_polys, int logn, const NttTab *tabs, int mod_base,
-                                   int mod_count, int fp, cudaStream_t s) {
-    return launch_inv(src, base, dst, n_polys, logn, tabs, mod_base, mod_count, fp, s);
+cudaError_t launch_ntt_inverse_add(const u64 *src, const u64 *base, int base_group, size_t base_stride, u64 *dst, int n_polys, int logn,
+                                   const NttTab *tabs, int mod_base, int mod_count, int fp, cudaStream_t s) {
+    return launch_inv(src, base, base_group, base_stride, dst, n_polys, logn, tabs, mod_base, mod_count, fp, s);
 }
 
 } // namespace cnhe

@@ -173,8 +173,13 @@ static void fp_schedule(NttTab &tb, int logN, bool force_int) {
             if (i == 0) return;  // the first pass reads straight from global memory: no re-centring slot
         }
     }
-    // inverse: canonical input (1.0); sums double every stage; bit v re-centres the sums produced by stage v
-    A = 1.0;
+    // lazy forward output (|x| <= A p) feeds products of two such values (tensor) or of one with a canonical key word: both operands
+    // of a modular product may be lazy only while A*A*p stays below 2^51
+    tb.fwd_out_rc = A * A * (double)p >= 0.9 * 2251799813685248.0;
+    tb.fwd_out_bound = tb.fwd_out_rc ? 0.51 : A;
+    // inverse: canonical or lazy input (tensor output: sum of two fresh products, <= 1.25 p); sums double every stage; bit v
+    // re-centres the sums produced by stage v
+    A = 1.25;
     for (int v = 0; v < logN; v++) {
         if (2 * A >= L) return;
         const double y = c(2 * A);
@@ -318,6 +323,10 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
         tb.pd = (double)p;
         tb.pinv = 1.0 / (double)p;
         tb.inv_n_d = tb.inv_n > p / 2 ? -(double)(p - tb.inv_n) : (double)tb.inv_n;
+        {
+            const u64 nw = hm::mul(iw[1], tb.inv_n, p);
+            tb.inv_n_w_d = nw > p / 2 ? -(double)(p - nw) : (double)nw;
+        }
         fp_schedule(tb, logN, getenv("CNHE_NTT_INT") != nullptr);
     }
     CNHE_CUDA(cudaMemcpy(c.d_table_mem, host.data(), host.size() * sizeof(u64), cudaMemcpyHostToDevice));
@@ -390,7 +399,7 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
         for (int i = 0; i < k; i++) {
             const u64 p = c.q[i];
             c.fp_elementwise = c.fp_elementwise && hm::bit_length(p) <= 49;
-            f.qd[i] = (double)p; f.qinv[i] = 1.0 / (double)p;
+            f.qd[i] = (double)p; f.qinv[i] = 1.0 / (double)p; f.q_u[i] = p;
             f.inv_qhat_mod_q[i] = cen(bc.inv_qhat_mod_q[i], p);
             f.mtilde_inv_qhat_mod_q[i] = cen(bc.mtilde_inv_qhat_mod_q[i], p);
             f.qhat_mod_mtilde[i] = bc.qhat_mod_mtilde[i];
@@ -401,7 +410,7 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
         for (int j = 0; j < kb; j++) {
             const u64 p = c.bsk[j];
             c.fp_elementwise = c.fp_elementwise && hm::bit_length(p) <= 48;
-            f.bd[j] = (double)p; f.binv[j] = 1.0 / (double)p;
+            f.bd[j] = (double)p; f.binv[j] = 1.0 / (double)p; f.b_u[j] = p;
             for (int i = 0; i < k; i++) f.qhat_mod_bsk[j][i] = cen(bc.qhat_mod_bsk[j][i], p);
             f.q_mod_bsk[j] = cen(bc.q_mod_bsk[j], p);
             f.inv_q_mod_bsk[j] = cen(bc.inv_q_mod_bsk[j], p);
@@ -413,6 +422,9 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
         }
         f.inv_B_mod_msk = cen(bc.inv_B_mod_msk, M_SK);
         f.msk_half = (double)(M_SK >> 1);
+        // lazy-double intermediates between the kernels of a multiply / key switch: FP64 everywhere on the q and Bsk transforms
+        c.lazy = c.fp_elementwise && getenv("CNHE_NO_LAZY") == nullptr;
+        for (int i = 0; i < k + kb; i++) c.lazy = c.lazy && c.h_tabs[i].fp_ok;
         CNHE_CUDA(cudaMalloc((void **)&c.d_bf, sizeof(BehzConstF)));
         CNHE_CUDA(cudaMemcpy(c.d_bf, &f, sizeof(BehzConstF), cudaMemcpyHostToDevice));
     }
@@ -503,9 +515,14 @@ void op_ntt(Context &c, const u64 *src, u64 *dst, int n_polys, int mod_base, int
             "ntt");
 }
 
-void op_key_switch(Context &c, const u64 *target, int n, const u64 *key, const DigitMap &dm, const u64 *base, u64 *out) {
+// out[i] = (base_i + sum_d NTT^-1(NTT(digit_d(target_i)) * key_d)): ciphertext i's target polynomial (k residues) is at
+// target + i * target_stride, its base (2 polynomials) at base + i * base_stride; out is packed [n][2][k][N]
+void op_key_switch(Context &c, const u64 *target, size_t target_stride, int n, const u64 *key, const DigitMap &dm, const u64 *base,
+                   size_t base_stride, u64 *out) {
     const int k = c.k;
     const size_t N = c.N;
+    const int fpq = fp_range(c, 0, k);
+    const bool lazy = c.lazy && fpq;
     for (int c0 = 0; c0 < n; c0 += c.chunk) {
         WsScope scope(c);
         const int m = std::min(c.chunk, n - c0);
@@ -513,15 +530,18 @@ void op_key_switch(Context &c, const u64 *target, int n, const u64 *key, const D
         u64 *acc = c.ws_alloc((size_t)m * 2 * k * N);
         {
             PROF(0, 16.0 * N * (double)m * dm.D * k); // 16N bytes per transform (8N digit source read + 8N written)
-            c.check(launch_ntt_forward_digits(target + (size_t)c0 * k * N, digits, m, k, dm, c.logN, c.d_tabs, fp_range(c, 0, k), c.stream), "ntt_forward_digits");
+            c.check(launch_ntt_forward_digits(target + (size_t)c0 * target_stride, target_stride, digits, m, k, dm, c.logN, c.d_tabs,
+                                              fpq | (lazy ? NTT_OUT_F : 0), c.stream),
+                    "ntt_forward_digits");
         }
         {
             PROF(3, 8.0 * N * ((double)m * dm.D * k + (double)dm.D * 2 * k + (double)m * 2 * k));
-            if (c.fp_elementwise) c.check(launch_ks_mac_fp(digits, key, acc, m, dm.D, k, c.logN, c.d_bf, c.stream), "ks_mac_fp");
+            if (c.fp_elementwise) c.check(launch_ks_mac_fp(digits, key, acc, m, dm.D, k, c.logN, &c.h_bf, lazy, c.stream), "ks_mac_fp");
             else c.check(launch_ks_mac(digits, key, acc, m, dm.D, k, c.logN, c.d_bc, c.stream), "ks_mac");
         }
         PROF(1, 24.0 * N * m * 2 * k);
-        c.check(launch_ntt_inverse_add(acc, base + (size_t)c0 * 2 * k * N, out + (size_t)c0 * 2 * k * N, m * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream),
+        c.check(launch_ntt_inverse_add(acc, base + (size_t)c0 * base_stride, 2 * k, base_stride, out + (size_t)c0 * 2 * k * N, m * 2 * k, c.logN,
+                                       c.d_tabs, 0, k, fpq | (lazy ? NTT_IN_F : 0), c.stream),
                 "ntt_inverse_add");
     }
 }
@@ -533,35 +553,38 @@ static void multiply_chunk(Context &c, int ch, const std::vector<const u64 *> &a
     for (int i = 0; i < m; i++) square = square && a[c0 + i] == b[c0 + i];
     std::vector<const u64 *> pa(a.begin() + c0, a.begin() + c0 + m);
     u64 *A = c.ws_alloc((size_t)m * 2 * kt * N);
+    const int fpt = fp_range(c, 0, kt);
+    const int lazy = c.lazy && fpt ? 1 : 0;
+    const int fmt = fpt | (lazy ? NTT_IN_F | NTT_OUT_F : 0);
     {
         PROF(2, 8.0 * N * m * 2 * (k + kt));
-        if (c.fp_elementwise) c.check(launch_behz_lift_fp(upload_ptrs(c, pa), A, m, c.logN, c.d_bf, c.stream), "behz_lift_fp");
+        if (c.fp_elementwise) c.check(launch_behz_lift_fp(upload_ptrs(c, pa), A, m, c.logN, &c.h_bf, lazy, c.stream), "behz_lift_fp");
         else c.check(launch_behz_lift(upload_ptrs(c, pa), A, m, c.logN, c.d_bc, c.stream), "behz_lift");
     }
     {
         PROF(0, 16.0 * N * m * 2 * kt);
-        c.check(launch_ntt_forward(A, A, m * 2 * kt, c.logN, c.d_tabs, 0, kt, fp_range(c, 0, kt), c.stream), "ntt_forward");
+        c.check(launch_ntt_forward(A, A, m * 2 * kt, c.logN, c.d_tabs, 0, kt, fmt, c.stream), "ntt_forward");
     }
     u64 *B = A;
     if (!square) {
         std::vector<const u64 *> pb(b.begin() + c0, b.begin() + c0 + m);
         B = c.ws_alloc((size_t)m * 2 * kt * N);
-        if (c.fp_elementwise) c.check(launch_behz_lift_fp(upload_ptrs(c, pb), B, m, c.logN, c.d_bf, c.stream), "behz_lift_fp");
+        if (c.fp_elementwise) c.check(launch_behz_lift_fp(upload_ptrs(c, pb), B, m, c.logN, &c.h_bf, lazy, c.stream), "behz_lift_fp");
         else c.check(launch_behz_lift(upload_ptrs(c, pb), B, m, c.logN, c.d_bc, c.stream), "behz_lift");
-        c.check(launch_ntt_forward(B, B, m * 2 * kt, c.logN, c.d_tabs, 0, kt, fp_range(c, 0, kt), c.stream), "ntt_forward");
+        c.check(launch_ntt_forward(B, B, m * 2 * kt, c.logN, c.d_tabs, 0, kt, fmt, c.stream), "ntt_forward");
     }
     u64 *D = c.ws_alloc((size_t)m * 3 * kt * N);
     {
         PROF(2, 8.0 * N * m * kt * (square ? 5 : 7));
-        if (c.fp_elementwise) c.check(launch_behz_tensor_fp(A, B, D, m, kt, c.logN, c.d_bf, c.stream), "behz_tensor_fp");
+        if (c.fp_elementwise) c.check(launch_behz_tensor_fp(A, B, D, m, kt, c.logN, &c.h_bf, lazy, c.stream), "behz_tensor_fp");
         else c.check(launch_behz_tensor(A, B, D, m, kt, c.logN, c.d_bc, c.stream), "behz_tensor");
     }
     {
         PROF(1, 16.0 * N * m * 3 * kt);
-        c.check(launch_ntt_inverse(D, D, m * 3 * kt, c.logN, c.d_tabs, 0, kt, fp_range(c, 0, kt), c.stream), "ntt_inverse");
+        c.check(launch_ntt_inverse(D, D, m * 3 * kt, c.logN, c.d_tabs, 0, kt, fmt, c.stream), "ntt_inverse");
     }
     PROF(2, 8.0 * N * m * 3 * (kt + k));
-    if (c.fp_elementwise) c.check(launch_behz_floor_fp(D, out3, m, c.ch[ch].t, c.logN, c.d_bf, c.stream), "behz_floor_fp");
+    if (c.fp_elementwise) c.check(launch_behz_floor_fp(D, out3, m, c.ch[ch].t, c.logN, &c.h_bf, lazy, c.stream), "behz_floor_fp");
     else c.check(launch_behz_floor(D, out3, m, c.ch[ch].t, c.logN, c.d_bc, c.stream), "behz_floor");
 }
 void op_multiply(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out3) {
@@ -576,12 +599,9 @@ void op_relinearize(Context &c, int ch, const u64 *in3, int n, u64 *out2) {
     if (!c.ch[ch].have_rlk) throw Error(-3, "relinearization keys are missing");
     const int k = c.k;
     const size_t N = c.N;
-    for (int c0 = 0; c0 < n; c0 += c.chunk) {
-        const int m = std::min(c.chunk, n - c0);
-        u64 *base = c.ws_alloc((size_t)m * 2 * k * N), *c2 = c.ws_alloc((size_t)m * k * N);
-        c.check(launch_split3(in3 + (size_t)c0 * 3 * k * N, base, c2, m, k, c.logN, c.stream), "split3");
-        op_key_switch(c, c2, m, c.ch[ch].rlk->p, c.dm_relin, base, out2 + (size_t)c0 * 2 * k * N);
-    }
+    // the size-3 layout [c0 c1 c2] is consumed in place: c2 is the key-switch target, (c0, c1) the base it is added to
+    const size_t s3 = (size_t)3 * k * N;
+    op_key_switch(c, in3 + (size_t)2 * k * N, s3, n, c.ch[ch].rlk->p, c.dm_relin, in3, s3, out2);
 }
 void op_multiply_relin(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out2) {
     if (!c.ch[ch].have_rlk) throw Error(-3, "relinearization keys are missing");
@@ -592,9 +612,8 @@ void op_multiply_relin(Context &c, int ch, const std::vector<const u64 *> &a, co
         const int m = std::min(c.chunk, n - c0);
         u64 *ct3 = c.ws_alloc((size_t)m * 3 * k * N);
         multiply_chunk(c, ch, a, b, c0, m, ct3);
-        u64 *base = c.ws_alloc((size_t)m * 2 * k * N), *c2 = c.ws_alloc((size_t)m * k * N);
-        c.check(launch_split3(ct3, base, c2, m, k, c.logN, c.stream), "split3");
-        op_key_switch(c, c2, m, c.ch[ch].rlk->p, c.dm_relin, base, out2 + (size_t)c0 * 2 * k * N);
+        const size_t s3 = (size_t)3 * k * N;
+        op_key_switch(c, ct3 + (size_t)2 * k * N, s3, m, c.ch[ch].rlk->p, c.dm_relin, ct3, s3, out2 + (size_t)c0 * 2 * k * N);
     }
 }
 
@@ -622,7 +641,7 @@ void op_apply_galois(Context &c, int ch, const u64 *in, int n, u64 elt, u64 *out
         const int m = std::min(c.chunk, n - c0);
         u64 *base = c.ws_alloc((size_t)m * 2 * k * N), *p1 = c.ws_alloc((size_t)m * k * N);
         c.check(launch_galois(in + (size_t)c0 * 2 * k * N, base, p1, m, einv, k, c.logN, c.d_bc, c.stream), "galois");
-        op_key_switch(c, p1, m, it->second->p, c.dm_galois, base, out + (size_t)c0 * 2 * k * N);
+        op_key_switch(c, p1, (size_t)k * N, m, it->second->p, c.dm_galois, base, (size_t)2 * k * N, out + (size_t)c0 * 2 * k * N);
     }
 }
 static std::vector<int> naf(int value) { // non-adjacent form, least significant term first (SEAL util::naf)
@@ -723,7 +742,7 @@ static void dot_with_secret(Context &c, int chi, const u64 *ct, int n, u64 *x) {
     CNHE_CUDA(cudaMemcpy2DAsync(c1, kN * 8, ct + kN, 2 * kN * 8, kN * 8, n, cudaMemcpyDeviceToDevice, c.stream));
     c.check(launch_ntt_forward(c1, c1, n * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
     c.check(launch_dyadic_bcast(c1, ch.sk->p, c1, n, 1, 1, 0, k, c.logN, c.d_bc, c.stream), "dyadic");
-    c.check(launch_ntt_inverse_add(c1, c0, x, n * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_inverse_add");
+    c.check(launch_ntt_inverse_add(c1, c0, 1, N, x, n * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_inverse_add");
 }
 void op_decrypt(Context &c, int chi, const u64 *ct, int n, u64 *plain) {
     u64 *x = c.ws_alloc((size_t)n * c.k * c.N);

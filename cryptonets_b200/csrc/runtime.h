@@ -53,6 +53,7 @@ struct Context {
     BehzConstF h_bf;
     BehzConstF *d_bf = nullptr;
     bool fp_elementwise = false; // every q_i, Bsk prime small enough for the FP64 element-wise kernels
+    bool lazy = false;           // ... and for lazy-double intermediates between the kernels of a multiply / key switch
     std::vector<NttTab> h_tabs;
     NttTab *d_tabs = nullptr;
     u64 *d_table_mem = nullptr;
@@ -132,7 +133,8 @@ void op_ntt(Context &c, const u64 *src, u64 *dst, int n_polys, int mod_base, int
 void op_multiply(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out3);
 void op_relinearize(Context &c, int ch, const u64 *in3, int n, u64 *out2);
 void op_multiply_relin(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out2);
-void op_key_switch(Context &c, const u64 *target, int n, const u64 *key, const DigitMap &dm, const u64 *base, u64 *out);
+void op_key_switch(Context &c, const u64 *target, size_t target_stride, int n, const u64 *key, const DigitMap &dm, const u64 *base,
+                   size_t base_stride, u64 *out);
 void op_apply_galois(Context &c, int ch, const u64 *in, int n, u64 elt, u64 *out);
 void op_rotate_rows(Context &c, int ch, const u64 *in, int n, int steps, u64 *out); // steps == 0 copies
 void op_rotate_columns(Context &c, int ch, const u64 *in, int n, u64 *out);

@@ -252,7 +252,7 @@ extern "C" int cnhe_raw_rotate_rows(cnhe_ctx *h, int channel, uint64_t in, int n
 extern "C" int cnhe_raw_behz_lift(cnhe_ctx *h, uint64_t in_cts, int n, uint64_t out) {
     API_BEGIN(h)
     if (c.fp_elementwise)
-        c.check(launch_behz_lift_fp(upload_ptrs(c, strided(in_cts, n, c.ct_words())), (u64 *)out, n, c.logN, c.d_bf, c.stream), "behz_lift_fp");
+        c.check(launch_behz_lift_fp(upload_ptrs(c, strided(in_cts, n, c.ct_words())), (u64 *)out, n, c.logN, &c.h_bf, 0, c.stream), "behz_lift_fp");
     else c.check(launch_behz_lift(upload_ptrs(c, strided(in_cts, n, c.ct_words())), (u64 *)out, n, c.logN, c.d_bc, c.stream), "behz_lift");
     API_END
 }
@@ -260,7 +260,7 @@ extern "C" int cnhe_raw_behz_floor(cnhe_ctx *h, int channel, uint64_t d, int n, 
     API_BEGIN(h)
     if (channel < 0 || channel >= c.P) fail("bad channel");
     c.set_channel(channel);
-    if (c.fp_elementwise) c.check(launch_behz_floor_fp((const u64 *)d, (u64 *)out3, n, c.ch[channel].t, c.logN, c.d_bf, c.stream), "behz_floor_fp");
+    if (c.fp_elementwise) c.check(launch_behz_floor_fp((const u64 *)d, (u64 *)out3, n, c.ch[channel].t, c.logN, &c.h_bf, 0, c.stream), "behz_floor_fp");
     else c.check(launch_behz_floor((const u64 *)d, (u64 *)out3, n, c.ch[channel].t, c.logN, c.d_bc, c.stream), "behz_floor");
     API_END
 }
@@ -536,6 +536,23 @@ extern "C" int cnhe_vec_destroy(cnhe_vec *v) {
         std::lock_guard<std::recursive_mutex> lock(v->ctx->mu);
         cudaSetDevice(v->ctx->device);
         delete v;
+    } catch (...) { return set_err(CNHE_ERR_INVALID, "destroy failed"); }
+    return CNHE_OK;
+}
+extern "C" int cnhe_vecs_destroy(cnhe_vec *const *vecs, int n) {
+    if (!vecs || n < 1) return CNHE_OK;
+    try {
+        Context *ctx = nullptr;
+        for (int i = 0; i < n && !ctx; i++)
+            if (vecs[i]) ctx = vecs[i]->ctx;
+        if (!ctx) return CNHE_OK;
+        std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+        cudaSetDevice(ctx->device);
+        for (int i = 0; i < n; i++)
+            if (vecs[i]) {
+                if (vecs[i]->ctx != ctx) return set_err(CNHE_ERR_INVALID, "vectors of different contexts");
+                delete vecs[i];
+            }
     } catch (...) { return set_err(CNHE_ERR_INVALID, "destroy failed"); }
     return CNHE_OK;
 }

@@ -32,11 +32,12 @@ def _vec_array(vecs):
 class Vec:
     """Owning handle of a cnhe_vec (== EncryptedSealBfvVector).  Dispose() mirrors IDisposable."""
 
-    __slots__ = ("eng", "h", "__weakref__")
+    __slots__ = ("eng", "h", "_m", "__weakref__")
 
     def __init__(self, eng, handle):
         self.eng = eng
         self.h = VECP(handle) if not isinstance(handle, VECP) else handle
+        self._m = None  # metadata cache: a cnhe_vec is immutable except for RegisterScale / RegisterDim
         eng._live.add(self)
 
     def dispose(self):
@@ -52,11 +53,14 @@ class Vec:
             pass
 
     def meta(self):
+        if self._m is not None:
+            return self._m
         dim, bs = C.c_uint64(), C.c_uint64()
         scale = C.c_double()
         fmt, enc, blocks = C.c_int(), C.c_int(), C.c_int()
         check(self.eng.L.cnhe_vec_meta(self.h, C.byref(dim), C.byref(scale), C.byref(fmt), C.byref(enc), C.byref(blocks), C.byref(bs)))
-        return dict(dim=dim.value, scale=scale.value, format=fmt.value, encrypted=bool(enc.value), blocks=blocks.value, block_size=bs.value)
+        self._m = dict(dim=dim.value, scale=scale.value, format=fmt.value, encrypted=bool(enc.value), blocks=blocks.value, block_size=bs.value)
+        return self._m
 
     dim = property(lambda s: s.meta()["dim"])
     scale = property(lambda s: s.meta()["scale"])
@@ -66,9 +70,11 @@ class Vec:
 
     def register_scale(self, scale):
         check(self.eng.L.cnhe_vec_register_scale(self.h, float(scale)))
+        self._m = None
 
     def register_dim(self, dim):
         check(self.eng.L.cnhe_vec_register_dim(self.h, int(dim)))
+        self._m = None
 
     def export_raw(self, channel=0, block=0):
         out = np.zeros(self.eng.ct_words, np.uint64)
@@ -183,6 +189,14 @@ class Engine:
         out = np.zeros(vec.dim, np.float64)
         check(self.L.cnhe_vec_decrypt(self.h, vec.h, out.ctypes.data_as(DBLP), out.size))
         return out
+
+    def dispose_many(self, vecs):
+        """Release a list of Vec handles with one ABI call."""
+        live = [v for v in vecs if v is not None and v.h]
+        if live and self.h:
+            check(self.L.cnhe_vecs_destroy(_vec_array(live), len(live)))
+        for v in live:
+            v.h = VECP(None)
 
     def decrypt_many(self, vecs):
         dim = vecs[0].dim

@@ -103,9 +103,11 @@ class B200BfvMatrix:
 
     def Dispose(self):
         if self.vectors is not None and not self.DataDisposedExternaly:
-            for v in self.vectors:
-                if v is not None:
-                    v.Dispose()
+            vs = [v for v in self.vectors if v is not None and v.vec is not None]
+            if vs:
+                self.eng.dispose_many([v.vec for v in vs])
+            for v in vs:
+                v.vec = None
         self.vectors = None
 
     def RegisterScale(self, scale):

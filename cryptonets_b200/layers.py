@@ -383,7 +383,9 @@ class PoolLayer(_ConvLayerBase):
         K = len(self.Offsets)
         M = maps * len(self.Corners)
         if self.Fused and hasattr(f, "ConvDenseLayer"):
-            gather = np.array([self._gather_row(c) for c in self.Corners] * maps, dtype=np.int32)  # k = map*corners + corner
+            if getattr(self, "_gather", None) is None:  # the topology is static: index table built once
+                self._gather = np.array([self._gather_row(c) for c in self.Corners] * maps, dtype=np.int32)  # k = map*corners + corner
+            gather = self._gather
             inputs = [m.GetColumn(i) for i in range(m.ColumnCount)]
             weights = [self.weightWindows[k // len(self.Corners)] for k in range(M)]
             bias = [self.biasVectors[k // len(self.Corners)] for k in range(M)]

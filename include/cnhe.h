@@ -86,6 +86,8 @@ int cnhe_vec_decrypt(cnhe_ctx *, const cnhe_vec *, double *out, uint64_t cap);
 int cnhe_vecs_decrypt(cnhe_ctx *, const cnhe_vec *const *vecs, int n, double *out /*[n][dim]*/, uint64_t dim);
 int cnhe_vec_copy(cnhe_ctx *, const cnhe_vec *, cnhe_vec **out); /* IFactory.CopyVector */
 int cnhe_vec_destroy(cnhe_vec *);
+/* Dispose of n vectors in one call (the Dispose loop of EncryptedSealBfvMatrix, EncryptedSealBfvMatrix.cs Dispose); null entries are skipped. */
+int cnhe_vecs_destroy(cnhe_vec *const *vecs, int n);
 int cnhe_vec_meta(const cnhe_vec *, uint64_t *dim, double *scale, int *format, int *is_encrypted, int *blocks, uint64_t *block_size);
 int cnhe_vec_register_scale(cnhe_vec *, double scale); /* IVector.RegisterScale */
 int cnhe_vec_register_dim(cnhe_vec *, uint64_t dim);   /* AtomicSealBfvVector.cs:316-319 */
