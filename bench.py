@@ -273,19 +273,35 @@ def run_b200(args):
     raw = eng.export_raw_many([v.vec for v in xm.vectors], host_in.data_ptr())
     del raw
 
-    def e2e_step():
-        vecs = eng.import_raw_many(host_in.data_ptr(), 784, 1, BATCH, 16.0)
-        m = B200BfvMatrix(f, [B200BfvVector(f, v) for v in vecs], EMatrixFormat.ColumnMajor, CopyVectors=False)
-        out = forward(layers, m)
-        m.Dispose()
-        eng.export_raw_many([v.vec for v in out.vectors], host_out.data_ptr())
-        out.Dispose()
+    def e2e_import():
+        vecs = eng.import_raw_many(host_in.data_ptr(), 784, 1, BATCH, 16.0)  # asynchronous: runs on the library's upload stream
+        return B200BfvMatrix(f, [B200BfvVector(f, v) for v in vecs], EMatrixFormat.ColumnMajor, CopyVectors=False)
 
-    e2e_step()
+    host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
+
+    def e2e_run(steps):
+        """`steps` batches: host ciphertexts in, score ciphertexts back on the host, pipelined one batch deep the way a serving loop
+        is: batch i+1 is uploaded and queued while batch i computes; the host only ever waits for batch i-1's scores."""
+        nxt = e2e_import()
+        pending = None
+        for s_ in range(steps):
+            cur = nxt
+            out = forward(layers, cur)
+            cur.Dispose()
+            ticket = eng.export_raw_many_async([v.vec for v in out.vectors], host_outs[s_ & 1].data_ptr())
+            out.Dispose()  # stream-ordered: released after the copies above
+            if s_ + 1 < steps:
+                nxt = e2e_import()
+            if pending is not None:
+                eng.export_wait(pending)
+            pending = ticket
+        eng.export_wait(pending)
+
+    eng.set_option("multi_stream", int(os.environ.get("CNHE_E2E_MULTI_STREAM", "0")))
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -303,7 +319,10 @@ def run_b200(args):
         roof = {"bound": "hbm", "kernel": "k_ntt_forward_fp / k_ntt_forward_digits_fp (N=8192), 16*N algorithmic bytes per transform", "achieved": achieved,
                 "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)",
-                "traffic": None, "launches_timed": fam["launches"], "share_of_step": fam["ms"] / ms if ms else None,
+                # ncu dram__bytes_read.sum + dram__bytes_write.sum of one k_ntt_forward_digits_fp launch (128-ciphertext wave = 16000
+                # transforms, 2.10 GB algorithmic at 16N per transform): the digit source is shared by 125 transforms through L2
+                "traffic": 1036.6e6, "traffic_source": "profiles/r01_square_path_ncu.txt (k_ntt_forward_digits_fp<13>, 42.4 MB read + 994.2 MB written per launch)",
+                "launches_timed": fam["launches"], "share_of_step": fam["ms"] / ms if ms else None,
                 "families_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}
         cpu_threads = os.cpu_count() or 1
         cpu_sec, cpu_desc = cpu_sample(primes, cpu_threads)

@@ -335,8 +335,8 @@ __device__ __forceinline__ double fwd_load_fp(const FwdSrc &s, int idx, double p
     }
     return u2d(v);
 }
-template <int LOGN, int S0, int R, bool FROM_G, int PASS, bool IN_F>
-__device__ __forceinline__ void fwd_pass_fp(double *sm, const double *twc, const FwdSrc &src, const NttTab &tb, int vt) {
+template <int LOGN, int S0, int R, bool FROM_G, int PASS, bool IN_F, int NV = 1>
+__device__ __forceinline__ void fwd_pass_fp(double *sm, const double *twc, const FwdSrc &src, const NttTab &tb, int vt, int vstride = 0) {
     constexpr int E = 1 << R, LG = LOGN - S0 - R;
     constexpr bool CACHED = (S0 + R) <= 9; // every twiddle index of this pass is below TWC
     const double p = tb.pd, pinv = tb.pinv;
@@ -385,34 +385,50 @@ __device__ __forceinline__ void fwd_pass_fp(double *sm, const double *twc, const
             for (int e = 0; e < E; e++) *reinterpret_cast<double2 *>(sm + swz(base + (e << LG))) = make_double2(x[e], y[e]);
         }
     } else {
-        const int c = vt & ((1 << LG) - 1), j = vt >> LG;
-        const int base = (j << (LG + R)) + c;
-        double x[E];
+        // NV independent groups per call (virtual threads vt, vt + vstride, ...): all their shared-memory loads are issued before
+        // the first butterfly, so one group's LDS latency hides under the other's arithmetic (the compiler cannot hoist them itself
+        // across the stores of the previous group)
+        double x[NV][E];
+        int jj[NV], bb[NV];
 #pragma unroll
-        for (int e = 0; e < E; e++) {
-            if constexpr (FROM_G) x[e] = fwd_load_fp<IN_F>(src, base + (e << LG), p, pinv);
-            else x[e] = sm[swz(base + (e << LG))];
+        for (int i = 0; i < NV; i++) {
+            const int v = vt + i * vstride;
+            const int c = v & ((1 << LG) - 1);
+            jj[i] = v >> LG;
+            bb[i] = (jj[i] << (LG + R)) + c;
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                if constexpr (FROM_G) x[i][e] = fwd_load_fp<IN_F>(src, bb[i] + (e << LG), p, pinv);
+                else x[i][e] = sm[swz(bb[i] + (e << LG))];
+            }
         }
         if (rc) {
 #pragma unroll
-            for (int e = 0; e < E; e++) x[e] = frecenter(x[e], p, pinv);
+            for (int i = 0; i < NV; i++)
+#pragma unroll
+                for (int e = 0; e < E; e++) x[i][e] = frecenter(x[i][e], p, pinv);
         }
 #pragma unroll
-        for (int u = 0; u < R; u++) {
-            const int h = E >> (u + 1);
+        for (int i = 0; i < NV; i++) {
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                if (e & h) continue;
-                const int ti = (1 << (S0 + u)) + (j << u) + (e >> (R - u));
-                const double w = CACHED ? twc[ti] : __ldg(tb.wd + ti);
-                const double t = fmodmul(x[e + h], w, p, pinv);
-                const double a = x[e];
-                x[e] = __dadd_rn(a, t);
-                x[e + h] = __dsub_rn(a, t);
+            for (int u = 0; u < R; u++) {
+                const int h = E >> (u + 1);
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    if (e & h) continue;
+                    const int ti = (1 << (S0 + u)) + (jj[i] << u) + (e >> (R - u));
+                    const double w = CACHED ? twc[ti] : __ldg(tb.wd + ti);
+                    const double t = fmodmul(x[i][e + h], w, p, pinv);
+                    const double a = x[i][e];
+                    x[i][e] = __dadd_rn(a, t);
+                    x[i][e + h] = __dsub_rn(a, t);
+                }
             }
         }
 #pragma unroll
-        for (int e = 0; e < E; e++) sm[swz(base + (e << LG))] = x[e];
+        for (int i = 0; i < NV; i++)
+#pragma unroll
+            for (int e = 0; e < E; e++) sm[swz(bb[i] + (e << LG))] = x[i][e];
     }
 }
 // Last forward pass: stages [LOGN-4, LOGN) on 16 consecutive words; canonical result goes straight to HBM.
@@ -514,7 +530,7 @@ __device__ __forceinline__ void fwd_body_fp(double *sm, const FwdSrc &src, u64 *
         CNHE_VTN(N / 16, (fwd_last_fp<12, 2, OUT_F>(sm, dst, tb, vt)));
     } else if constexpr (LOGN == 13) {
         CNHE_VTN(N / 32, (fwd_pass_fp<13, 0, 5, true, 0, IN_F>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (fwd_pass_fp<13, 5, 4, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads();
+        CNHE_VTN(N / 16, (fwd_pass_fp<13, 5, 4, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads(); // NV=2 (both groups' loads first) measured 5% slower
         CNHE_VTN(N / 16, (fwd_last_fp<13, 2, OUT_F>(sm, dst, tb, vt)));
     } else {
         CNHE_VTN(N / 32, (fwd_pass_fp<14, 0, 5, true, 0, IN_F>(sm, twc, src, tb, vt))); __syncthreads();
@@ -617,8 +633,8 @@ __device__ __forceinline__ void inv_first_fp(double *sm, const u64 *src, const N
 }
 // The last stage (one twiddle, iw[1]) carries N^-1: sums are multiplied by N^-1, differences by iw[1]*N^-1, so every output is a
 // fresh modular product in (-0.51p, 0.51p): written as is (OUT_F, lazy double) or sign-fixed on the integer pipe (canonical).
-template <int LOGN, int V0, int R, bool LAST, bool OUT_F>
-__device__ __forceinline__ void inv_pass_fp(double *sm, const double *twc, u64 *dst, const u64 *base_add, const NttTab &tb, int vt) {
+template <int LOGN, int V0, int R, bool LAST, bool OUT_F, int NV = 1>
+__device__ __forceinline__ void inv_pass_fp(double *sm, const double *twc, u64 *dst, const u64 *base_add, const NttTab &tb, int vt, int vstride = 0) {
     constexpr int N = 1 << LOGN, E = 1 << R;
     constexpr bool CACHED = (N >> V0) <= TWC; // stage v reads indices [N>>(v+1), N>>v)
     const double p = tb.pd, pinv = tb.pinv;
@@ -682,44 +698,56 @@ __device__ __forceinline__ void inv_pass_fp(double *sm, const double *twc, u64 *
             }
         }
     } else {
-        const int c = vt & ((1 << V0) - 1), j = vt >> V0;
-        const int base = (j << (V0 + R)) + c;
-        double x[E];
+        double x[NV][E];
+        int jj[NV], bb[NV];
 #pragma unroll
-        for (int e = 0; e < E; e++) x[e] = sm[swz(base + (e << V0))];
+        for (int i = 0; i < NV; i++) { // NV independent groups: loads first (see fwd_pass_fp)
+            const int v = vt + i * vstride;
+            const int c = v & ((1 << V0) - 1);
+            jj[i] = v >> V0;
+            bb[i] = (jj[i] << (V0 + R)) + c;
 #pragma unroll
-        for (int u = 0; u < R; u++) {
-            const int h = 1 << u;
-            const bool rc = (tb.inv_recenter >> (V0 + u)) & 1;
+            for (int e = 0; e < E; e++) x[i][e] = sm[swz(bb[i] + (e << V0))];
+        }
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                if (e & h) continue;
-                const int ti = (N >> (V0 + u + 1)) + (j << (R - 1 - u)) + (e >> (u + 1));
-                const double w = CACHED ? twc[ti] : __ldg(tb.iwd + ti);
-                const double a = x[e], bq = x[e + h];
-                if (LAST && u == R - 1) {
-                    x[e] = fmodmul(__dadd_rn(a, bq), tb.inv_n_d, p, pinv);
-                    x[e + h] = fmodmul(__dsub_rn(a, bq), tb.inv_n_w_d, p, pinv);
-                } else {
-                    x[e] = __dadd_rn(a, bq);
-                    x[e + h] = fmodmul(__dsub_rn(a, bq), w, p, pinv);
+        for (int i = 0; i < NV; i++) {
+#pragma unroll
+            for (int u = 0; u < R; u++) {
+                const int h = 1 << u;
+                const bool rc = (tb.inv_recenter >> (V0 + u)) & 1;
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    if (e & h) continue;
+                    const int ti = (N >> (V0 + u + 1)) + (jj[i] << (R - 1 - u)) + (e >> (u + 1));
+                    const double w = CACHED ? twc[ti] : __ldg(tb.iwd + ti);
+                    const double a = x[i][e], bq = x[i][e + h];
+                    if (LAST && u == R - 1) {
+                        x[i][e] = fmodmul(__dadd_rn(a, bq), tb.inv_n_d, p, pinv);
+                        x[i][e + h] = fmodmul(__dsub_rn(a, bq), tb.inv_n_w_d, p, pinv);
+                    } else {
+                        x[i][e] = __dadd_rn(a, bq);
+                        x[i][e + h] = fmodmul(__dsub_rn(a, bq), w, p, pinv);
+                    }
+                }
+                if (rc && !(LAST && u == R - 1)) {
+#pragma unroll
+                    for (int e = 0; e < E; e++)
+                        if (!(e & h)) x[i][e] = frecenter(x[i][e], p, pinv);
                 }
             }
-            if (rc && !(LAST && u == R - 1)) {
-#pragma unroll
-                for (int e = 0; e < E; e++)
-                    if (!(e & h)) x[e] = frecenter(x[e], p, pinv);
-            }
         }
-        if constexpr (LAST) {
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                const int idx = base + (e << V0);
-                dst[idx] = finish(x[e], idx);
+        for (int i = 0; i < NV; i++) {
+            if constexpr (LAST) {
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const int idx = bb[i] + (e << V0);
+                    dst[idx] = finish(x[i][e], idx);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; e++) sm[swz(bb[i] + (e << V0))] = x[i][e];
             }
-        } else {
-#pragma unroll
-            for (int e = 0; e < E; e++) sm[swz(base + (e << V0))] = x[e];
         }
     }
 }

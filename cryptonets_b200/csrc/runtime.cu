@@ -1,5 +1,7 @@
 // Host runtime of libcnhe (see runtime.h).  Product code: builds every table with hostmath.h, never touches oracle/.
 #include "runtime.h"
+#include <chrono>
+#include <cstdio>
 
 #include <algorithm>
 #include <cstdlib>
@@ -13,8 +15,31 @@ void cuda_check(cudaError_t e, const char *what) {
     if (e != cudaSuccess) throw Error(-2, std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
 }
 
+// CNHE_TRACE_SLOW=<ms>: report host-side calls that take longer than that (diagnosing launch-path stalls)
+static double trace_slow_ms() {
+    static const double v = getenv("CNHE_TRACE_SLOW") ? atof(getenv("CNHE_TRACE_SLOW")) : 0.0;
+    return v;
+}
+void Context::trace_gap(const char *what) {
+    static thread_local std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    const auto now = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(now - last).count();
+    if (ms > trace_ms && ms < 1000.0) fprintf(stderr, "[cnhe] %.2f ms of host time before/in launch of %s\n", ms, what);
+    last = now;
+}
 DevBuf::DevBuf(size_t w, cudaStream_t s) : words(w), stream(s) {
-    if (w) CNHE_CUDA(cudaMallocAsync((void **)&p, w * sizeof(u64), s));
+    if (!w) return;
+    if (trace_slow_ms() > 0) {
+        const auto t0 = std::chrono::steady_clock::now();
+        CNHE_CUDA(cudaMallocAsync((void **)&p, w * sizeof(u64), s));
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > trace_slow_ms()) fprintf(stderr, "[cnhe] slow cudaMallocAsync: %.2f ms for %.1f MB\n", ms, w * 8.0 / 1e6);
+        return;
+    }
+    CNHE_CUDA(cudaMallocAsync((void **)&p, w * sizeof(u64), s));
+}
+DevBuf::DevBuf(size_t w, cudaMemPool_t pool, cudaStream_t alloc_stream, cudaStream_t release_stream) : words(w), stream(release_stream) {
+    if (w) CNHE_CUDA(cudaMallocFromPoolAsync((void **)&p, w * sizeof(u64), pool, alloc_stream));
 }
 DevBuf::~DevBuf() {
     if (p) cudaFreeAsync(p, stream);
@@ -107,6 +132,7 @@ struct ProfScope {
 Context::~Context() {
     cudaSetDevice(device);
     for (cudaStream_t s : streams) cudaStreamSynchronize(s);
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
     g_temps.m.erase(this);
     ch.clear();
     if (d_bc) cudaFree(d_bc);
@@ -121,6 +147,10 @@ Context::~Context() {
     if (ev1) cudaEventDestroy(ev1);
     if (ev_join) cudaEventDestroy(ev_join);
     for (cudaStream_t s : streams) cudaStreamDestroy(s);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (upload_pool) cudaMemPoolDestroy(upload_pool);
+    if (ev_copy) cudaEventDestroy(ev_copy);
+    for (cudaEvent_t e : ev_export) cudaEventDestroy(e);
 }
 // free the temporaries of the previous operation (stream ordered, so kernels still in flight keep their memory)
 void ws_release_all(Context &c) {
@@ -279,6 +309,22 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
     c.streams.resize(P);
     for (int i = 0; i < P; i++) CNHE_CUDA(cudaStreamCreateWithFlags(&c.streams[i], cudaStreamNonBlocking));
     c.stream = c.streams[0];
+    c.trace_ms = trace_slow_ms();
+    CNHE_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    CNHE_CUDA(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
+    {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        CNHE_CUDA(cudaMemPoolCreate(&c.upload_pool, &props));
+        uint64_t thr = ~0ULL;
+        CNHE_CUDA(cudaMemPoolSetAttribute(c.upload_pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        int off = 0; // never make the upload stream wait for a release that is still queued behind another stream's kernels
+        CNHE_CUDA(cudaMemPoolSetAttribute(c.upload_pool, cudaMemPoolReuseAllowInternalDependencies, &off));
+    }
     CNHE_CUDA(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     CNHE_CUDA(cudaEventCreate(&c.ev0));
     CNHE_CUDA(cudaEventCreate(&c.ev1));

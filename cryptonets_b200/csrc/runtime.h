@@ -25,8 +25,9 @@ void cuda_check(cudaError_t e, const char *what);
 struct DevBuf {
     u64 *p = nullptr;
     size_t words = 0;
-    cudaStream_t stream = nullptr; // allocation (and release) stream: the channel the buffer belongs to
+    cudaStream_t stream = nullptr; // release stream: the channel the buffer belongs to (also the allocation stream unless given)
     DevBuf(size_t w, cudaStream_t s);
+    DevBuf(size_t w, cudaMemPool_t pool, cudaStream_t alloc_stream, cudaStream_t release_stream);
     ~DevBuf();
     DevBuf(const DevBuf &) = delete;
 };
@@ -71,6 +72,13 @@ struct Context {
     void set_channel(int ch) { stream = streams[multi_stream ? ch : 0]; }
     void join_streams(); // stream 0 waits for the tail of every other stream
     void fork_streams(); // every other stream waits for the tail of stream 0
+    // bulk ciphertext uploads (cnhe_vecs_import_raw) run on their own stream, fenced by events against the owning channel's stream:
+    // the upload of the next batch overlaps the kernels of the current one (double buffering across API calls)
+    cudaStream_t copy_stream = nullptr;
+    cudaMemPool_t upload_pool = nullptr; // its allocations never wait for a free queued behind kernels (no internal dependencies)
+    cudaEvent_t ev_copy = nullptr;
+    std::vector<cudaEvent_t> ev_export; // ring of 8 tickets x P channel events (cnhe_vecs_export_raw_async)
+    int export_next = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_join = nullptr;
     std::recursive_mutex mu;
     int chunk = 128;
@@ -104,7 +112,9 @@ struct Context {
     void ws_reserve(size_t words); // grow before taking pointers
     BufRef alloc(size_t words) { return std::make_shared<DevBuf>(words, stream); }
     void launched(int n = 1) { launches += n; }
-    void check(cudaError_t e, const char *what) { cuda_check(e, what); launched(); }
+    void check(cudaError_t e, const char *what) { cuda_check(e, what); launched(); if (trace_ms > 0) trace_gap(what); }
+    double trace_ms = 0; // CNHE_TRACE_SLOW: report host-side gaps between consecutive launches longer than this
+    void trace_gap(const char *what);
     void sync();
 };
 

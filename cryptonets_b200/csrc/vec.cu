@@ -607,11 +607,13 @@ extern "C" int cnhe_vecs_import_raw(cnhe_ctx *h, const uint64_t *src, int n, int
     std::vector<BufRef> big(c.P);
     for (int ch = 0; ch < c.P; ch++) {
         c.set_channel(ch);
-        big[ch] = c.alloc(words);
-        // one channel after the other over PCIe, each on its own stream: channel 0 computes while channel 1 is still uploading
-        if (ch > 0) CNHE_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
-        CNHE_CUDA(cudaMemcpyAsync(big[ch]->p, src + (size_t)ch * words, words * 8, cudaMemcpyHostToDevice, c.stream));
-        if (ch + 1 < c.P) CNHE_CUDA(cudaEventRecord(c.ev_join, c.stream));
+        // allocation and copy are ordered on the upload stream only (not behind the kernels already queued on the channel's stream):
+        // channels follow each other over PCIe, channel 0 computes while channel 1 is still uploading, and an import issued before
+        // the previous batch is exported overlaps that batch's kernels.  The buffer is released on the channel's stream, after its users.
+        big[ch] = std::make_shared<DevBuf>(words, c.upload_pool, c.copy_stream, c.stream);
+        CNHE_CUDA(cudaMemcpyAsync(big[ch]->p, src + (size_t)ch * words, words * 8, cudaMemcpyHostToDevice, c.copy_stream));
+        CNHE_CUDA(cudaEventRecord(c.ev_copy, c.copy_stream));
+        CNHE_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
     }
     for (int i = 0; i < n; i++) {
         cnhe_vec *o = new_vec(c, dim, scale, format, true, blocks);
@@ -637,6 +639,44 @@ extern "C" int cnhe_vecs_export_raw(cnhe_ctx *h, const cnhe_vec *const *vecs, in
     }
     c.sync();
     API_END
+}
+extern "C" int cnhe_vecs_export_raw_async(cnhe_ctx *h, const cnhe_vec *const *vecs, int n, uint64_t *dst, size_t cap, int *ticket) {
+    API_BEGIN(h)
+    if (n < 1 || !dst || !ticket) fail("bad arguments");
+    const int blocks = vecs[0]->blocks;
+    const size_t per = (size_t)blocks * c.ct_words();
+    if (cap < (size_t)c.P * n * per) fail("destination too small");
+    for (int i = 0; i < n; i++) {
+        same_ctx(c, vecs[i]);
+        if (!vecs[i]->enc || vecs[i]->blocks != blocks) fail("expecting encrypted vectors with equal block counts");
+    }
+    if (c.ev_export.empty()) {
+        c.ev_export.resize((size_t)8 * c.P);
+        for (cudaEvent_t &e : c.ev_export) CNHE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const int t = c.export_next;
+    c.export_next = (c.export_next + 1) & 7;
+    for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
+        for (int i = 0; i < n; i++)
+            CNHE_CUDA(cudaMemcpyAsync(dst + ((size_t)ch * n + i) * per, vecs[i]->ptr(ch), per * 8, cudaMemcpyDeviceToHost, c.stream));
+        CNHE_CUDA(cudaEventRecord(c.ev_export[(size_t)t * c.P + ch], c.stream));
+    }
+    *ticket = t;
+    API_END
+}
+extern "C" int cnhe_export_wait(cnhe_ctx *h, int ticket) {
+    if (!h) return set_err(CNHE_ERR_INVALID, "null context");
+    Context &c = *h->c;
+    try {
+        if (ticket < 0 || ticket > 7 || c.ev_export.empty()) fail("bad ticket");
+        // no context lock: waiting must not block another thread that is queueing the next batch
+        CNHE_CUDA(cudaSetDevice(c.device));
+        for (int ch = 0; ch < c.P; ch++) CNHE_CUDA(cudaEventSynchronize(c.ev_export[(size_t)ticket * c.P + ch]));
+    }
+    catch (const Error &e) { return set_err(e.code, e.what()); }
+    catch (const std::exception &e) { return set_err(CNHE_ERR_INVALID, e.what()); }
+    return CNHE_OK;
 }
 extern "C" int cnhe_vec_device_ptr(const cnhe_vec *v, int channel, uint64_t *dptr, size_t *words) {
     if (!v || channel < 0 || channel >= v->ctx->P) return set_err(CNHE_ERR_INVALID, "bad arguments");

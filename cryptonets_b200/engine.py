@@ -221,7 +221,7 @@ class Engine:
             src = _p(a)
         out = (VECP * n)()
         check(self.L.cnhe_vecs_import_raw(self.h, src, n, blocks, int(dim), float(scale), fmt, out))
-        return [Vec(self, out[i]) for i in range(n)]
+        return self._wrap_many(out, n)
 
     def export_raw_many(self, vecs, host_ptr=None):
         n, blocks = len(vecs), vecs[0].blocks
@@ -232,6 +232,16 @@ class Engine:
             return a.reshape(self.P, n, blocks, self.ct_words)
         check(self.L.cnhe_vecs_export_raw(self.h, _vec_array(vecs), n, C.cast(host_ptr, U64P), words))
         return None
+
+    def export_raw_many_async(self, vecs, host_ptr):
+        """Queue the device-to-host copies behind the producing kernels; returns a ticket for export_wait().  `host_ptr`: pinned memory."""
+        n, blocks = len(vecs), vecs[0].blocks
+        t = C.c_int()
+        check(self.L.cnhe_vecs_export_raw_async(self.h, _vec_array(vecs), n, C.cast(host_ptr, U64P), self.P * n * blocks * self.ct_words, C.byref(t)))
+        return t.value
+
+    def export_wait(self, ticket):
+        check(self.L.cnhe_export_wait(self.h, int(ticket)))
 
     def dev_copy(self, dst, src, words):
         check(self.L.cnhe_dev_copy(self.h, int(dst), int(src), int(words)))
@@ -332,13 +342,22 @@ class Engine:
         check(self.L.cnhe_layer_conv_dense(
             self.h, _vec_array(inputs), len(inputs), None if g is None else g.ctypes.data_as(C.POINTER(C.c_int32)), _vec_array(weights),
             None if bias is None else _vec_array(bias), M, K, out))
-        return [Vec(self, out[i]) for i in range(M)]
+        return self._wrap_many(out, M)
+
+    def _wrap_many(self, out, n):
+        """Vec handles for the n outputs of one batched call: they share dim/scale/format/blocks, so the metadata is queried once."""
+        vecs = [Vec(self, out[i]) for i in range(n)]
+        if n > 1:
+            m = vecs[0].meta()
+            for v in vecs[1:]:
+                v._m = m
+        return vecs
 
     def layer_square(self, inputs):
         n = len(inputs)
         out = (VECP * n)()
         check(self.L.cnhe_layer_square(self.h, _vec_array(inputs), n, out))
-        return [Vec(self, out[i]) for i in range(n)]
+        return self._wrap_many(out, n)
 
     # ---- raw device arrays (micro-benchmarks, kernel parity tests)
     def dev_alloc(self, words):

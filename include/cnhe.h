@@ -99,6 +99,11 @@ int cnhe_vec_import_raw(cnhe_ctx *, const uint64_t *src /*[P][blocks][2kN]*/, in
  * host buffer may be pinned (cudaHostAlloc / torch pin_memory) for full PCIe rate. */
 int cnhe_vecs_import_raw(cnhe_ctx *, const uint64_t *src, int n, int blocks, uint64_t dim, double scale, int format, cnhe_vec **out);
 int cnhe_vecs_export_raw(cnhe_ctx *, const cnhe_vec *const *vecs, int n, uint64_t *dst, size_t cap_words);
+/* Asynchronous form for a pipelined serving loop: the device-to-host copies are queued behind the kernels that produce the vectors
+ * and the call returns at once with a ticket; cnhe_export_wait(ticket) blocks until exactly those copies have landed in `dst`
+ * (pinned host memory), without waiting for work queued afterwards.  Up to 8 tickets may be outstanding. */
+int cnhe_vecs_export_raw_async(cnhe_ctx *, const cnhe_vec *const *vecs, int n, uint64_t *dst, size_t cap_words, int *ticket);
+int cnhe_export_wait(cnhe_ctx *, int ticket);
 /* device pointer of a channel's ciphertext blocks (for NCCL gathers through torch; plumbing only) */
 int cnhe_vec_device_ptr(const cnhe_vec *, int channel, uint64_t *dptr, size_t *words);
 int cnhe_noise_budget(cnhe_ctx *, const cnhe_vec *, int channel, int block, int *bits); /* CryptoTracker.cs:41-52 */
