@@ -520,3 +520,329 @@ class LLDenseLayer(BaseLayer):
         if self.BiasVector is not None:
             self.BiasVector.Dispose()
         self.WeightsMatrix = self.BiasVector = None
+
+
+class LLSingleLineReader(MatrixSource):
+    """One image per GetNext() as a single column vector (`LLSingleLineReader.cs`; TSV parsing replaced by an in-memory array)."""
+
+    def __init__(self, features, Scale, NormalizationFactor):
+        super().__init__(features, Scale, NormalizationFactor, MaxSlots=1)
+
+    def GetNext(self):
+        if self.pos >= len(self.features):
+            self.pos = 0
+        f = self.features[self.pos] * self.NormalizationFactor
+        self.pos += 1
+        return RawMatrix(f.reshape(-1, 1), self.Scale, EMatrixFormat.ColumnMajor, 0)
+
+
+class LLDuplicateLayer(BaseLayer):
+    """`NeuralNetworks/LLDuplicateLayer.cs:8-29`: every column is replicated `Count` times at power-of-two strides."""
+
+    Count = 1
+
+    def Apply(self, m):
+        env = self.Factory.AllocateComputationEnv()
+        cols = [m.GetColumn(i).Duplicate(int(self.Count), env) for i in range(m.ColumnCount)]
+        return self.Factory.GetMatrix(cols, m.Format, CopyVectors=False)
+
+    def OutputDimension(self):
+        shift, dim = 1, self.Source.OutputDimension()
+        while shift < dim:
+            shift *= 2
+        return shift * int(self.Count)
+
+
+class LLInterleaveLayer(BaseLayer):
+    """`NeuralNetworks/LLInterleaveLayer.cs:12-56`: keep the selected slots of every column (mask), then pack the columns into one
+    vector, column c shifted by c*Shift slots."""
+
+    def __init__(self, **kw):
+        self.Shift = 0
+        self.SelectedIndices = None
+        self.InputGrossDimension = -1
+        self.mask = None
+        super().__init__(**kw)
+
+    def Prepare(self):
+        if self.mask is not None:
+            return
+        if self.InputGrossDimension < 0:
+            self.InputGrossDimension = max(self.SelectedIndices) + 1
+        hot = np.zeros(self.InputGrossDimension)
+        hot[list(self.SelectedIndices)] = 1.0
+        self.mask = self.Factory.GetPlainVector(hot, EVectorFormat.dense, 1)
+
+    def Apply(self, m):
+        f = self.Factory
+        env = f.AllocateComputationEnv()
+        clean = [m.GetColumn(i).PointwiseMultiply(self.mask, env) for i in range(m.ColumnCount)]
+        cm = f.GetMatrix(clean, EMatrixFormat.ColumnMajor, CopyVectors=False)
+        packed = cm.Interleave(self.Shift, env)
+        cm.Dispose()
+        return f.GetMatrix([packed], EMatrixFormat.ColumnMajor, CopyVectors=False)
+
+    def OutputDimension(self):
+        return self.InputGrossDimension
+
+    def Dispose(self):
+        if self.mask is not None:
+            self.mask.Dispose()
+        self.mask = None
+
+
+class LLPackedDenseLayer(BaseLayer):
+    """`NeuralNetworks/LLPackedDenseLayer.cs:10-76`: `PackingCount` weight rows share one plaintext, each in its own
+    `PackingShift`-slot segment; one multiply + partial rotate-and-sum evaluates them all against the duplicated input, the
+    result of segment c landing in its last slot (where the bias sits)."""
+
+    def __init__(self, **kw):
+        self.Weights = None
+        self.Bias = None
+        self.WeightsScale = 1.0
+        self.PackingCount = 1
+        self.PackingShift = 0
+        self.WeightsMatrix = None
+        self.BiasMatrix = None
+        super().__init__(**kw)
+
+    def GetOutputScale(self):
+        return self.WeightsScale * self.Source.GetOutputScale()
+
+    def Prepare(self):
+        if self.layerPrepared:
+            return
+        maps = len(self.Bias)
+        w = np.asarray(self.Weights, dtype=np.float64).reshape(maps, -1)
+        pc, ps = int(self.PackingCount), int(self.PackingShift)
+        rows = (maps + pc - 1) // pc
+        stacked = np.zeros((rows, pc * ps))
+        bias = np.zeros((rows, pc * ps))
+        for i in range(maps):
+            row, col = divmod(i, pc)
+            stacked[row, col * ps: col * ps + w.shape[1]] = w[i]
+            bias[row, (col + 1) * ps - 1] = self.Bias[i]
+        f = self.Factory
+        self.BiasMatrix = f.GetPlainMatrix(bias, EMatrixFormat.RowMajor, self.Source.GetOutputScale() * self.WeightsScale)
+        self.WeightsMatrix = f.GetPlainMatrix(stacked, EMatrixFormat.RowMajor, self.WeightsScale)
+        self.layerPrepared = True
+
+    def OutputDimension(self):
+        return len(self.Bias)
+
+    def Apply(self, m):
+        if m.ColumnCount > 1:
+            raise Exception("Expecting only one column")
+        env = self.Factory.AllocateComputationEnv()
+        v = m.GetColumn(0)
+        res = []
+        for k in range(self.WeightsMatrix.RowCount):
+            mul = self.WeightsMatrix.GetRow(k).DotProduct(v, env, length=int(self.PackingShift))
+            res.append(mul.Add(self.BiasMatrix.GetRow(k), env))
+            mul.Dispose()
+        return self.Factory.GetMatrix(res, EMatrixFormat.ColumnMajor, CopyVectors=False)
+
+    def Dispose(self):
+        for mat in (self.WeightsMatrix, self.BiasMatrix):
+            if mat is not None:
+                mat.Dispose()
+        self.WeightsMatrix = self.BiasMatrix = None
+
+
+class LLInterleavedDenseLayer(BaseLayer):
+    """`NeuralNetworks/LLInterleavedDenseLayer.cs:12-77`: dense layer whose inputs sit at the slots an LLInterleaveLayer left them in."""
+
+    def __init__(self, **kw):
+        self.Weights = None
+        self.Bias = None
+        self.WeightsScale = 1
+        self.Shift = 0
+        self.SelectedIndices = None
+        self.WeightsMatrix = None
+        self.BiasVector = None
+        super().__init__(**kw)
+
+    def GetOutputScale(self):
+        return self.Source.GetOutputScale() * self.WeightsScale
+
+    def OutputDimension(self):
+        return len(self.Bias)
+
+    def _targets(self, count):
+        out, offset = [], 0
+        while count > 0:
+            for s in self.SelectedIndices:
+                if count == 0:
+                    break
+                out.append(s + offset)
+                count -= 1
+            offset += self.Shift
+        return out
+
+    def Prepare(self):
+        if self.layerPrepared:
+            return
+        rows = len(self.Bias)
+        small = np.asarray(self.Weights, dtype=np.float64).reshape(rows, -1)
+        big = np.zeros((rows, self.Source.OutputDimension()))
+        for i, t in enumerate(self._targets(small.shape[1])):
+            big[:, t] = small[:, i]
+        f = self.Factory
+        self.BiasVector = f.GetPlainVector(np.asarray(self.Bias, dtype=np.float64), EVectorFormat.sparse, self.GetOutputScale())
+        self.WeightsMatrix = f.GetPlainMatrix(big, EMatrixFormat.RowMajor, self.WeightsScale)
+        self.layerPrepared = True
+
+    def Apply(self, m):
+        env = self.Factory.AllocateComputationEnv()
+        mul = self.WeightsMatrix.Mul(m.GetColumn(0), env)
+        v = mul.Add(self.BiasVector, env)
+        mul.Dispose()
+        return self.Factory.GetMatrix([v], EMatrixFormat.ColumnMajor, CopyVectors=False)
+
+    def Dispose(self):
+        if self.WeightsMatrix is not None:
+            self.WeightsMatrix.Dispose()
+        if self.BiasVector is not None:
+            self.BiasVector.Dispose()
+        self.WeightsMatrix = self.BiasVector = None
+
+
+class LLPreConvLayer(BaseLayer):
+    """`NeuralNetworks/LLPreConvLayer.cs:13-170`: builds the im2col columns of a convolution *homomorphically* from one encrypted
+    image vector.  Column i (kernel offset i) is a permutation of the image: for every block of output rows, mask the pixels that
+    offset touches and rotate them so that output position `CornersMap[j]` holds corner j's pixel -- the same map for every offset,
+    so the following LLPoolLayer is a plain column-wise weighted sum (with `HotIndices` marking the live slots for the bias)."""
+
+    def __init__(self, **kw):
+        self.ce = ConvolutionEngine()
+        self.UseAxisForBlocks = None
+        self.outputDim = -1
+        self.shifts = None
+        self.masks = None
+        self.CornersMap = None
+        self._hot = None
+        super().__init__(**kw)
+
+    InputShape = property(lambda s: s.ce.InputShape, lambda s, v: setattr(s.ce, "InputShape", list(v)))
+    KernelShape = property(lambda s: s.ce.KernelShape, lambda s, v: setattr(s.ce, "KernelShape", list(v)))
+    Stride = property(lambda s: s.ce.Stride, lambda s, v: setattr(s.ce, "Stride", list(v)))
+    Padding = property(lambda s: s.ce.Padding, lambda s, v: setattr(s.ce, "Padding", list(v)))
+    Upperpadding = property(lambda s: s.ce.Upperpadding, lambda s, v: setattr(s.ce, "Upperpadding", list(v)))
+    Lowerpadding = property(lambda s: s.ce.Lowerpadding, lambda s, v: setattr(s.ce, "Lowerpadding", list(v)))
+
+    @property
+    def HotIndices(self):
+        if not self.layerPrepared:
+            self.Prepare()
+        return self._hot
+
+    def _block_offsets(self):
+        """Offsets of the stride cosets used as blocks: an odometer over the flagged axes, axis 0 fastest (:31-59)."""
+        n = len(self.Stride)
+        step = [1] * n
+        for i in range(1, n):
+            step[i] = step[i - 1] * self.InputShape[i - 1]
+        block, offset, out = [0] * n, 0, []
+        while True:
+            out.append(offset)
+            advanced = False
+            for i in range(n):
+                if not self.UseAxisForBlocks[i]:
+                    continue
+                block[i] += 1
+                offset += step[i]
+                if block[i] < self.Stride[i]:
+                    advanced = True
+                    break
+                offset -= block[i] * step[i]
+                block[i] = 0
+            if not advanced:
+                return out
+
+    def Prepare(self):
+        if self.layerPrepared:
+            return
+        ce = self.ce
+        ce.Prepare()
+        if self.UseAxisForBlocks is None:
+            self.UseAxisForBlocks = [True] * len(self.InputShape)
+        dim = int(np.prod(ce.InputShape))
+        row = dim // ce.InputShape[0]
+        boff = self._block_offsets()
+        nb = len(boff)
+        first_axis = sorted({c[0] for c in ce.Corners})
+        small = len(first_axis) // nb
+        large = -(-len(first_axis) // nb)
+        n_large = len(first_axis) - nb * small
+        cmap = [-1] * len(ce.Corners)
+        f = self.Factory
+        self.masks, self.shifts = [], []
+        for off in ce.Offsets:
+            sh = [0] * nb
+            for j in range(nb):
+                size = small if j > n_large else large  # (sic) `>`: block n_large still counts as large in the shift recurrence (:99)
+                sh[j] = ce.Location(None, off, ce.InputShape) if j == 0 else sh[j - 1] + boff[j - 1] - boff[j] + size * ce.Stride[0] * row
+            sel = [[] for _ in range(nb)]
+            for j, corner in enumerate(ce.Corners):
+                loc = ce.Location(corner, off, ce.InputShape)
+                cid = (corner[0] - ce.Corners[0][0]) // ce.Stride[0]
+                block = cid // large if cid < large * n_large else n_large + (cid - large * n_large) // small
+                if loc >= 0:
+                    sel[block].append(loc)
+                    where = loc - sh[block]
+                    if cmap[j] >= 0 and cmap[j] != where:
+                        raise Exception("Internal Error")
+                    cmap[j] = where
+            mk = []
+            for s in sel:
+                if s:
+                    hot = np.zeros(dim)
+                    hot[s] = 1.0
+                    mk.append(f.GetPlainVector(hot, EVectorFormat.dense, 1))
+                else:
+                    mk.append(None)
+            self.masks.append(mk)
+            self.shifts.append(sh)
+        large_max = 0 if n_large == 0 else row * (1 + ce.Stride[0] * (large - 1)) + boff[n_large - 1]
+        small_max = row * (1 + ce.Stride[0] * (small - 1)) + boff[-1]
+        self.outputDim = max(large_max, small_max)
+        self.CornersMap = cmap
+        self._hot = np.zeros(self.outputDim)
+        self._hot[cmap] = 1.0
+        self.layerPrepared = True
+
+    def Apply(self, m):
+        if m.ColumnCount != 1:
+            raise Exception("Expecting only a single column")
+        if not self.layerPrepared:
+            self.Prepare()
+        env = self.Factory.AllocateComputationEnv()
+        v = m.GetColumn(0)
+        cols = [v.Permute(self.masks[k], self.shifts[k], self.outputDim, env) for k in range(len(self.masks))]
+        return self.Factory.GetMatrix(cols, EMatrixFormat.ColumnMajor, CopyVectors=False)
+
+    def OutputDimension(self):
+        if not self.layerPrepared:
+            self.Prepare()
+        return self.outputDim
+
+    def RearrangeWeights(self, weights):
+        """Weights of the next dense layer re-indexed from corner order to the slot order this layer produces (:154-168)."""
+        if not self.layerPrepared:
+            self.Prepare()
+        weights = np.asarray(weights, dtype=np.float64)
+        nc = len(self.ce.Corners)
+        maps = len(weights) // nc
+        out = np.zeros(maps * self.outputDim)
+        for i in range(maps):
+            for j in range(nc):
+                out[i * self.outputDim + self.CornersMap[j]] = weights[j + i * nc]
+        return out
+
+    def Dispose(self):
+        if self.masks:
+            for mk in self.masks:
+                for v in mk:
+                    if v is not None:
+                        v.Dispose()
+        self.masks = None

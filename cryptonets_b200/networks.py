@@ -8,12 +8,15 @@ import os
 
 import numpy as np
 
-from .layers import (EncryptLayer, LLConvReader, LLDenseLayer, LLPoolLayer, LLVectorizeLayer, MatrixSource, PoolLayer, SquareActivation,
-                     TimingLayer)
+from .layers import (EncryptLayer, LLConvReader, LLDenseLayer, LLDuplicateLayer, LLInterleavedDenseLayer, LLInterleaveLayer,
+                     LLPackedDenseLayer, LLPoolLayer, LLPreConvLayer, LLSingleLineReader, LLVectorizeLayer, MatrixSource, PoolLayer,
+                     SquareActivation, TimingLayer)
 
 _GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 CRYPTONETS_PRIMES = [549764251649, 549764284417]  # CryptoNets.cs:17
 LOLA_SMALL_PRIMES = [2277377, 2424833]            # LoLaCryptonets.cs:285
+LOLA_PRIMES = [557057, 638977, 737281, 786433]    # LoLaCryptonets.cs:208 (N=8192, default decomposition bit counts)
+LOLA_DENSE_PRIMES = [34359771137, 34360754177]    # LoLaCryptonets.cs:123 (N=16384, w=60, SmallModulusCount=7)
 
 
 def load_weights(name, shapes, seed=0):
@@ -81,3 +84,48 @@ def lola_small(factory, images, weights=None):
     act3 = SquareActivation(Source=vec2)
     dense4 = LLDenseLayer(Source=act3, Bias=w["Biases_1"], Weights=w["Weights_1"], WeightsScale=weightscale)
     return dense4, reader
+
+
+def lola(factory, images, weights=None):
+    """LoLa (`LowLatencyCryptoNets/LoLaCryptonets.cs:203-276`): im2col input, 8-way packed dense layer, interleave, square, dense."""
+    w = weights or cryptonets_weights()
+    weightscale = 32
+    reader = LLConvReader(images, Scale=16.0, NormalizationFactor=1.0 / 256.0, InputShape=[28, 28], KernelShape=[5, 5], Stride=[2, 2],
+                          Upperpadding=[1, 1])
+    enc = EncryptLayer(Source=reader, Factory=factory)
+    conv1 = LLPoolLayer(Source=enc, InputShape=[28, 28], KernelShape=[5, 5], Upperpadding=[1, 1], Stride=[2, 2], MapCount=[5, 1],
+                        WeightsScale=weightscale, Weights=w["Weights_0"])
+    vec2 = LLVectorizeLayer(Source=conv1)
+    act3 = SquareActivation(Source=vec2)
+    dup4 = LLDuplicateLayer(Source=act3, Count=8)
+    dense5 = LLPackedDenseLayer(Source=dup4, Weights=transpose(w["Weights_1"], 5 * 13 * 13, 100), Bias=w["Biases_2"],
+                                WeightsScale=weightscale * weightscale, PackingCount=8, PackingShift=1024)
+    sel = [1023 + i * 1024 for i in range(8)]
+    inter6 = LLInterleaveLayer(Source=dense5, Shift=-1, SelectedIndices=sel)
+    act7 = SquareActivation(Source=inter6)
+    dense8 = LLInterleavedDenseLayer(Source=act7, Weights=w["Weights_3"], Bias=w["Biases_3"], WeightsScale=weightscale, Shift=-1,
+                                     SelectedIndices=sel)
+    return dense8, reader
+
+
+def lola_dense(factory, images, weights=None):
+    """LoLa-Dense (`LoLaCryptonets.cs:116-201`): the image arrives as ONE ciphertext; the im2col columns are built homomorphically
+    (LLPreConvLayer), 16-way packed dense layer, square, interleave, dense."""
+    w = weights or cryptonets_weights()
+    weightscale = 32
+    reader = LLSingleLineReader(images, Scale=16.0, NormalizationFactor=1.0 / 256.0)
+    enc = EncryptLayer(Source=reader, Factory=factory)
+    pre1 = LLPreConvLayer(Source=enc, InputShape=[28, 28], KernelShape=[5, 5], Upperpadding=[1, 1], Stride=[2, 2], UseAxisForBlocks=[True, True])
+    conv2 = LLPoolLayer(Source=pre1, InputShape=[28, 28], KernelShape=[5, 5], Upperpadding=[1, 1], Stride=[2, 2], MapCount=[5, 1],
+                        WeightsScale=weightscale, Weights=w["Weights_0"], HotIndices=pre1.HotIndices)
+    vec3 = LLVectorizeLayer(Source=conv2)
+    act4 = SquareActivation(Source=vec3)
+    dup5 = LLDuplicateLayer(Source=act4, Count=16)
+    dense6 = LLPackedDenseLayer(Source=dup5, Weights=pre1.RearrangeWeights(transpose(w["Weights_1"], 5 * 13 * 13, 100)), Bias=w["Biases_2"],
+                                WeightsScale=weightscale * weightscale, PackingCount=16, PackingShift=1024)
+    act7 = SquareActivation(Source=dense6)
+    sel = [1023 + i * 1024 for i in range(16)]
+    inter8 = LLInterleaveLayer(Source=act7, Shift=-1, SelectedIndices=sel)
+    dense9 = LLInterleavedDenseLayer(Source=inter8, Weights=w["Weights_3"], Bias=w["Biases_3"], WeightsScale=weightscale, Shift=-1,
+                                     SelectedIndices=sel)
+    return dense9, reader

@@ -184,3 +184,68 @@ def test_lola_small_scores_equal_raw_backend(small_modulus_count):
             assert 10 <= budget <= 30  # what is left for the dense layer: not enough for its 845-slot MultiplyPlain
     finally:
         f.Dispose()
+
+
+def _compare_layerwise(net, raw_net, rd, rrd, upto=None):
+    """Apply the two layer chains side by side; returns the last pair of matrices.  Layers whose output carries unselected slots
+    (packed dense: partial sums outside the segment ends) are compared only through the layers that consume them."""
+    ma, mb = rd.GetNext(), rrd.GetNext()
+    pairs = list(zip(_layer_chain(net), _layer_chain(raw_net)))[1:]  # [0] is the reader
+    for A, B in pairs[:upto]:
+        ma, mb = A.Apply(ma), B.Apply(mb)
+    return ma, mb
+
+
+def test_lola_scores_equal_raw_backend():
+    """LoLa (LoLaCryptonets.cs:203-276; 4 plaintext primes, N=8192, default moduli and decomposition): LLPoolLayer, LLVectorizeLayer,
+    square, LLDuplicateLayer, LLPackedDenseLayer, LLInterleaveLayer, square, LLInterleavedDenseLayer on one encrypted image."""
+    from cryptonets_b200.he import B200BfvFactory
+    from cryptonets_b200.networks import LOLA_PRIMES, lola, synthetic_mnist
+    from cryptonets_b200.raw import RawFactory
+    f = B200BfvFactory(LOLA_PRIMES, 8192, seed=5)
+    try:
+        imgs = synthetic_mnist(2, seed=6)
+        net, _ = lola(f, imgs)
+        net.PrepareNetwork()
+        raw_net, _ = lola(RawFactory(8192), imgs)
+        raw_net.PrepareNetwork()
+        for _ in range(2):
+            out = net.GetNext()
+            budget = min(f.engine.noise_budget(v.vec, ch, 0) for v in out.vectors for ch in range(f.engine.P))
+            got = np.asarray(out.Decrypt()).reshape(-1)
+            want = np.asarray(raw_net.GetNext().Decrypt()).reshape(-1)
+            assert budget > 0
+            assert np.allclose(got, want, rtol=1e-9, atol=1e-9) and got.argmax() == want.argmax()
+    finally:
+        f.Dispose()
+
+
+@pytest.mark.parametrize("small_modulus_count", [8, 7])
+def test_lola_dense_scores_equal_raw_backend(small_modulus_count):
+    """LoLa-Dense (LoLaCryptonets.cs:116-201; N=16384, w=60): the im2col columns are built homomorphically by LLPreConvLayer.
+    With the reference's SmallModulusCount=7 (341-bit q, 35-bit t) a SEAL-3.2-faithful BFV starts at 270 bits of budget (the
+    Delta*m rounding term of 3.2's encryption is ~t/2) and the nine plaintext/ciphertext multiplications of the topology need
+    ~283: layers are compared through the interleave layer (36 bits left), the last dense layer cannot decrypt.  With one more
+    prime the whole network equals the Raw backend."""
+    from cryptonets_b200.he import B200BfvFactory
+    from cryptonets_b200.networks import LOLA_DENSE_PRIMES, lola_dense, synthetic_mnist
+    from cryptonets_b200.raw import RawFactory
+    f = B200BfvFactory(LOLA_DENSE_PRIMES, 16384, DecompositionBitCount=60, GaloisDecompositionBitCount=60,
+                       SmallModulusCount=small_modulus_count, seed=5)
+    try:
+        imgs = synthetic_mnist(1, seed=6)
+        net, rd = lola_dense(f, imgs)
+        net.PrepareNetwork()
+        raw_net, rrd = lola_dense(RawFactory(16384), imgs)
+        raw_net.PrepareNetwork()
+        if small_modulus_count == 8:
+            got = np.asarray(net.GetNext().Decrypt()).reshape(-1)
+            want = np.asarray(raw_net.GetNext().Decrypt()).reshape(-1)
+            assert np.allclose(got, want, rtol=1e-9, atol=1e-9) and got.argmax() == want.argmax()
+        else:
+            ma, mb = _compare_layerwise(net, raw_net, rd, rrd, upto=-1)  # everything but the last dense layer
+            assert np.allclose(np.asarray(ma.Decrypt()), np.asarray(mb.Decrypt()), rtol=1e-9, atol=1e-9)
+            budget = min(f.engine.noise_budget(v.vec, ch, 0) for v in ma.vectors for ch in range(2))
+            assert 20 <= budget <= 50
+    finally:
+        f.Dispose()

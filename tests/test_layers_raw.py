@@ -94,3 +94,84 @@ def test_lola_small_topology_on_raw_backend():
     w1 = np.rint(w["Weights_1"] * 64).reshape(10, 845)
     want = (w1 @ a + np.rint(w["Biases_1"] * s * 64)) / (s * 64)
     assert np.allclose(got, want, rtol=1e-12, atol=0)
+
+
+def test_lola_and_lola_dense_topologies_equal_cryptonets_on_raw_backend():
+    """LoLa (LoLaCryptonets.cs:203-276) and LoLa-Dense (:116-201) evaluate the SAME model as CryptoNets (same shipped weights) through
+    completely different data flows (im2col + packed dense + interleave; LoLa-Dense additionally builds the im2col columns with
+    LLPreConvLayer permutations): all three must give the same scores -- which exercises LLDuplicateLayer, LLPackedDenseLayer,
+    LLInterleaveLayer, LLInterleavedDenseLayer, LLPreConvLayer.RearrangeWeights/HotIndices end to end."""
+    from cryptonets_b200.networks import lola, lola_dense
+    imgs = synthetic_mnist(3, seed=11)
+    w = cryptonets_weights()
+    want = _numpy_cryptonets(imgs, w)
+    for build, block in ((lola, 8192), (lola_dense, 16384)):
+        net, _ = build(RawFactory(block), imgs, weights=w)
+        net.PrepareNetwork()
+        for i in range(len(imgs)):
+            got = np.asarray(net.GetNext().Decrypt(None)).reshape(-1)
+            assert got.shape == (10,)
+            assert np.allclose(got, want[i], rtol=1e-9, atol=1e-9), (build.__name__, i)
+
+
+def test_preconv_layer_builds_im2col_columns():
+    """LLPreConvLayer output column k, slot CornersMap[j] == pixel (corner j + offset k) of the image, 0 where padded (LLPreConvLayer.cs:75-127)."""
+    from cryptonets_b200.layers import LLPreConvLayer, LLSingleLineReader
+    img = synthetic_mnist(1, seed=3)
+    rd = LLSingleLineReader(img, Scale=1.0, NormalizationFactor=1.0)
+    from cryptonets_b200.layers import EncryptLayer
+    enc = EncryptLayer(Source=rd, Factory=RawFactory(16384))
+    pre = LLPreConvLayer(Source=enc, InputShape=[28, 28], KernelShape=[5, 5], Upperpadding=[1, 1], Stride=[2, 2])
+    pre.PrepareNetwork()
+    out = pre.Apply(enc.GetNext())
+    assert out.ColumnCount == 25
+    ce = pre.ce
+    assert pre.HotIndices.sum() == len(ce.Corners) == 169 and pre.OutputDimension() == len(pre.HotIndices)
+    cols = [np.asarray(out.GetColumn(k).Decrypt(None)).reshape(-1) for k in range(25)]
+    for k, off in enumerate(ce.Offsets):
+        for j, corner in enumerate(ce.Corners):
+            l = ce.Location(corner, off, ce.InputShape)
+            assert cols[k][pre.CornersMap[j]] == (img[0][l] if l >= 0 else 0)
+
+
+def test_packed_dense_and_interleave_known_answer():
+    """4 outputs packed 2 per plaintext at stride 8 over a duplicated input; interleave gathers the 2 segment results of each row."""
+    from cryptonets_b200.interfaces import EMatrixFormat, EVectorFormat
+    from cryptonets_b200.layers import LLDuplicateLayer, LLInterleaveLayer, LLPackedDenseLayer
+    f = RawFactory(64)
+    x = np.arange(1, 7, dtype=np.float64)  # 6 inputs -> padded to 8 by Duplicate
+
+    class Src:
+        Factory = f
+
+        def GetOutputScale(self):
+            return 1.0
+
+        def OutputDimension(self):
+            return 6
+
+        def PrepareNetwork(self):
+            pass
+
+    m = f.GetMatrix([f.GetPlainVector(x, EVectorFormat.dense, 1.0)], EMatrixFormat.ColumnMajor, CopyVectors=False)
+    dup = LLDuplicateLayer(Source=Src(), Count=2)
+    assert dup.OutputDimension() == 16
+    d = dup.Apply(m)
+    W = np.arange(24, dtype=np.float64).reshape(4, 6) - 7
+    b = np.array([0.5, -1.0, 2.0, 3.0])
+    dense = LLPackedDenseLayer(Source=dup, Weights=W.reshape(-1), Bias=b, WeightsScale=2.0, PackingCount=2, PackingShift=8)
+    dense.Prepare()
+    y = dense.Apply(d)
+    assert y.ColumnCount == 2
+    want = W @ x + b
+    got = [np.asarray(y.GetColumn(r).Decrypt(None)).reshape(-1) for r in range(2)]
+    for i in range(4):
+        row, col = divmod(i, 2)
+        assert np.isclose(got[row][(col + 1) * 8 - 1], want[i])
+    inter = LLInterleaveLayer(Source=dense, Shift=-1, SelectedIndices=[7, 15])
+    inter.Prepare()
+    z = np.asarray(inter.Apply(y).GetColumn(0).Decrypt(None)).reshape(-1)
+    # column c is shifted by c * Shift = -c slots: output i = 2*row + col sits at slot (col+1)*8 - 1 - row
+    for i in range(4):
+        row, col = divmod(i, 2)
+        assert np.isclose(z[(col + 1) * 8 - 1 - row], want[i])
