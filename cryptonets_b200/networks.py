@@ -8,7 +8,8 @@ import os
 
 import numpy as np
 
-from .layers import (EncryptLayer, LLConvReader, LLDenseLayer, LLDuplicateLayer, LLInterleavedDenseLayer, LLInterleaveLayer,
+from .interfaces import EVectorFormat
+from .layers import (ConvolutionEngine, EncryptLayer, LLConvReader, LLDenseLayer, LLDuplicateLayer, LLInterleavedDenseLayer, LLInterleaveLayer,
                      LLPackedDenseLayer, LLPoolLayer, LLPreConvLayer, LLSingleLineReader, LLVectorizeLayer, MatrixSource, PoolLayer,
                      SquareActivation, TimingLayer)
 
@@ -17,6 +18,7 @@ CRYPTONETS_PRIMES = [549764251649, 549764284417]  # CryptoNets.cs:17
 LOLA_SMALL_PRIMES = [2277377, 2424833]            # LoLaCryptonets.cs:285
 LOLA_PRIMES = [557057, 638977, 737281, 786433]    # LoLaCryptonets.cs:208 (N=8192, default decomposition bit counts)
 LOLA_DENSE_PRIMES = [34359771137, 34360754177]    # LoLaCryptonets.cs:123 (N=16384, w=60, SmallModulusCount=7)
+CIFAR_PRIMES = [957181001729, 957181034497]       # LolaCifarCryptoNet.cs:35 (N=16384, w=60, SmallModulusCount=8)
 
 
 def load_weights(name, shapes, seed=0):
@@ -129,3 +131,40 @@ def lola_dense(factory, images, weights=None):
     dense9 = LLInterleavedDenseLayer(Source=inter8, Weights=w["Weights_3"], Bias=w["Biases_3"], WeightsScale=weightscale, Shift=-1,
                                      SelectedIndices=sel)
     return dense9, reader
+
+
+def cifar_weights(seed=7):
+    """Synthetic weights with the shapes and the per-layer spread of the shipped `CifarWeight.csv` / `CifarBias.csv` (21 MB of text,
+    not copied into this repo): conv 83 x (3*8*8), conv-as-dense 112 x (83*10*10), dense 10 x 5488."""
+    rng = np.random.default_rng(seed)
+
+    def draw(n, std, cap):
+        return np.clip(rng.normal(0, std, n), -cap, cap)
+
+    return dict(Weights_0=draw(83 * 192, 0.073, 0.51), Biases_0=draw(83, 0.12, 0.39), Weights_1=draw(112 * 8300, 0.020, 0.11),
+                Biases_1=draw(112, 0.12, 0.22), Weights_2=draw(10 * 5488, 0.187, 1.03), Biases_2=draw(10, 0.67, 1.44))
+
+
+def synthetic_cifar(n_images, seed=20240917):
+    return np.random.default_rng(seed).integers(0, 256, (n_images, 3 * 32 * 32)).astype(np.float64)
+
+
+def lola_cifar(factory, images, weights=None):
+    """LoLa-CIFAR (`CifarCryptoNet/LolaCifarCryptoNet.cs:27-131`): 3x32x32 image as an im2col matrix [196 x 192], conv 83 maps,
+    square, the second convolution as a 5488 x 16268 row-major dense layer (rotate-and-sum per row), square, dense 5488 -> 10."""
+    w = weights or cifar_weights()
+    reader = LLConvReader(images, Scale=8.0, NormalizationFactor=1.0 / 256.0, InputShape=[3, 32, 32], KernelShape=[3, 8, 8], Stride=[1000, 2, 2],
+                          Upperpadding=[0, 1, 1], Lowerpadding=[0, 1, 1])
+    enc = EncryptLayer(Source=reader, Factory=factory)
+    conv1 = LLPoolLayer(Source=enc, InputShape=[3, 32, 32], KernelShape=[3, 8, 8], Upperpadding=[0, 1, 1], Lowerpadding=[0, 1, 1],
+                        Stride=[1000, 2, 2], MapCount=[83, 1, 1], WeightsScale=256.0, Weights=w["Weights_0"], Bias=w["Biases_0"])
+    vec2 = LLVectorizeLayer(Source=conv1)
+    act3 = SquareActivation(Source=vec2)
+    ce = ConvolutionEngine()
+    ce.InputShape, ce.KernelShape, ce.Stride, ce.MapCount = [83, 14, 14], [83, 10, 10], [83, 2, 2], [112, 1, 1]
+    ce.Upperpadding, ce.Lowerpadding = [0, 4, 4], [0, 4, 4]
+    dense4 = LLDenseLayer(Source=act3, WeightsScale=512.0, Weights=ce.GetDenseWeights(w["Weights_1"]), Bias=ce.GetDenseBias(w["Biases_1"]),
+                          InputFormat=EVectorFormat.dense, ForceDenseFormat=True)
+    act5 = SquareActivation(Source=dense4)
+    dense6 = LLDenseLayer(Source=act5, Weights=w["Weights_2"], Bias=w["Biases_2"], WeightsScale=512.0, InputFormat=EVectorFormat.dense)
+    return dense6, reader

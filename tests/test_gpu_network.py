@@ -249,3 +249,34 @@ def test_lola_dense_scores_equal_raw_backend(small_modulus_count):
             assert 20 <= budget <= 50
     finally:
         f.Dispose()
+
+
+@pytest.mark.parametrize("small_modulus_count", [9, 8])
+def test_lola_cifar_scores_equal_raw_backend(small_modulus_count):
+    """LoLa-CIFAR (LolaCifarCryptoNet.cs:27-131; BASELINE config 4) on one synthetic 3x32x32 image with synthetic weights of the
+    shipped shapes: 192-column im2col input, 83-map convolution, square, the 5488 x 16268 row-major dense layer (batched
+    multiply_plain + rotate-and-sum + one-hot masks, ForceDenseFormat), square, dense 5488 -> 10.  As for LoLa-Dense, the reference's
+    SmallModulusCount=8 leaves ~25 bits before the last 16384-slot MultiplyPlain (~55 bits): compared through the second square
+    there, and end to end with one more prime."""
+    from cryptonets_b200.he import B200BfvFactory
+    from cryptonets_b200.networks import CIFAR_PRIMES, lola_cifar, synthetic_cifar
+    from cryptonets_b200.raw import RawFactory
+    f = B200BfvFactory(CIFAR_PRIMES, 16384, DecompositionBitCount=60, GaloisDecompositionBitCount=60,
+                       SmallModulusCount=small_modulus_count, seed=5)
+    try:
+        imgs = synthetic_cifar(1)
+        net, rd = lola_cifar(f, imgs)
+        net.PrepareNetwork()
+        raw_net, rrd = lola_cifar(RawFactory(16384), imgs)
+        raw_net.PrepareNetwork()
+        if small_modulus_count == 9:
+            got = np.asarray(net.GetNext().Decrypt()).reshape(-1)
+            want = np.asarray(raw_net.GetNext().Decrypt()).reshape(-1)
+            assert np.allclose(got, want, rtol=1e-9, atol=1e-9) and got.argmax() == want.argmax()
+        else:
+            ma, mb = _compare_layerwise(net, raw_net, rd, rrd, upto=-1)
+            assert np.allclose(np.asarray(ma.Decrypt()), np.asarray(mb.Decrypt()), rtol=1e-9, atol=1e-9)
+            budget = min(f.engine.noise_budget(v.vec, ch, 0) for v in ma.vectors for ch in range(2))
+            assert 10 <= budget <= 40
+    finally:
+        f.Dispose()

@@ -3,7 +3,8 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from cryptonets_b200.he import B200BfvFactory
-from cryptonets_b200.networks import LOLA_DENSE_PRIMES, LOLA_PRIMES, lola, lola_dense, synthetic_mnist
+from cryptonets_b200.networks import (CIFAR_PRIMES, LOLA_DENSE_PRIMES, LOLA_PRIMES, lola, lola_cifar, lola_dense, synthetic_cifar,
+                                      synthetic_mnist)
 from cryptonets_b200.raw import RawFactory
 
 
@@ -20,6 +21,10 @@ imgs = synthetic_mnist(1, seed=6)
 if which == "lola":
     f = B200BfvFactory(LOLA_PRIMES, 8192, seed=5)
     build, block = lola, 8192
+elif which == "cifar":
+    imgs = synthetic_cifar(1)
+    f = B200BfvFactory(CIFAR_PRIMES, 16384, DecompositionBitCount=60, GaloisDecompositionBitCount=60, SmallModulusCount=8, seed=5)
+    build, block = lola_cifar, 16384
 else:
     f = B200BfvFactory(LOLA_DENSE_PRIMES, 16384, DecompositionBitCount=60, GaloisDecompositionBitCount=60, SmallModulusCount=7, seed=5)
     build, block = lola_dense, 16384
