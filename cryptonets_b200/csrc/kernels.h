@@ -155,6 +155,11 @@ cudaError_t launch_split3(const u64 *ct3, u64 *base, u64 *c2, int n, int k, int 
 // ---- sampling / encode / encrypt / decrypt
 enum SampleKind { SAMPLE_TERNARY = 0, SAMPLE_NOISE = 1, SAMPLE_UNIFORM = 2 };
 // out[i][l][x] for i<n: stream ids stream0 + i*stream_step (+ l for UNIFORM); lifted into each residue
+// Dense layer (every output reads the same K inputs) on the integer tensor cores: wfrag = signed 8-bit weights packed as m16n8k32
+// A fragments [ceil(M/16)][ceil(K/32)][32 lanes][16 bytes]; weights in [-254, 254] are split W = W1 + W2 (wfrag2, may be null);
+// limbs = ceil(bits(q)/8); needs K*254*255 < 2^31
+cudaError_t launch_mac_dense_imma(const u64 *const *in_ptrs, const void *wfrag, const void *wfrag2, const u64 *bias, int K, int M, int limbs,
+                                  u64 *const *out_ptrs, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
 cudaError_t launch_sample(u64 *out, int n, int kind, u64 seed, u64 stream0, u64 stream_step, int k, int logn, const BehzConst *bc, cudaStream_t s);
 // plain[i][index_map[j]] = values[i][j]  (j < count), zero elsewhere
 cudaError_t launch_encode_scatter(const u64 *values, u64 *plain, int n, int count, const u32 *index_map, int logn, cudaStream_t s);

@@ -431,6 +431,47 @@ __device__ __forceinline__ void fwd_pass_fp(double *sm, const double *twc, const
             for (int e = 0; e < E; e++) sm[swz(bb[i] + (e << LG))] = x[i][e];
     }
 }
+// First forward pass split in two so that its HBM loads are in flight while the CTA fills its twiddle cache and waits at the
+// barrier (ncu source view: 11 % of a transform's warp time sat in that fill with no data load outstanding).
+// fwd_first_load: E = 2^R raw words of virtual thread vt (stride N/E); fwd_first_compute: convert, R stages, store to smem.
+template <int LOGN, int R, bool IN_F>
+__device__ __forceinline__ void fwd_first_load(u64 (&raw)[1 << R], const FwdSrc &src, int vt) {
+    constexpr int E = 1 << R, LG = LOGN - R;
+#pragma unroll
+    for (int e = 0; e < E; e++) raw[e] = src.src[vt + (e << LG)];
+}
+template <int LOGN, int R, bool IN_F>
+__device__ __forceinline__ void fwd_first_compute(double *sm, const double *twc, const u64 (&raw)[1 << R], const FwdSrc &src, const NttTab &tb, int vt) {
+    constexpr int E = 1 << R, LG = LOGN - R;
+    const double p = tb.pd, pinv = tb.pinv;
+    double x[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        if constexpr (IN_F) x[e] = __longlong_as_double((long long)raw[e]);
+        else {
+            u64 v = raw[e];
+            if (src.digit) v = (v >> src.shift) & src.mask; // source residue < 2^50, so every digit converts exactly
+            x[e] = u2d(v);
+            if (src.digit && src.need_reduce) x[e] = frecenter(x[e], p, pinv);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < R; u++) { // j = 0: the whole CTA uses twiddles [2^u, 2^(u+1)) in stage u
+        const int h = E >> (u + 1);
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            if (e & h) continue;
+            const double w = twc[(1 << u) + (e >> (R - u))];
+            const double t = fmodmul(x[e + h], w, p, pinv);
+            const double a = x[e];
+            x[e] = __dadd_rn(a, t);
+            x[e + h] = __dsub_rn(a, t);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) sm[swz(vt + (e << LG))] = x[e];
+}
+
 // Last forward pass: stages [LOGN-4, LOGN) on 16 consecutive words; canonical result goes straight to HBM.
 template <int LOGN, int PASS, bool OUT_F>
 __device__ __forceinline__ void fwd_last_fp(const double *sm, u64 *dst, const NttTab &tb, int j) {
@@ -514,6 +555,24 @@ template <int LOGN, bool IN_F, bool OUT_F>
 __device__ __forceinline__ void fwd_body_fp(double *sm, const FwdSrc &src, u64 *dst, const NttTab &tb, int tid) {
     constexpr int N = 1 << LOGN, TR = fp_threads(LOGN);
     double *twc = sm + N;
+    if constexpr (LOGN == 12 || LOGN == 14) { // loads first, then the twiddle cache fill (+2..3 % at N=4096/16384; -3 % at N=8192, which keeps the plain order)
+        constexpr int R1 = LOGN == 12 ? 4 : 5;
+        static_assert((N >> R1) == TR, "first pass: one virtual thread per thread");
+        u64 raw[1 << R1];
+        fwd_first_load<LOGN, R1, IN_F>(raw, src, tid);
+        load_twiddle_cache(twc, tb.wd, tid, TR);
+        __syncthreads();
+        fwd_first_compute<LOGN, R1, IN_F>(sm, twc, raw, src, tb, tid);
+        __syncthreads();
+        if constexpr (LOGN == 12) {
+            CNHE_VTN(N / 16, (fwd_pass_fp<12, 4, 4, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads();
+            CNHE_VTN(N / 16, (fwd_last_fp<12, 2, OUT_F>(sm, dst, tb, vt)));
+        } else {
+            CNHE_VTN(N / 32, (fwd_pass_fp<14, 5, 5, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads();
+            CNHE_VTN(N / 16, (fwd_last_fp<14, 2, OUT_F>(sm, dst, tb, vt)));
+        }
+        return;
+    }
     load_twiddle_cache(twc, tb.wd, tid, TR);
     __syncthreads();
     if constexpr (LOGN == 10) {
@@ -524,18 +583,10 @@ __device__ __forceinline__ void fwd_body_fp(double *sm, const FwdSrc &src, u64 *
         CNHE_VTN(N / 16, (fwd_pass_fp<11, 0, 3, true, 0, IN_F>(sm, twc, src, tb, vt))); __syncthreads();
         CNHE_VTN(N / 16, (fwd_pass_fp<11, 3, 4, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads();
         CNHE_VTN(N / 16, (fwd_last_fp<11, 2, OUT_F>(sm, dst, tb, vt)));
-    } else if constexpr (LOGN == 12) {
-        CNHE_VTN(N / 16, (fwd_pass_fp<12, 0, 4, true, 0, IN_F>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (fwd_pass_fp<12, 4, 4, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (fwd_last_fp<12, 2, OUT_F>(sm, dst, tb, vt)));
     } else if constexpr (LOGN == 13) {
         CNHE_VTN(N / 32, (fwd_pass_fp<13, 0, 5, true, 0, IN_F>(sm, twc, src, tb, vt))); __syncthreads();
         CNHE_VTN(N / 16, (fwd_pass_fp<13, 5, 4, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads(); // NV=2 (both groups' loads first) measured 5% slower
         CNHE_VTN(N / 16, (fwd_last_fp<13, 2, OUT_F>(sm, dst, tb, vt)));
-    } else {
-        CNHE_VTN(N / 32, (fwd_pass_fp<14, 0, 5, true, 0, IN_F>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 32, (fwd_pass_fp<14, 5, 5, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads();
-        CNHE_VTN(N / 16, (fwd_last_fp<14, 2, OUT_F>(sm, dst, tb, vt)));
     }
 }
 template <int LOGN, bool IN_F, bool OUT_F>

@@ -9,6 +9,7 @@
 // util::apply_galois, BatchEncoder::encode/decode index map.
 // All are HBM-bound streaming kernels except the MAC layer, which is integer-ALU bound.
 #include "kernels.h"
+#include "plainops.cuh"
 
 namespace cnhe {
 
@@ -39,12 +40,7 @@ __global__ void __launch_bounds__(256) k_ct_add_many(const u64 *const *__restric
     out[i] = acc;
 }
 
-// ---------------------------------------------------------------- Delta*m helpers
-__device__ __forceinline__ u64 scale_plain(u64 m, int l, const DMod &q, const PlainConst &pc) {
-    U128 v = mul64wide(pc.delta[l], m);
-    if (m >= pc.threshold) add128(v, pc.q_mod_t[l]);
-    return barrett128(v, q);
-}
+// ---------------------------------------------------------------- Delta*m helpers (scale_plain: plainops.cuh)
 __device__ __forceinline__ u64 lift_plain(u64 m, u64 q, const PlainConst &pc) { return m >= pc.threshold ? m + (q - pc.t) : m; }
 
 __global__ void __launch_bounds__(256) k_ct_add_plain(const u64 *ct, u64 *out, int n, int size, const u64 *__restrict__ plain,

@@ -38,11 +38,51 @@ DevBuf::DevBuf(size_t w, cudaStream_t s) : words(w), stream(s) {
     }
     CNHE_CUDA(cudaMallocAsync((void **)&p, w * sizeof(u64), s));
 }
+constexpr size_t RECYCLE_MIN_WORDS = (size_t)1 << 19;        // 4 MB
+constexpr size_t RECYCLE_CAP_WORDS = (size_t)40 << 27;       // 40 GB parked at most
+DevBuf::DevBuf(size_t w, cudaStream_t s, Context *ctx) : words(w), stream(s), owner(ctx) {
+    if (!w) return;
+    if (ctx && w >= RECYCLE_MIN_WORDS) {
+        size_t got = 0;
+        p = ctx->take_recycled(w, s, got);
+        if (p) { words = got; return; }
+    }
+    DevBuf fresh(w, s); // traced allocation path
+    p = fresh.p;
+    fresh.p = nullptr;
+}
+u64 *Context::take_recycled(size_t words, cudaStream_t s, size_t &got_words) {
+    int best = -1;
+    for (int i = 0; i < (int)recycle.size(); i++) {
+        const Recycled &r = recycle[i];
+        if (r.stream != s || r.words < words || r.words > words + words / 2) continue;
+        if (best < 0 || r.words < recycle[best].words) best = i;
+    }
+    if (best < 0) return nullptr;
+    u64 *p = recycle[best].p;
+    got_words = recycle[best].words;
+    recycle_words -= got_words;
+    recycle.erase(recycle.begin() + best);
+    return p;
+}
+bool Context::give_recycled(u64 *p, size_t words, cudaStream_t s) {
+    if (!recycle_on || words < RECYCLE_MIN_WORDS || recycle_words + words > RECYCLE_CAP_WORDS || recycle.size() >= 256) return false;
+    recycle.push_back({p, words, s});
+    recycle_words += words;
+    return true;
+}
+void Context::drop_recycled() {
+    for (const Recycled &r : recycle) cudaFreeAsync(r.p, r.stream);
+    recycle.clear();
+    recycle_words = 0;
+}
 DevBuf::DevBuf(size_t w, cudaMemPool_t pool, cudaStream_t alloc_stream, cudaStream_t release_stream) : words(w), stream(release_stream) {
     if (w) CNHE_CUDA(cudaMallocFromPoolAsync((void **)&p, w * sizeof(u64), pool, alloc_stream));
 }
 DevBuf::~DevBuf() {
-    if (p) cudaFreeAsync(p, stream);
+    if (!p) return;
+    if (owner && owner->give_recycled(p, words, stream)) return;
+    cudaFreeAsync(p, stream);
 }
 
 static std::vector<BufRef> &temps_of(Context &c);
@@ -133,8 +173,10 @@ Context::~Context() {
     cudaSetDevice(device);
     for (cudaStream_t s : streams) cudaStreamSynchronize(s);
     if (copy_stream) cudaStreamSynchronize(copy_stream);
+    recycle_on = false; // buffers released from here on go straight back to the driver
     g_temps.m.erase(this);
     ch.clear();
+    drop_recycled();
     if (d_bc) cudaFree(d_bc);
     if (d_bf) cudaFree(d_bf);
     if (d_tabs) cudaFree(d_tabs);

@@ -26,7 +26,9 @@ struct DevBuf {
     u64 *p = nullptr;
     size_t words = 0;
     cudaStream_t stream = nullptr; // release stream: the channel the buffer belongs to (also the allocation stream unless given)
+    struct Context *owner = nullptr; // set: a large block goes back to the context's per-stream recycle list instead of the driver pool
     DevBuf(size_t w, cudaStream_t s);
+    DevBuf(size_t w, cudaStream_t s, struct Context *owner);
     DevBuf(size_t w, cudaMemPool_t pool, cudaStream_t alloc_stream, cudaStream_t release_stream);
     ~DevBuf();
     DevBuf(const DevBuf &) = delete;
@@ -110,7 +112,17 @@ struct Context {
     void ws_reset() { ws_used = 0; }
     u64 *ws_alloc(size_t words);   // valid until the next ws_reset(); may synchronise when growing
     void ws_reserve(size_t words); // grow before taking pointers
-    BufRef alloc(size_t words) { return std::make_shared<DevBuf>(words, stream); }
+    BufRef alloc(size_t words) { return std::make_shared<DevBuf>(words, stream, this); }
+    // Large blocks (layer slabs, the 1 GB digit waves) are recycled per stream: a block released on stream S is handed to the next
+    // request of a similar size on S without a driver call -- stream order makes that safe, and it removes cudaMallocAsync's slow path
+    // (measured: 120 ms for 1 GB when the pool has no fitting free block) from the steady state.
+    struct Recycled { u64 *p; size_t words; cudaStream_t stream; };
+    std::vector<Recycled> recycle;
+    size_t recycle_words = 0;
+    bool recycle_on = true;
+    u64 *take_recycled(size_t words, cudaStream_t s, size_t &got_words);
+    bool give_recycled(u64 *p, size_t words, cudaStream_t s);
+    void drop_recycled();
     void launched(int n = 1) { launches += n; }
     void check(cudaError_t e, const char *what) { cuda_check(e, what); launched(); if (trace_ms > 0) trace_gap(what); }
     double trace_ms = 0; // CNHE_TRACE_SLOW: report host-side gaps between consecutive launches longer than this

@@ -1139,6 +1139,7 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
             }
         }
     }
+    const int order_rows = (int)(grows.size() / K);
     const double out_scale = in[0]->scale * weights[0]->scale;
     std::vector<BufRef> big(c.P);
     for (int ch = 0; ch < c.P; ch++) {
@@ -1167,6 +1168,39 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
                 wmax = std::max(wmax, std::fabs(d));
             }
         const bool fp_mac = maxbits <= 50 && wmax < 131072.0 && (double)K * wmax * 67108864.0 < 4503599627370496.0 && !getenv("CNHE_MAC_INT");
+        // dense layer (one gather row shared by every output, 8-bit weights): exact integer GEMM on the tensor cores (mac_imma.cu)
+        const int limbs = (maxbits + 7) / 8;
+        const bool imma = order_rows == 1 && wmax <= 254.0 && K >= 32 && M >= 8 && limbs >= 5 && limbs <= 7 && (double)K * 254.0 * 255.0 < 2147483648.0 &&
+                          !getenv("CNHE_MAC_NO_IMMA") && !getenv("CNHE_MAC_INT");
+        const void *d_wfrag = nullptr, *d_wfrag2 = nullptr;
+        if (imma) {
+            const int mtiles = (M + 15) / 16, chunks = (K + 31) / 32;
+            const size_t fwords = (size_t)mtiles * chunks * 32 * 4;
+            std::vector<uint32_t> frag(2 * fwords, 0); // W1 = clamp(W, +-127) then the residual W2 = W - W1
+            bool any2 = false;
+            auto wq = [&](int m, int kk, int part) -> uint32_t { // signed weight of output m, tap kk (0 outside the matrix / on padded taps)
+                if (m >= M || kk >= K || grows[kk] < 0) return 0;
+                const int w = (int)wdh[(size_t)m * K + kk], w1 = std::max(-127, std::min(127, w));
+                const int v = part ? w - w1 : w1;
+                if (part && v) any2 = true;
+                return (uint32_t)(uint8_t)(int8_t)v;
+            };
+            for (int part = 0; part < 2; part++)
+                for (int mt = 0; mt < mtiles; mt++)
+                    for (int cch = 0; cch < chunks; cch++)
+                        for (int lane = 0; lane < 32; lane++) {
+                            const int g = lane >> 2, tig = lane & 3;
+                            uint32_t *dst = &frag[part * fwords + (((size_t)mt * chunks + cch) * 32 + lane) * 4];
+                            for (int r = 0; r < 4; r++) { // r: 0 (row g, k 0..15) 1 (row g+8) 2 (row g, k 16..31) 3 (row g+8, k 16..31)
+                                const int row = mt * 16 + g + (r & 1) * 8, k0 = cch * 32 + tig * 4 + (r >> 1) * 16;
+                                dst[r] = wq(row, k0, part) | (wq(row, k0 + 1, part) << 8) | (wq(row, k0 + 2, part) << 16) | (wq(row, k0 + 3, part) << 24);
+                            }
+                        }
+            u64 *buf = c.ws_alloc((frag.size() * 4 + 7) / 8);
+            c.h2d(buf, frag.data(), (any2 ? 2 : 1) * fwords * 4);
+            d_wfrag = buf;
+            if (any2) d_wfrag2 = reinterpret_cast<const uint32_t *>(buf) + fwords;
+        }
         const double *d_wd = nullptr;
         if (fp_mac) {
             u64 *buf = c.ws_alloc(wdh.size());
@@ -1189,7 +1223,13 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
             double used = 0;
             for (auto &t : tiles) { int kk = 0; for (int j = 0; j < K; j++) kk += grows[(size_t)t.gather_row * K + j] >= 0; used += kk + t.n_out; }
             c.prof_begin(4, used * 8.0 * c.ct_words());
-            if (fp_mac)
+            if (imma) {
+                std::vector<const u64 *> ipg(K);
+                for (int kk = 0; kk < K; kk++) ipg[kk] = ip[grows[kk] < 0 ? 0 : grows[kk]]; // padded taps carry weight 0
+                c.check(launch_mac_dense_imma(upload_ptrs(c, ipg), d_wfrag, d_wfrag2, d_bias, K, M, limbs, upload_ptrs_mut(c, op), c.k, c.logN, c.d_bc, c.ch[ch].pc,
+                                              c.stream),
+                        "mac_dense_imma");
+            } else if (fp_mac)
                 c.check(launch_mac_layer_fp(upload_ptrs(c, ip), d_gather, d_tiles, (int)tiles.size(), d_wd, d_bias, K, upload_ptrs_mut(c, op), c.k, c.logN,
                                             c.d_bc, c.ch[ch].pc, c.stream),
                         "mac_layer_fp");

@@ -262,3 +262,49 @@ def test_mac_layer_and_square_layer(pair):
     for i in range(4):
         assert np.array_equal(sq[i].export_raw(0, 0), wantsq[i]), i
         assert sq[i].scale == 32.0 * 32.0
+
+
+def test_dense_layer_on_tensor_cores(pair):
+    """Dense layer (all outputs read the same K inputs, |w| <= 254): the exact 8-bit-limb integer GEMM of mac_imma.cu must give
+    the same ciphertext words as the oracle's 128-bit multiply-accumulate -- odd M and K (padding inside the m16/k32 tiles), a padded
+    tap, zero weights, extreme weights +-127 and maximal residues, bias on coefficient 0 of c0; and the same layer with the tensor-core
+    path disabled."""
+    import os
+    from cryptonets_b200.engine import DENSE, SPARSE
+    eng, orc, name = pair
+    N = eng.N
+    rng = np.random.default_rng(23)
+    n_in, M, K = 45, 21, 43
+    vals, cts = _fresh_cts(orc, n_in, 12, nonce0=900)
+    q = np.array(orc.q, dtype=np.uint64)
+    cts = np.array(cts, dtype=np.uint64).reshape(n_in, 2, len(q), N)
+    cts[0] = (q - 1)[None, :, None]                       # every word of input 0 at its maximum
+    cts[1, :, :, ::2] = (q - 1)[None, :, None]
+    cts = cts.reshape(n_in, -1)
+    ins = [eng.import_raw(cts[i], 1, N, 4.0) for i in range(n_in)]
+    row = rng.permutation(n_in)[:K].astype(np.int32)
+    row[7] = -1                                           # one padded tap
+    gather = np.tile(row, (M, 1)).astype(np.int32)
+    w = rng.integers(-127, 128, (M, K)).astype(np.float64)
+    w[:, 0] = 127
+    w[:, 1] = -127
+    w[5, 3], w[6, 40], w[20, 42] = 254, -254, 165  # beyond 8 bits: carried by the residual fragment
+    w[3, :] = 0
+    w[3, 2] = 1
+    bias = rng.integers(-1000, 1000, M).astype(np.float64)
+    wv = [eng.plain(w[m], 1.0, SPARSE) for m in range(M)]
+    bv = [eng.plain(np.full(N, bias[m]), 4.0, DENSE) for m in range(M)]
+    t = orc.t
+    wres = np.where(w < 0, w + t, w).astype(np.uint64)
+    bres = np.where(bias * 4 < 0, bias * 4 + t, bias * 4).astype(np.uint64)
+    want = orc.mac_layer(cts, gather, wres, bres, M, K, threads=4).reshape(M, -1)
+    outs = eng.layer_conv_dense(ins, gather, wv, bv, M, K)
+    for m in range(M):
+        assert np.array_equal(outs[m].export_raw(0, 0), want[m]), m
+    os.environ["CNHE_MAC_NO_IMMA"] = "1"
+    try:
+        outs2 = eng.layer_conv_dense(ins, gather, wv, bv, M, K)
+    finally:
+        del os.environ["CNHE_MAC_NO_IMMA"]
+    for m in range(M):
+        assert np.array_equal(outs2[m].export_raw(0, 0), want[m]), m
