@@ -50,7 +50,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -227,15 +227,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the device-resident number is taken on ONE stream so that the per-kernel CUDA-event times are not inflated by kernels of the
+    # other plaintext-modulus channel running concurrently; warm up in the same mode (the block recycler is per stream)
+    eng.set_option("multi_stream", 0)
     for _ in range(args.warmup):
         forward(layers, xm).Dispose()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = eng.launch_count()
-    # the device-resident number is taken on ONE stream so that the per-kernel CUDA-event times are not inflated by kernels of the
-    # other plaintext-modulus channel running concurrently; the end-to-end number below uses one stream per channel
-    eng.set_option("multi_stream", 0)
     eng.prof_enable(True)
     eng.timer_start()
     last = None
@@ -247,7 +247,6 @@ def run_b200(args):
     barrier()
     prof = eng.prof_collect()
     eng.prof_enable(False)
-    eng.set_option("multi_stream", 1)
     launches = eng.launch_count() - launches0
     clocks = sampler.stop()
     if world > 1:
@@ -298,7 +297,7 @@ def run_b200(args):
         eng.export_wait(pending)
 
     eng.set_option("multi_stream", int(os.environ.get("CNHE_E2E_MULTI_STREAM", "0")))
-    e2e_run(2)
+    e2e_run(max(4, args.warmup))  # reaches the steady state of the rotating upload slots
     barrier()
     t0 = time.perf_counter()
     e2e_run(args.steps)

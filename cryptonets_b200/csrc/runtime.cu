@@ -76,11 +76,50 @@ void Context::drop_recycled() {
     recycle.clear();
     recycle_words = 0;
 }
-DevBuf::DevBuf(size_t w, cudaMemPool_t pool, cudaStream_t alloc_stream, cudaStream_t release_stream) : words(w), stream(release_stream) {
-    if (w) CNHE_CUDA(cudaMallocFromPoolAsync((void **)&p, w * sizeof(u64), pool, alloc_stream));
+BufRef Context::alloc_upload(size_t words, cudaStream_t release_stream) {
+    int pick = -1;
+    for (int pass = 0; pass < 2 && pick < 0; pass++) // first a free slot whose last users are already done, else the longest-released one
+        for (int i = 0; i < (int)upload_slots.size(); i++) {
+            UploadSlot &u = upload_slots[i];
+            if (u.busy || u.words < words || u.words > words + words / 2) continue;
+            if (pass == 0 && cudaEventQuery(u.released) != cudaSuccess) continue;
+            if (pick < 0 || u.stamp < upload_slots[pick].stamp) pick = i;
+        }
+    if (pick >= 0 && cudaEventQuery(upload_slots[pick].released) != cudaSuccess) { // grow to three slots of this size (enough for a
+        int same = 0;                                                               // one-deep pipeline), then wait for the oldest
+        for (const UploadSlot &u : upload_slots) same += u.words >= words && u.words <= words + words / 2;
+        if (same < 3 * (int)streams.size()) pick = -1;
+    }
+    (void)cudaGetLastError(); // cudaEventQuery's cudaErrorNotReady is not an error
+    if (pick < 0) {
+        UploadSlot u;
+        u.words = words;
+        u.busy = false;
+        u.stamp = 0;
+        CNHE_CUDA(cudaMalloc((void **)&u.p, words * sizeof(u64)));
+        CNHE_CUDA(cudaEventCreateWithFlags(&u.released, cudaEventDisableTiming));
+        upload_slots.push_back(u);
+        pick = (int)upload_slots.size() - 1;
+    }
+    UploadSlot &u = upload_slots[pick];
+    u.busy = true;
+    CNHE_CUDA(cudaStreamWaitEvent(copy_stream, u.released, 0)); // a never-recorded event is complete
+    BufRef b = std::make_shared<DevBuf>(0, release_stream);
+    b->p = u.p;
+    b->words = u.words;
+    b->owner = this;
+    b->upload_slot = pick;
+    return b;
+}
+void Context::release_upload(int slot, cudaStream_t s) {
+    UploadSlot &u = upload_slots[slot];
+    cudaEventRecord(u.released, s);
+    u.busy = false;
+    u.stamp = ++upload_stamp;
 }
 DevBuf::~DevBuf() {
     if (!p) return;
+    if (upload_slot >= 0) { owner->release_upload(upload_slot, stream); return; }
     if (owner && owner->give_recycled(p, words, stream)) return;
     cudaFreeAsync(p, stream);
 }
@@ -190,7 +229,7 @@ Context::~Context() {
     if (ev_join) cudaEventDestroy(ev_join);
     for (cudaStream_t s : streams) cudaStreamDestroy(s);
     if (copy_stream) cudaStreamDestroy(copy_stream);
-    if (upload_pool) cudaMemPoolDestroy(upload_pool);
+    for (UploadSlot &u : upload_slots) { cudaFree(u.p); cudaEventDestroy(u.released); }
     if (ev_copy) cudaEventDestroy(ev_copy);
     for (cudaEvent_t e : ev_export) cudaEventDestroy(e);
 }
@@ -354,19 +393,6 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
     c.trace_ms = trace_slow_ms();
     CNHE_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     CNHE_CUDA(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
-    {
-        cudaMemPoolProps props;
-        memset(&props, 0, sizeof(props));
-        props.allocType = cudaMemAllocationTypePinned;
-        props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice;
-        props.location.id = device;
-        CNHE_CUDA(cudaMemPoolCreate(&c.upload_pool, &props));
-        uint64_t thr = ~0ULL;
-        CNHE_CUDA(cudaMemPoolSetAttribute(c.upload_pool, cudaMemPoolAttrReleaseThreshold, &thr));
-        int off = 0; // never make the upload stream wait for a release that is still queued behind another stream's kernels
-        CNHE_CUDA(cudaMemPoolSetAttribute(c.upload_pool, cudaMemPoolReuseAllowInternalDependencies, &off));
-    }
     CNHE_CUDA(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     CNHE_CUDA(cudaEventCreate(&c.ev0));
     CNHE_CUDA(cudaEventCreate(&c.ev1));

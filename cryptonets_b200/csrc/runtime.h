@@ -29,7 +29,7 @@ struct DevBuf {
     struct Context *owner = nullptr; // set: a large block goes back to the context's per-stream recycle list instead of the driver pool
     DevBuf(size_t w, cudaStream_t s);
     DevBuf(size_t w, cudaStream_t s, struct Context *owner);
-    DevBuf(size_t w, cudaMemPool_t pool, cudaStream_t alloc_stream, cudaStream_t release_stream);
+    int upload_slot = -1; // >= 0: the block is one of the context's persistent upload slots (returned, not freed)
     ~DevBuf();
     DevBuf(const DevBuf &) = delete;
 };
@@ -77,7 +77,14 @@ struct Context {
     // bulk ciphertext uploads (cnhe_vecs_import_raw) run on their own stream, fenced by events against the owning channel's stream:
     // the upload of the next batch overlaps the kernels of the current one (double buffering across API calls)
     cudaStream_t copy_stream = nullptr;
-    cudaMemPool_t upload_pool = nullptr; // its allocations never wait for a free queued behind kernels (no internal dependencies)
+    // persistent device blocks for uploaded ciphertext batches: a slot is handed out again once the event recorded at its release (on
+    // the consuming channel's stream) allows it -- no driver allocation in the steady state, and with three slots in rotation the
+    // upload of batch i+1 never waits for batch i's kernels
+    struct UploadSlot { u64 *p; size_t words; cudaEvent_t released; bool busy; uint64_t stamp; };
+    std::vector<UploadSlot> upload_slots;
+    uint64_t upload_stamp = 0;
+    BufRef alloc_upload(size_t words, cudaStream_t release_stream); // the copy stream is made to wait for the slot's last release
+    void release_upload(int slot, cudaStream_t s);
     cudaEvent_t ev_copy = nullptr;
     std::vector<cudaEvent_t> ev_export; // ring of 8 tickets x P channel events (cnhe_vecs_export_raw_async)
     int export_next = 0;

@@ -607,10 +607,10 @@ extern "C" int cnhe_vecs_import_raw(cnhe_ctx *h, const uint64_t *src, int n, int
     std::vector<BufRef> big(c.P);
     for (int ch = 0; ch < c.P; ch++) {
         c.set_channel(ch);
-        // allocation and copy are ordered on the upload stream only (not behind the kernels already queued on the channel's stream):
-        // channels follow each other over PCIe, channel 0 computes while channel 1 is still uploading, and an import issued before
-        // the previous batch is exported overlaps that batch's kernels.  The buffer is released on the channel's stream, after its users.
-        big[ch] = std::make_shared<DevBuf>(words, c.upload_pool, c.copy_stream, c.stream);
+        // the block comes from the context's rotating upload slots and the copy is ordered on the upload stream only (not behind the
+        // kernels already queued on the channel's stream): channels follow each other over PCIe, channel 0 computes while channel 1 is
+        // still uploading, and an import issued before the previous batch is exported overlaps that batch's kernels
+        big[ch] = c.alloc_upload(words, c.stream);
         CNHE_CUDA(cudaMemcpyAsync(big[ch]->p, src + (size_t)ch * words, words * 8, cudaMemcpyHostToDevice, c.copy_stream));
         CNHE_CUDA(cudaEventRecord(c.ev_copy, c.copy_stream));
         CNHE_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
