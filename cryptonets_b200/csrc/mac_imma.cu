@@ -9,19 +9,19 @@
 // Same residues as k_mac_layer / k_mac_layer_fp (tests/test_gpu_kernels.py::test_mac_layer_*), 6 limb products instead of
 // K*M 64-bit modular multiply-adds per word: the layer becomes bound by reading its inputs once.
 //
-// CTA: 256 threads, a tile of 32 ciphertext words x up to 128 outputs; warp w owns outputs [16w, 16w+16).  Per 32-tap chunk the CTA
-// loads 32x32 words (each thread 4 taps of one word), cuts them into limbs and stores them tap-major per word (48-byte rows:
-// conflict-free ldmatrix); every warp then issues 6 limbs x 4 n8-tiles = 24 MMAs against its A fragment (weights pre-packed in
-// fragment order on the host, L2 resident).
+// CTA: 256 threads, a tile of TN (16 or 32) ciphertext words x up to 128 outputs; warp w owns outputs [16w, 16w+16).  Per 32-tap chunk
+// the CTA loads 32 x TN words (each loader thread 4 taps of one word), cuts them into limbs and stores them tap-major per word
+// (32-byte rows with a half-row swizzle: conflict-free stores and ldmatrix); every warp then issues limbs x TN/8 MMAs against its A
+// fragment (weights pre-packed in fragment order on the host, L2 resident).
+#include <cstdlib>
 #include "fparith.cuh"
 #include "kernels.h"
 #include "plainops.cuh"
 
 namespace cnhe {
 
-constexpr int IM_TN = 32;      // ciphertext words per CTA
-constexpr int IM_ROW = 48;     // bytes per (word, limb) row of 32 taps: 32 used + 16 pad (ldmatrix rows hit distinct banks)
-constexpr int IM_LIMBS_MAX = 7;
+constexpr int IM_ROW = 32;     // bytes per (word, limb) row of 32 taps; the two 16-byte halves are swapped on rows with bit 2 set, which
+                               // makes both the loaders' 32-bit stores and the 8-row ldmatrix reads bank-conflict free
 
 __device__ __forceinline__ void ldmatrix_x4(unsigned &r0, unsigned &r1, unsigned &r2, unsigned &r3, const void *smem_row) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(smem_row);
@@ -34,31 +34,35 @@ __device__ __forceinline__ void imma_s8u8(int (&c)[4], const uint4 &a, unsigned 
 }
 
 // wfrag: [m-tile][tap chunk][lane] uint4, the m16n8k32 A fragment of the (zero padded) signed 8-bit weight matrix
-template <int LIMBS>
-__global__ void __launch_bounds__(256) k_mac_dense_imma(const u64 *const *__restrict__ in_ptrs, const uint4 *__restrict__ wfrag,
+template <int LIMBS, int TN>
+__global__ void __launch_bounds__(256, TN == 16 ? 2 : 1) k_mac_dense_imma(const u64 *const *__restrict__ in_ptrs, const uint4 *__restrict__ wfrag,
                                                       const uint4 *__restrict__ wfrag2, const u64 *__restrict__ bias,
                                                       int K, int M, u64 *const *__restrict__ out_ptrs, int k, int logn,
                                                       const BehzConst *__restrict__ bc, PlainConst pc) {
-    __shared__ __align__(16) unsigned char sb[2][LIMBS][IM_TN][IM_ROW];
+    __shared__ __align__(16) unsigned char sb[2][LIMBS][TN][IM_ROW];
+    constexpr int NT8 = TN / 8; // n8 tiles per warp
     const int N = 1 << logn;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t col0 = (size_t)blockIdx.x * IM_TN;         // first ciphertext word of the tile
+    const size_t col0 = (size_t)blockIdx.x * TN;            // first ciphertext word of the tile
     const int l = (int)((col0 >> logn) % k);                // its residue
     const int chunks = (K + 31) / 32;
     const int mt = blockIdx.y * 8 + warp;                   // this warp's m16 tile
     const bool have_m = mt * 16 < M;
-    // loader role: word n of the tile, taps 4*kq .. 4*kq+3 of the chunk
+    // loader role (threads 0 .. 8*TN-1): word n of the tile, taps 4*kq .. 4*kq+3 of the chunk
     const int ln = tid >> 3, kq = tid & 7;
-    int acc[LIMBS][4][4];
+    const bool loader = ln < TN;
+    const int sw_off = (((kq >> 2) ^ ((ln >> 2) & 1)) << 4) + ((kq & 3) << 2); // byte offset of this thread's word inside its row
+    int acc[LIMBS][NT8][4];
 #pragma unroll
     for (int a = 0; a < LIMBS; a++)
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+        for (int j = 0; j < NT8; j++)
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[a][j][e] = 0;
 
     u64 v[4];
     auto fetch = [&](int chunk) {
+        if (!loader) return;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int kk = chunk * 32 + kq * 4 + j;
@@ -66,11 +70,12 @@ __global__ void __launch_bounds__(256) k_mac_dense_imma(const u64 *const *__rest
         }
     };
     auto stage = [&](int buf) { // limb a of the four taps -> one 32-bit word (tap j in byte j)
+        if (!loader) return;
 #pragma unroll
         for (int a = 0; a < LIMBS; a++) {
             const unsigned b0 = (unsigned)(v[0] >> (8 * a)) & 0xffu, b1 = (unsigned)(v[1] >> (8 * a)) & 0xffu;
             const unsigned b2 = (unsigned)(v[2] >> (8 * a)) & 0xffu, b3 = (unsigned)(v[3] >> (8 * a)) & 0xffu;
-            *reinterpret_cast<unsigned *>(&sb[buf][a][ln][kq * 4]) = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+            *reinterpret_cast<unsigned *>(&sb[buf][a][ln][sw_off]) = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
         }
     };
 
@@ -90,9 +95,10 @@ __global__ void __launch_bounds__(256) k_mac_dense_imma(const u64 *const *__rest
 #pragma unroll
             for (int a = 0; a < LIMBS; a++) {
 #pragma unroll
-                for (int jp = 0; jp < 2; jp++) { // two n8 tiles per ldmatrix.x4
+                for (int jp = 0; jp < NT8 / 2; jp++) { // two n8 tiles per ldmatrix.x4
                     unsigned b0, b1, b2, b3;
-                    ldmatrix_x4(b0, b1, b2, b3, &sb[buf][a][jp * 16 + (mat >> 1) * 8 + r][(mat & 1) * 16]);
+                    const int row = jp * 16 + (mat >> 1) * 8 + r;
+                    ldmatrix_x4(b0, b1, b2, b3, &sb[buf][a][row][((mat & 1) ^ ((row >> 2) & 1)) << 4]);
                     imma_s8u8(acc[a][jp * 2], afrag, b0, b1);
                     imma_s8u8(acc[a][jp * 2 + 1], afrag, b2, b3);
                     if (second) {
@@ -118,7 +124,7 @@ __global__ void __launch_bounds__(256) k_mac_dense_imma(const u64 *const *__rest
         if (m >= M) continue;
         u64 *orow = out_ptrs[m];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < NT8; j++) {
             u64 res[2];
 #pragma unroll
             for (int e = 0; e < 2; e++) {
@@ -137,16 +143,31 @@ __global__ void __launch_bounds__(256) k_mac_dense_imma(const u64 *const *__rest
     }
 }
 
+template <int LIMBS, int TN>
+static void imma_go(const u64 *const *in_ptrs, const uint4 *wf, const uint4 *wf2, const u64 *bias, int K, int M, u64 *const *out_ptrs, int k, int logn,
+                    const BehzConst *bc, PlainConst pc, cudaStream_t s) {
+    const size_t ct_words = (size_t)2 * k << logn;
+    dim3 grid((unsigned)(ct_words / TN), (unsigned)((M + 127) / 128));
+    k_mac_dense_imma<LIMBS, TN><<<grid, 256, 0, s>>>(in_ptrs, wf, wf2, bias, K, M, out_ptrs, k, logn, bc, pc);
+}
 cudaError_t launch_mac_dense_imma(const u64 *const *in_ptrs, const void *wfrag, const void *wfrag2, const u64 *bias, int K, int M, int limbs,
                                   u64 *const *out_ptrs, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s) {
-    const size_t ct_words = (size_t)2 * k << logn;
-    dim3 grid((unsigned)(ct_words / IM_TN), (unsigned)((M + 127) / 128));
     const uint4 *wf = reinterpret_cast<const uint4 *>(wfrag), *wf2 = reinterpret_cast<const uint4 *>(wfrag2);
-    switch (limbs) {
-    case 5: k_mac_dense_imma<5><<<grid, 256, 0, s>>>(in_ptrs, wf, wf2, bias, K, M, out_ptrs, k, logn, bc, pc); break;
-    case 6: k_mac_dense_imma<6><<<grid, 256, 0, s>>>(in_ptrs, wf, wf2, bias, K, M, out_ptrs, k, logn, bc, pc); break;
-    case 7: k_mac_dense_imma<7><<<grid, 256, 0, s>>>(in_ptrs, wf, wf2, bias, K, M, out_ptrs, k, logn, bc, pc); break;
-    default: return cudaErrorInvalidValue;
+    static const int tn = getenv("CNHE_IMMA_TN") ? atoi(getenv("CNHE_IMMA_TN")) : 16; // ciphertext words per CTA (16: two CTAs per SM)
+    if (tn == 32) {
+        switch (limbs) {
+        case 5: imma_go<5, 32>(in_ptrs, wf, wf2, bias, K, M, out_ptrs, k, logn, bc, pc, s); break;
+        case 6: imma_go<6, 32>(in_ptrs, wf, wf2, bias, K, M, out_ptrs, k, logn, bc, pc, s); break;
+        case 7: imma_go<7, 32>(in_ptrs, wf, wf2, bias, K, M, out_ptrs, k, logn, bc, pc, s); break;
+        default: return cudaErrorInvalidValue;
+        }
+    } else {
+        switch (limbs) {
+        case 5: imma_go<5, 16>(in_ptrs, wf, wf2, bias, K, M, out_ptrs, k, logn, bc, pc, s); break;
+        case 6: imma_go<6, 16>(in_ptrs, wf, wf2, bias, K, M, out_ptrs, k, logn, bc, pc, s); break;
+        case 7: imma_go<7, 16>(in_ptrs, wf, wf2, bias, K, M, out_ptrs, k, logn, bc, pc, s); break;
+        default: return cudaErrorInvalidValue;
+        }
     }
     return cudaGetLastError();
 }
