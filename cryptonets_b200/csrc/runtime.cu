@@ -91,15 +91,20 @@ BufRef Context::alloc_upload(size_t words, cudaStream_t release_stream) {
         if (same < 3 * (int)streams.size()) pick = -1;
     }
     (void)cudaGetLastError(); // cudaEventQuery's cudaErrorNotReady is not an error
-    if (pick < 0) {
-        UploadSlot u;
-        u.words = words;
-        u.busy = false;
-        u.stamp = 0;
-        CNHE_CUDA(cudaMalloc((void **)&u.p, words * sizeof(u64)));
-        CNHE_CUDA(cudaEventCreateWithFlags(&u.released, cudaEventDisableTiming));
-        upload_slots.push_back(u);
-        pick = (int)upload_slots.size() - 1;
+    if (pick < 0) { // first batch of this size: create the whole rotation at once (cudaMalloc of 0.5 GB costs ~50 ms; pay it up front)
+        int same = 0;
+        for (const UploadSlot &u : upload_slots) same += u.words >= words && u.words <= words + words / 2;
+        const int want = same == 0 ? 3 * (int)streams.size() : same + 1;
+        for (; same < want; same++) {
+            UploadSlot u;
+            u.words = words;
+            u.busy = false;
+            u.stamp = 0;
+            CNHE_CUDA(cudaMalloc((void **)&u.p, words * sizeof(u64)));
+            CNHE_CUDA(cudaEventCreateWithFlags(&u.released, cudaEventDisableTiming));
+            upload_slots.push_back(u);
+            if (pick < 0) pick = (int)upload_slots.size() - 1;
+        }
     }
     UploadSlot &u = upload_slots[pick];
     u.busy = true;

@@ -1,0 +1,52 @@
+"""Host-side breakdown of the pipelined end-to-end loop of bench.py (import / forward issue / export issue / wait), per step."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import bench
+from cryptonets_b200.he import B200BfvFactory, B200BfvMatrix, B200BfvVector
+from cryptonets_b200.interfaces import EMatrixFormat
+from cryptonets_b200.networks import CRYPTONETS_PRIMES, synthetic_mnist
+
+f = B200BfvFactory(CRYPTONETS_PRIMES, bench.BATCH, seed=1)
+eng = f.engine
+layers = bench.build_network(f)
+x = np.rint(synthetic_mnist(bench.BATCH, seed=7) / 256.0 * 16.0)
+xm = f.GetEncryptedMatrix(x, EMatrixFormat.ColumnMajor, 1)
+xm.RegisterScale(16.0)
+eng.set_option("multi_stream", int(os.environ.get("MS", "1")))
+host_in = torch.empty(eng.P * 784 * eng.ct_words, dtype=torch.int64).pin_memory()
+host_outs = [torch.empty(eng.P * 10 * eng.ct_words, dtype=torch.int64).pin_memory() for _ in range(2)]
+eng.export_raw_many([v.vec for v in xm.vectors], host_in.data_ptr())
+
+
+def imp():
+    vecs = eng.import_raw_many(host_in.data_ptr(), 784, 1, bench.BATCH, 16.0)
+    return B200BfvMatrix(f, [B200BfvVector(f, v) for v in vecs], EMatrixFormat.ColumnMajor, CopyVectors=False)
+
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+rows = []
+t_start = time.perf_counter()
+nxt = imp()
+pending = None
+for s in range(steps):
+    t0 = time.perf_counter()
+    cur = nxt
+    out = bench.forward(layers, cur)
+    cur.Dispose()
+    t1 = time.perf_counter()
+    ticket = eng.export_raw_many_async([v.vec for v in out.vectors], host_outs[s & 1].data_ptr())
+    out.Dispose()
+    t2 = time.perf_counter()
+    if s + 1 < steps:
+        nxt = imp()
+    t3 = time.perf_counter()
+    if pending is not None:
+        eng.export_wait(pending)
+    t4 = time.perf_counter()
+    pending = ticket
+    rows.append([round((b - a) * 1e3, 1) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, t4))])
+eng.export_wait(pending)
+total = (time.perf_counter() - t_start) * 1e3
+print(json.dumps({"steps": steps, "ms_per_step": round(total / steps, 2), "forward_export_import_wait_ms": rows}))
