@@ -14,6 +14,7 @@ Prints ONE JSON line (rank 0).  `value` is the whole-job aggregate with inputs r
 public API with host (pinned) ciphertext buffers; `roofline` is the NTT kernel family measured live with CUDA events on
 the library's stream."""
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -365,6 +366,72 @@ def run_b200(args):
         print(json.dumps(out))
 
 
+def run_microbench(args):
+    """BASELINE config 5: NTT and multiply+relinearise micro-benchmark, GPU (libcnhe) next to the CPU oracle (this leg is a
+    cpu_baseline: the oracle is timed, never used for results) on the box's host cores.  N in {4096, 8192, 16384}, k = 2..6
+    coefficient moduli (prefixes of SEAL's default tables).  One JSON line per case."""
+    from cryptonets_b200.engine import Engine
+    from oracle.oracle_py import Oracle
+    PEAK = 6580.3
+    try:
+        PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    threads = os.cpu_count() or 1
+    cases = [(4096, 2), (4096, 3), (8192, 2), (8192, 4), (8192, 5), (16384, 4), (16384, 6)]
+    t = {4096: 40961, 8192: 65537, 16384: 65537}
+    rng = np.random.default_rng(0)
+    for N, k in cases:
+        eng = Engine([t[N]], N, 10, 20, k)
+        eng.keygen(1)
+        eng.set_option("multi_stream", 0)
+        q = np.array(eng.q, dtype=np.uint64)
+        n_polys = (1 << 27) // N // k * k  # 1 GiB of residue polynomials
+        d = eng.dev_from(rng.integers(0, 1 << 35, n_polys * N, dtype=np.uint64))
+        res = {"N": N, "k": k}
+        for inverse in (False, True):
+            for _ in range(2):
+                eng.raw_ntt(d, d, n_polys, 0, k, inverse)
+            eng.timer_start()
+            for _ in range(5):
+                eng.raw_ntt(d, d, n_polys, 0, k, inverse)
+            ms = eng.timer_stop_ms() / 5
+            res["gpu_%s_Mpolys_s" % ("intt" if inverse else "ntt")] = round(n_polys / ms / 1e3, 2)
+            res["gpu_%s_frac_hbm" % ("intt" if inverse else "ntt")] = round(16.0 * N * n_polys / (ms * 1e-3) / 1e9 / PEAK, 3)
+        eng.dev_free(d)
+        # multiply + relinearise of n ciphertexts
+        n = 256 if N <= 8192 else 128
+        cts = (rng.integers(0, 1 << 62, (n, 2, k, N), dtype=np.uint64) % q[None, None, :, None]).astype(np.uint64)
+        a = eng.dev_from(cts)
+        out = eng.dev_alloc(n * 2 * k * N)
+        for _ in range(2):
+            eng.raw_multiply_relin(0, a, a, n, out)
+        eng.timer_start()
+        for _ in range(3):
+            eng.raw_multiply_relin(0, a, a, n, out)
+        res["gpu_square_relin_us_per_ct"] = round(eng.timer_stop_ms() / 3 * 1e3 / n, 2)
+        eng.close()
+        # CPU oracle, all host threads
+        orc = Oracle(t[N], N, k, 10, 20)
+        orc.keygen(1)
+        cpu_polys = threads * 64 // k * k
+        host = rng.integers(0, 1 << 35, cpu_polys * N, dtype=np.uint64)
+        hp = host.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+        orc.L.orc_ntt_batch(orc.h, 0, hp, cpu_polys, 0, threads)  # in place; first call warms the pages and the thread pool
+        t0 = time.perf_counter()
+        for _ in range(3):
+            orc.L.orc_ntt_batch(orc.h, 0, hp, cpu_polys, 0, threads)
+        res["cpu_ntt_Mpolys_s"] = round(3 * cpu_polys / (time.perf_counter() - t0) / 1e6, 3)
+        m = min(n, 2 * threads)
+        t0 = time.perf_counter()
+        orc.square_layer(cts[:m].reshape(m, -1), threads=threads)
+        res["cpu_square_relin_us_per_ct"] = round((time.perf_counter() - t0) * 1e6 / m, 1)
+        res["cpu_threads"] = threads
+        res["speedup_ntt"] = round(res["gpu_ntt_Mpolys_s"] / res["cpu_ntt_Mpolys_s"], 1)
+        res["speedup_square_relin"] = round(res["cpu_square_relin_us_per_ct"] / res["gpu_square_relin_us_per_ct"], 1)
+        print(json.dumps(res), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -372,8 +439,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--plain-moduli", type=int, default=2, choices=[1, 2])
+    ap.add_argument("--microbench", action="store_true", help="NTT / multiply+relinearise micro-benchmark (BASELINE config 5), one JSON line per case")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.microbench:
+        run_microbench(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
