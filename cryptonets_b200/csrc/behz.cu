@@ -178,16 +178,6 @@ __global__ void __launch_bounds__(256) k_ks_mac(const u64 *__restrict__ digits, 
     acc[o + (size_t)k * N] = barrett128(a1, m);
 }
 
-__global__ void __launch_bounds__(256) k_split3(const u64 *__restrict__ ct3, u64 *__restrict__ base, u64 *__restrict__ c2, int n, int kN) {
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)n * 3 * kN;
-    if (gid >= total) return;
-    const size_t c = gid / (3 * (size_t)kN), r = gid % (3 * (size_t)kN);
-    const u64 v = ct3[gid];
-    if (r < 2 * (size_t)kN) base[c * 2 * kN + r] = v;
-    else c2[c * kN + (r - 2 * (size_t)kN)] = v;
-}
-
 // ---- Decryptor::decrypt scale-and-round through {t, gamma}
 __global__ void __launch_bounds__(256) k_decrypt_round(const u64 *__restrict__ xs, u64 *__restrict__ plain, int n, int logn,
                                                       const BehzConst *__restrict__ gbc, PlainConst pc) {
@@ -233,11 +223,6 @@ cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *d, int n, int kt
 cudaError_t launch_ks_mac(const u64 *digits, const u64 *key, u64 *acc, int n, int D, int k, int logn, const BehzConst *bc, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     k_ks_mac<<<blocks_for(((size_t)n * k) << logn), 256, 0, s>>>(digits, key, acc, n, D, logn, bc);
-    return cudaGetLastError();
-}
-cudaError_t launch_split3(const u64 *ct3, u64 *base, u64 *c2, int n, int k, int logn, cudaStream_t s) {
-    if (n <= 0) return cudaSuccess;
-    k_split3<<<blocks_for((size_t)n * 3 * k << logn), 256, 0, s>>>(ct3, base, c2, n, k << logn);
     return cudaGetLastError();
 }
 cudaError_t launch_decrypt_round(const u64 *x, u64 *plain, int n, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s) {

@@ -150,7 +150,6 @@ cudaError_t launch_ks_mac_fp(const u64 *digits, const u64 *key, u64 *acc, int n,
 // ---- K6: key-switch inner product. digits [n][D][k][N] (NTT), key [D][2][k][N] (NTT) -> acc [n][2][k][N] (NTT)
 cudaError_t launch_ks_mac(const u64 *digits, const u64 *key, u64 *acc, int n, int D, int k, int logn, const BehzConst *bc, cudaStream_t s);
 // split a size-3 array [n][3][k][N] view: base[n][2][k][N] = (c0,c1), c2[n][k][N]
-cudaError_t launch_split3(const u64 *ct3, u64 *base, u64 *c2, int n, int k, int logn, cudaStream_t s);
 
 // ---- sampling / encode / encrypt / decrypt
 enum SampleKind { SAMPLE_TERNARY = 0, SAMPLE_NOISE = 1, SAMPLE_UNIFORM = 2 };

@@ -142,7 +142,6 @@ u64 *Context::ws_alloc(size_t words) {
     ws_used += words;
     return b->p;
 }
-void Context::ws_reserve(size_t) {}
 void Context::sync() {
     for (cudaStream_t s : streams) CNHE_CUDA(cudaStreamSynchronize(s));
 }

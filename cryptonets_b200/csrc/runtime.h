@@ -102,9 +102,7 @@ struct Context {
     void prof_begin(int family, double bytes);
     void prof_end();
     void prof_flush();
-    // workspace arena (grown on demand, reused by every op)
-    u64 *ws = nullptr;
-    size_t ws_words = 0, ws_used = 0;
+    size_t ws_used = 0; // words handed out as temporaries since the last release (diagnostic)
     // host CRT data of the wrapper ("HE Wrapper/EncryptedSealBfvVector.cs:79-90")
     unsigned __int128 big_factor = 0;
     std::vector<unsigned __int128> crt_coeff;
@@ -116,9 +114,7 @@ struct Context {
 
     ~Context();
     size_t ct_words() const { return (size_t)2 * k * N; }
-    void ws_reset() { ws_used = 0; }
-    u64 *ws_alloc(size_t words);   // valid until the next ws_reset(); may synchronise when growing
-    void ws_reserve(size_t words); // grow before taking pointers
+    u64 *ws_alloc(size_t words); // temporary of the current operation: released (stream ordered / recycled) by WsScope or the next API call
     BufRef alloc(size_t words) { return std::make_shared<DevBuf>(words, stream, this); }
     // Large blocks (layer slabs, the 1 GB digit waves) are recycled per stream: a block released on stream S is handed to the next
     // request of a similar size on S without a driver call -- stream order makes that safe, and it removes cudaMallocAsync's slow path

@@ -179,3 +179,36 @@ def test_rowmajor_matrix_vector_batched_equals_per_row(F, force_dense):
     for ch in range(F.engine.P):
         for blk in range(a.vec.blocks):
             assert np.array_equal(a.vec.export_raw(ch, blk), b.vec.export_raw(ch, blk)), (ch, blk)
+
+
+def test_pipelined_import_export_and_batched_dispose(F):
+    """The serving-loop entry points: cnhe_vecs_import_raw on the upload stream (several imports in flight, slots rotating),
+    cnhe_vecs_export_raw_async tickets waited out of order, cnhe_vecs_destroy.  Every batch must come back word for word, and the
+    vectors imported from host words must decrypt to the values that were encrypted."""
+    import torch
+    eng = F.engine
+    rng = np.random.default_rng(4)
+    n = 6
+    vals = rng.integers(-500, 500, (n, eng.N)).astype(np.float64)
+    src = eng.encrypt_many(vals, 3.0)
+    words = eng.export_raw_many(src)                                  # [P][n][1][ct_words], synchronous path
+    host = torch.from_numpy(words.reshape(-1).astype(np.int64)).pin_memory()
+    outs = [torch.zeros_like(host).pin_memory() for _ in range(4)]
+    batches, tickets = [], []
+    for i in range(4):                                                # 4 uploads queued back to back, none waited for
+        vecs = eng.import_raw_many(host.data_ptr(), n, 1, eng.N, 3.0)
+        batches.append(vecs)
+        tickets.append(eng.export_raw_many_async(vecs, outs[i].data_ptr()))
+    for i in (2, 0, 3, 1):
+        eng.export_wait(tickets[i])
+        assert torch.equal(outs[i], host), i
+    from cryptonets_b200.he import B200BfvVector
+    assert np.array_equal(B200BfvVector(F, batches[3][2]).Decrypt(), vals[2])
+    for vecs in batches:
+        eng.dispose_many(vecs)
+        assert all(not v.h for v in vecs)
+    eng.dispose_many(src)
+    eng.dispose_many([])                                              # no-op
+    again = eng.import_raw_many(host.data_ptr(), n, 1, eng.N, 3.0)    # slots are reusable after their release
+    assert np.array_equal(eng.export_raw_many(again).reshape(-1), words.reshape(-1))
+    eng.dispose_many(again)
