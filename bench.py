@@ -235,7 +235,8 @@ def run_b200(args):
         forward(layers, xm).Dispose()
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:  # one nvidia-smi loop per job, on the rank that reports
+        sampler.start()
     launches0 = eng.launch_count()
     eng.prof_enable(True)
     eng.timer_start()
@@ -339,7 +340,8 @@ def run_b200(args):
                 # ncu dram__bytes_read.sum + dram__bytes_write.sum of one k_ntt_forward_digits_fp launch (128-ciphertext wave = 16000
                 # transforms, 2.10 GB algorithmic at 16N per transform): the digit source is shared by 125 transforms through L2
                 "traffic": 1036.6e6, "traffic_source": "profiles/r01_square_path_ncu.txt (k_ntt_forward_digits_fp<13>, 42.4 MB read + 994.2 MB written per launch)",
-                "launches_timed": fam["launches"], "share_of_step": fam["ms"] / ms if ms else None,
+                "launches_timed": fam["launches"], "algorithmic_bytes_per_launch": fam["bytes"] / max(1, fam["launches"]),
+                "avg_launch_ms": fam["ms"] / max(1, fam["launches"]), "share_of_step": fam["ms"] / ms if ms else None,
                 "families_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}
         cpu_threads = os.cpu_count() or 1
         cpu_sec, cpu_desc = cpu_sample(primes, cpu_threads)
