@@ -90,6 +90,18 @@ struct BehzConstF {
     double inv_B_mod_msk, msk_half, B_mod_q[KMAX];
     u64 q_u[KMAX], b_u[KBMAX]; // the moduli as integers (sign fix-up of canonical outputs on the integer pipe)
 };
+// Constants of the folded fast_floor / fastbconv_sk kernel (k_behz_floor_fold_fp), per plaintext modulus: every product by a constant
+// that SEAL applies in sequence (x t, x q-hat_i^-1, x q^-1, x B-hat_j^-1) is merged into the next conversion matrix on the host --
+// the same residues (modular arithmetic is exact), 19 % fewer FP64 instructions.
+struct FloorConstF {
+    int k, kb, pad0_, pad1_;
+    double qd[KMAX], qinv[KMAX], bd[KBMAX], binv[KBMAX];
+    double xq[KMAX];              // t * (q/q_i)^-1 mod q_i
+    double xb[KBMAX];             // j < kb-1: t * q^-1 * B-hat_j^-1 mod p_j;  j = kb-1 (m_sk): t * q^-1 mod m_sk
+    double conv[KBMAX][KMAX];     // (q/q_i) * q^-1 (* B-hat_j^-1 for j < kb-1) mod p_j
+    double bhat_mod_q[KMAX][KBMAX], bhat_mod_msk[KBMAX];
+    double inv_B_mod_msk, msk_half, B_mod_q[KMAX];
+};
 // Per plaintext modulus t.
 struct PlainConst {
     u64 t, threshold;                 // (t+1)/2
@@ -145,6 +157,8 @@ cudaError_t launch_behz_floor(const u64 *d, u64 *out3, int n, u64 t, int logn, c
 cudaError_t launch_behz_lift_fp(const u64 *const *ct_ptrs, u64 *out, int n, int logn, const BehzConstF *f, int lazy, cudaStream_t s);
 cudaError_t launch_behz_tensor_fp(const u64 *a, const u64 *b, u64 *d, int n, int kt, int logn, const BehzConstF *f, int lazy, cudaStream_t s);
 cudaError_t launch_behz_floor_fp(const u64 *d, u64 *out3, int n, u64 t, int logn, const BehzConstF *f, int lazy, cudaStream_t s);
+// folded constants + software-pipelined loads (lazy input only)
+cudaError_t launch_behz_floor_fold_fp(const u64 *d, u64 *out3, int n, int logn, const FloorConstF *f, cudaStream_t s);
 cudaError_t launch_ks_mac_fp(const u64 *digits, const u64 *key, u64 *acc, int n, int D, int k, int logn, const BehzConstF *f, int lazy,
                              cudaStream_t s);
 // ---- K6: key-switch inner product. digits [n][D][k][N] (NTT), key [D][2][k][N] (NTT) -> acc [n][2][k][N] (NTT)

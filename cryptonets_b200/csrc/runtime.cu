@@ -570,6 +570,31 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
             pc.qhat_mod_t[i] = hm::product_mod(c.q, i, t);
             pc.qhat_mod_gamma[i] = hm::product_mod(c.q, i, GAMMA);
         }
+        { // folded constants of the floor kernel (FloorConstF)
+            FloorConstF &ff = ch.floor_f;
+            memset(&ff, 0, sizeof(ff));
+            auto cen = [](u64 v, u64 p) { return v > p / 2 ? -(double)(p - v) : (double)v; };
+            ff.k = k; ff.kb = kb;
+            const int na_ = kb - 1;
+            for (int i = 0; i < k; i++) {
+                const u64 p = c.q[i];
+                ff.qd[i] = (double)p; ff.qinv[i] = 1.0 / (double)p;
+                ff.xq[i] = cen(hm::mul(t % p, bc.inv_qhat_mod_q[i], p), p);
+                ff.B_mod_q[i] = cen(bc.B_mod_q[i], p);
+                for (int j = 0; j < na_; j++) ff.bhat_mod_q[i][j] = cen(bc.bhat_mod_q[i][j], p);
+            }
+            for (int j = 0; j < kb; j++) {
+                const u64 p = c.bsk[j];
+                ff.bd[j] = (double)p; ff.binv[j] = 1.0 / (double)p;
+                u64 post = bc.inv_q_mod_bsk[j];                                   // q^-1 mod p_j ...
+                if (j < na_) post = hm::mul(post, bc.inv_bhat_mod_b[j], p);       // ... times B-hat_j^-1 for the base-B primes
+                ff.xb[j] = cen(hm::mul(t % p, post, p), p);
+                for (int i = 0; i < k; i++) ff.conv[j][i] = cen(hm::mul(bc.qhat_mod_bsk[j][i], post, p), p);
+            }
+            for (int j = 0; j < na_; j++) ff.bhat_mod_msk[j] = cen(bc.bhat_mod_msk[j], M_SK);
+            ff.inv_B_mod_msk = cen(bc.inv_B_mod_msk, M_SK);
+            ff.msk_half = (double)(M_SK >> 1);
+        }
         pc.neg_inv_q_mod_t = hm::neg(hm::inv(hm::product_mod(c.q, -1, t), t), t);
         pc.neg_inv_q_mod_gamma = hm::neg(hm::inv(hm::product_mod(c.q, -1, GAMMA), GAMMA), GAMMA);
         pc.inv_gamma_mod_t = hm::inv(GAMMA % t, t);
@@ -702,7 +727,9 @@ static void multiply_chunk(Context &c, int ch, const std::vector<const u64 *> &a
         c.check(launch_ntt_inverse(D, D, m * 3 * kt, c.logN, c.d_tabs, 0, kt, fmt, c.stream), "ntt_inverse");
     }
     PROF(2, 8.0 * N * m * 3 * (kt + k));
-    if (c.fp_elementwise) c.check(launch_behz_floor_fp(D, out3, m, c.ch[ch].t, c.logN, &c.h_bf, lazy, c.stream), "behz_floor_fp");
+    static const bool fold = getenv("CNHE_FLOOR_NOFOLD") == nullptr;
+    if (c.fp_elementwise && lazy && fold) c.check(launch_behz_floor_fold_fp(D, out3, m, c.logN, &c.ch[ch].floor_f, c.stream), "behz_floor_fold_fp");
+    else if (c.fp_elementwise) c.check(launch_behz_floor_fp(D, out3, m, c.ch[ch].t, c.logN, &c.h_bf, lazy, c.stream), "behz_floor_fp");
     else c.check(launch_behz_floor(D, out3, m, c.ch[ch].t, c.logN, c.d_bc, c.stream), "behz_floor");
 }
 void op_multiply(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out3) {

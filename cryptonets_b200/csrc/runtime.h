@@ -44,6 +44,7 @@ struct Channel { // one plaintext modulus (one AtomicSealBfvEncryptedEnvironment
     std::map<u64, BufRef> glk;
     u64 seed = 0;
     u64 nonce = 1; // running encryption counter
+    FloorConstF floor_f; // folded fast_floor constants for this t (valid when the context's fp_elementwise is set)
 };
 
 struct Context {
