@@ -339,7 +339,7 @@ def run_b200(args):
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)",
                 # ncu dram__bytes_read.sum + dram__bytes_write.sum of one k_ntt_forward_digits_fp launch (128-ciphertext wave = 16000
                 # transforms, 2.10 GB algorithmic at 16N per transform): the digit source is shared by 125 transforms through L2
-                "traffic": 1036.6e6, "traffic_source": "profiles/r01_square_path_ncu.txt (k_ntt_forward_digits_fp<13>, 42.4 MB read + 994.2 MB written per launch)",
+                "traffic": 1038.2e6, "traffic_source": "profiles/r01_square_path_v2_ncu.txt (k_ntt_forward_digits_fp<13,1>, 42.3 MB read + 995.9 MB written per launch)",
                 "launches_timed": fam["launches"], "algorithmic_bytes_per_launch": fam["bytes"] / max(1, fam["launches"]),
                 "avg_launch_ms": fam["ms"] / max(1, fam["launches"]), "share_of_step": fam["ms"] / ms if ms else None,
                 "families_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}
