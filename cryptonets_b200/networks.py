@@ -19,6 +19,7 @@ LOLA_SMALL_PRIMES = [2277377, 2424833]            # LoLaCryptonets.cs:285
 LOLA_PRIMES = [557057, 638977, 737281, 786433]    # LoLaCryptonets.cs:208 (N=8192, default decomposition bit counts)
 LOLA_DENSE_PRIMES = [34359771137, 34360754177]    # LoLaCryptonets.cs:123 (N=16384, w=60, SmallModulusCount=7)
 CIFAR_PRIMES = [957181001729, 957181034497]       # LolaCifarCryptoNet.cs:35 (N=16384, w=60, SmallModulusCount=8)
+LOLA_LARGE_PRIMES = [2148728833, 2148794369, 2149810177]  # LoLaCryptonets.cs:336 (N=16384, w=60, SmallModulusCount=7)
 
 
 def load_weights(name, shapes, seed=0):
@@ -167,4 +168,38 @@ def lola_cifar(factory, images, weights=None):
                           InputFormat=EVectorFormat.dense, ForceDenseFormat=True)
     act5 = SquareActivation(Source=dense4)
     dense6 = LLDenseLayer(Source=act5, Weights=w["Weights_2"], Bias=w["Biases_2"], WeightsScale=512.0, InputFormat=EVectorFormat.dense)
+    return dense6, reader
+
+
+def lola_large_weights(seed=9):
+    """Synthetic weights with the shapes and per-layer spread of the shipped `MnistLargeWeight.csv` / `MnistLargeBias.csv`:
+    conv 83 x (8*8), conv-as-dense 163 x (83*6*6), dense 10 x 2608."""
+    rng = np.random.default_rng(seed)
+
+    def draw(n, std, cap):
+        return np.clip(rng.normal(0, std, n), -cap, cap)
+
+    return dict(Weights_0=draw(83 * 64, 0.062, 0.46), Biases_0=draw(83, 0.088, 0.35), Weights_1=draw(163 * 83 * 36, 0.025, 0.117),
+                Biases_1=draw(163, 0.039, 0.09), Weights_2=draw(10 * 2608, 0.42, 1.63), Biases_2=draw(10, 1.6, 3.9))
+
+
+def lola_large(factory, images, weights=None):
+    """Large LoLa (`LoLaCryptonets.cs:330-409`): 28x28 image as im2col [144 x 64], conv 83 maps of 8x8 stride 2 (pixels are NOT
+    normalised; the weights carry the 1/256), square, the second convolution (163 maps of 83x6x6, stride 2 over 83x12x12) as a
+    2608 x 11952 row-major dense layer with ForceDenseFormat, square, dense 2608 -> 10."""
+    w = weights or lola_large_weights()
+    reader = LLConvReader(images, Scale=16.0, NormalizationFactor=1.0, InputShape=[1, 28, 28], KernelShape=[1, 8, 8], Stride=[1000, 2, 2],
+                          Upperpadding=[0, 1, 1], Lowerpadding=[0, 1, 1])
+    enc = EncryptLayer(Source=reader, Factory=factory)
+    conv1 = LLPoolLayer(Source=enc, InputShape=[1, 28, 28], KernelShape=[1, 8, 8], Upperpadding=[0, 1, 1], Lowerpadding=[0, 1, 1],
+                        Stride=[1000, 2, 2], MapCount=[83, 1, 1], WeightsScale=4096, Weights=np.asarray(w["Weights_0"]) / 256.0, Bias=w["Biases_0"])
+    vec2 = LLVectorizeLayer(Source=conv1)
+    act3 = SquareActivation(Source=vec2)
+    ce = ConvolutionEngine()
+    ce.InputShape, ce.KernelShape, ce.Stride, ce.MapCount = [83, 12, 12], [83, 6, 6], [83, 2, 2], [163, 1, 1]
+    ce.Padding = [False, False, False]
+    dense4 = LLDenseLayer(Source=act3, WeightsScale=64, Weights=ce.GetDenseWeights(w["Weights_1"]), Bias=ce.GetDenseBias(w["Biases_1"]),
+                          InputFormat=EVectorFormat.dense, ForceDenseFormat=True)
+    act5 = SquareActivation(Source=dense4)
+    dense6 = LLDenseLayer(Source=act5, Weights=w["Weights_2"], Bias=w["Biases_2"], WeightsScale=512, InputFormat=EVectorFormat.dense)
     return dense6, reader

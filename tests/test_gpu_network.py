@@ -280,3 +280,33 @@ def test_lola_cifar_scores_equal_raw_backend(small_modulus_count):
             assert 10 <= budget <= 40
     finally:
         f.Dispose()
+
+
+@pytest.mark.parametrize("small_modulus_count", [8, 7])
+def test_lola_large_scores_equal_raw_backend(small_modulus_count):
+    """Large LoLa (LoLaCryptonets.cs:330-409; 3 plaintext primes, N=16384, w=60) with synthetic weights of the shipped shapes: 83-map
+    8x8 convolution on un-normalised pixels, square, 2608 x 11952 row-major dense layer (ForceDenseFormat), square, dense -> 10.
+    Same budget situation as LoLa-Dense / CIFAR: end to end with one more prime than the reference's SmallModulusCount=7, layer by layer
+    through the second square with 7."""
+    from cryptonets_b200.he import B200BfvFactory
+    from cryptonets_b200.networks import LOLA_LARGE_PRIMES, lola_large, synthetic_mnist
+    from cryptonets_b200.raw import RawFactory
+    f = B200BfvFactory(LOLA_LARGE_PRIMES, 16384, DecompositionBitCount=60, GaloisDecompositionBitCount=60,
+                       SmallModulusCount=small_modulus_count, seed=5)
+    try:
+        imgs = synthetic_mnist(1, seed=3)
+        net, rd = lola_large(f, imgs)
+        net.PrepareNetwork()
+        raw_net, rrd = lola_large(RawFactory(16384), imgs)
+        raw_net.PrepareNetwork()
+        if small_modulus_count == 8:
+            got = np.asarray(net.GetNext().Decrypt()).reshape(-1)
+            want = np.asarray(raw_net.GetNext().Decrypt()).reshape(-1)
+            assert np.allclose(got, want, rtol=1e-9, atol=1e-9) and got.argmax() == want.argmax()
+        else:
+            ma, mb = _compare_layerwise(net, raw_net, rd, rrd, upto=-1)
+            assert np.allclose(np.asarray(ma.Decrypt()), np.asarray(mb.Decrypt()), rtol=1e-9, atol=1e-9)
+            budget = min(f.engine.noise_budget(v.vec, ch, 0) for v in ma.vectors for ch in range(3))
+            assert 5 <= budget <= 60
+    finally:
+        f.Dispose()

@@ -175,3 +175,44 @@ def test_packed_dense_and_interleave_known_answer():
     for i in range(4):
         row, col = divmod(i, 2)
         assert np.isclose(z[(col + 1) * 8 - 1 - row], want[i])
+
+
+def test_lola_large_and_cifar_topologies_on_raw_backend():
+    """LoLa-Large and LoLa-CIFAR (synthetic weights of the shipped shapes) against a direct numpy evaluation: conv -> square ->
+    conv-as-dense (ConvolutionEngine.GetDenseWeights) -> square -> dense."""
+    from cryptonets_b200.networks import cifar_weights, lola_cifar, lola_large, lola_large_weights, synthetic_cifar
+
+    def direct(x, w, shape1, kern1, pad, maps1, s0, ws0, shape2, kern2, pad2, stride2, maps2, ws1, ws2):
+        ce = ConvolutionEngine()
+        ce.InputShape, ce.KernelShape, ce.Stride, ce.MapCount = shape1, kern1, [1000, 2, 2], [maps1, 1, 1]
+        ce.Upperpadding, ce.Lowerpadding = pad, pad
+        a = ce.GetDenseWeights(np.rint(np.asarray(w["Weights_0"]) * ws0)).reshape(-1, int(np.prod(shape1))) @ x
+        a = a + np.rint(ce.GetDenseBias(w["Biases_0"]) * s0 * ws0)
+        a = a * a
+        ce2 = ConvolutionEngine()
+        ce2.InputShape, ce2.KernelShape, ce2.Stride, ce2.MapCount = shape2, kern2, stride2, [maps2, 1, 1]
+        if pad2:
+            ce2.Upperpadding, ce2.Lowerpadding = pad2, pad2
+        s1 = (s0 * ws0) ** 2
+        b = np.rint(ce2.GetDenseWeights(w["Weights_1"]) * ws1).reshape(-1, a.size) @ a + np.rint(ce2.GetDenseBias(w["Biases_1"]) * s1 * ws1)
+        b = b * b
+        s2 = (s1 * ws1) ** 2
+        out = np.rint(np.asarray(w["Weights_2"]) * ws2).reshape(10, -1) @ b + np.rint(np.asarray(w["Biases_2"]) * s2 * ws2)
+        return out / (s2 * ws2)
+
+    img = synthetic_mnist(1, seed=3)
+    w = lola_large_weights()
+    net, _ = lola_large(RawFactory(16384), img, weights=w)
+    net.PrepareNetwork()
+    got = np.asarray(net.GetNext().Decrypt(None)).reshape(-1)
+    wl = dict(w, Weights_0=np.asarray(w["Weights_0"]) / 256.0)
+    want = direct(np.rint(img[0] * 16.0), wl, [1, 28, 28], [1, 8, 8], [0, 1, 1], 83, 16.0, 4096, [83, 12, 12], [83, 6, 6], None, [83, 2, 2], 163, 64, 512)
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-12)
+    img = synthetic_cifar(1)
+    w = cifar_weights()
+    net, _ = lola_cifar(RawFactory(16384), img, weights=w)
+    net.PrepareNetwork()
+    got = np.asarray(net.GetNext().Decrypt(None)).reshape(-1)
+    want = direct(np.rint(img[0] / 256.0 * 8.0), w, [3, 32, 32], [3, 8, 8], [0, 1, 1], 83, 8.0, 256.0, [83, 14, 14], [83, 10, 10], [0, 4, 4], [83, 2, 2], 112,
+                  512.0, 512.0)
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-12)
