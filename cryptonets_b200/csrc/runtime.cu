@@ -666,9 +666,10 @@ void op_key_switch(Context &c, const u64 *target, size_t target_stride, int n, c
     const size_t N = c.N;
     const int fpq = fp_range(c, 0, k);
     const bool lazy = c.lazy && fpq;
-    for (int c0 = 0; c0 < n; c0 += c.chunk) {
+    const int wave = c.wave(((size_t)dm.D * k + 2 * k) * N);
+    for (int c0 = 0; c0 < n; c0 += wave) {
         WsScope scope(c);
-        const int m = std::min(c.chunk, n - c0);
+        const int m = std::min(wave, n - c0);
         u64 *digits = c.ws_alloc((size_t)m * dm.D * k * N);
         u64 *acc = c.ws_alloc((size_t)m * 2 * k * N);
         {
@@ -734,9 +735,10 @@ static void multiply_chunk(Context &c, int ch, const std::vector<const u64 *> &a
 }
 void op_multiply(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out3) {
     const int n = (int)a.size();
-    for (int c0 = 0; c0 < n; c0 += c.chunk) {
+    const int wave = c.wave((size_t)(7 * (c.k + c.kb)) * c.N);
+    for (int c0 = 0; c0 < n; c0 += wave) {
         WsScope scope(c);
-        const int m = std::min(c.chunk, n - c0);
+        const int m = std::min(wave, n - c0);
         multiply_chunk(c, ch, a, b, c0, m, out3 + (size_t)c0 * 3 * c.k * c.N);
     }
 }
@@ -752,9 +754,10 @@ void op_multiply_relin(Context &c, int ch, const std::vector<const u64 *> &a, co
     if (!c.ch[ch].have_rlk) throw Error(-3, "relinearization keys are missing");
     const int n = (int)a.size(), k = c.k;
     const size_t N = c.N;
-    for (int c0 = 0; c0 < n; c0 += c.chunk) {
-        WsScope scope(c); // stream-ordered frees: the next chunk reuses the pool memory once these kernels are done
-        const int m = std::min(c.chunk, n - c0);
+    const int wave = c.wave(((size_t)c.dm_relin.D * k + 7 * (k + c.kb) + 5 * k) * N);
+    for (int c0 = 0; c0 < n; c0 += wave) {
+        WsScope scope(c); // stream-ordered frees: the next wave reuses the memory once these kernels are done
+        const int m = std::min(wave, n - c0);
         u64 *ct3 = c.ws_alloc((size_t)m * 3 * k * N);
         multiply_chunk(c, ch, a, b, c0, m, ct3);
         const size_t s3 = (size_t)3 * k * N;

@@ -3,6 +3,7 @@
 // plus the SEAL objects it owns (SEALContext, KeyGenerator, Evaluator, Encryptor, Decryptor, BatchEncoder).
 #pragma once
 #include <cstdint>
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -91,7 +92,11 @@ struct Context {
     int export_next = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_join = nullptr;
     std::recursive_mutex mu;
-    int chunk = 128;
+    int chunk = 1024; // ciphertexts per kernel wave (upper bound: wave() also keeps a wave's scratch under ~8 GiB)
+    int wave(size_t words_per_ct) const { // ciphertexts per wave for an operation needing `words_per_ct` scratch words per ciphertext
+        const size_t fit = ((size_t)1 << 30) / (words_per_ct ? words_per_ct : 1); // 2^30 words = 8 GiB
+        return (int)std::max<size_t>(16, std::min<size_t>((size_t)chunk, fit));
+    }
     uint64_t launches = 0;
     // optional per-kernel-family timing
     bool prof = false;
