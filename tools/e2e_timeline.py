@@ -15,6 +15,8 @@ x = np.rint(synthetic_mnist(bench.BATCH, seed=7) / 256.0 * 16.0)
 xm = f.GetEncryptedMatrix(x, EMatrixFormat.ColumnMajor, 1)
 xm.RegisterScale(16.0)
 eng.set_option("multi_stream", int(os.environ.get("MS", "1")))
+if os.environ.get("CHUNK"):
+    eng.set_option("chunk", int(os.environ["CHUNK"]))
 host_in = torch.empty(eng.P * 784 * eng.ct_words, dtype=torch.int64).pin_memory()
 host_outs = [torch.empty(eng.P * 10 * eng.ct_words, dtype=torch.int64).pin_memory() for _ in range(2)]
 eng.export_raw_many([v.vec for v in xm.vectors], host_in.data_ptr())
