@@ -25,6 +25,10 @@ _SIGS = {
     "cnhe_context_set_option": [C.c_void_p, C.c_char_p, i64],
     "cnhe_context_sync": [C.c_void_p],
     "cnhe_keys_generate": [C.c_void_p, u64],
+    "cnhe_keys_generate_secure": [C.c_void_p],
+    "cnhe_op_counts": [C.c_void_p, U64P, i32, i32],
+    "cnhe_op_name": [i32],
+    "cnhe_trace_read": [C.c_void_p, C.POINTER(C.c_int32), sz, C.POINTER(sz), i32],
     "cnhe_keys_export": [C.c_void_p, i32, i32, u64, U64P, sz],
     "cnhe_keys_import": [C.c_void_p, i32, i32, u64, U64P, sz],
     "cnhe_keys_set_seed": [C.c_void_p, i32, u64],
@@ -84,7 +88,7 @@ _SIGS = {
     "cnhe_last_error": [],
     "cnhe_version": [],
 }
-_RESTYPE = {"cnhe_last_error": C.c_char_p, "cnhe_version": C.c_char_p, "cnhe_kernel_launch_count": C.c_uint64}
+_RESTYPE = {"cnhe_op_name": C.c_char_p, "cnhe_last_error": C.c_char_p, "cnhe_version": C.c_char_p, "cnhe_kernel_launch_count": C.c_uint64}
 
 EXPORTS = sorted(_SIGS)
 

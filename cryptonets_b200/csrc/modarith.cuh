@@ -67,15 +67,54 @@ __device__ __forceinline__ u64 mul_shoup_lazy(u64 x, u64 w, u64 ws, u64 p) {
     return w * x - q * p;
 }
 
-// counter-based sampler shared with the CPU oracle (DESIGN.md "sampler")
+// ---- randomness.  Two generators behind one interface (RngKey):
+//  * secure (default): ChaCha20 keyed with 256 bits of OS entropy (getrandom) drawn per channel when the context is created and again at
+//    every cnhe_keys_generate_secure; block counter = index / 8, nonce = 64-bit stream id.  This is what SEAL's std::random_device-seeded
+//    sampler provides the reference: secret key, key-switching masks and the encryption randomness (u, e0, e1) are unpredictable.
+//  * deterministic (tests only, explicit seed): the counter-based splitmix64 sampler shared with the CPU oracle, so that keys and fresh
+//    ciphertexts are bit-comparable.  splitmix64 is an invertible mixer, NOT a cipher: never use a seeded context for real data.
 __host__ __device__ __forceinline__ u64 splitmix64(u64 x) {
     x += 0x9E3779B97F4A7C15ULL;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
     return x ^ (x >> 31);
 }
+struct RngKey {
+    u32 key[8]; // ChaCha20 key (secure mode)
+    u64 seed;   // deterministic mode
+    int secure, pad_;
+};
+__host__ __device__ __forceinline__ u32 rotl32(u32 v, int c) { return (v << c) | (v >> (32 - c)); }
+#define CNHE_QR(a, b, c, d)                                                                                            \
+    a += b; d ^= a; d = rotl32(d, 16);                                                                                 \
+    c += d; b ^= c; b = rotl32(b, 12);                                                                                 \
+    a += b; d ^= a; d = rotl32(d, 8);                                                                                  \
+    c += d; b ^= c; b = rotl32(b, 7);
+// word `i & 7` (64-bit) of ChaCha20 block `i >> 3` under nonce `stream`
+__host__ __device__ __forceinline__ u64 chacha20_word(const RngKey &rk, u64 stream, u64 i) {
+    const u64 blk = i >> 3;
+    u32 s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, rk.key[0], rk.key[1], rk.key[2], rk.key[3], rk.key[4], rk.key[5],
+                 rk.key[6],   rk.key[7],   (u32)blk,    (u32)(blk >> 32), (u32)stream, (u32)(stream >> 32)};
+    u32 x[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = s[j];
+#pragma unroll 1
+    for (int r = 0; r < 10; r++) {
+        CNHE_QR(x[0], x[4], x[8], x[12]) CNHE_QR(x[1], x[5], x[9], x[13]) CNHE_QR(x[2], x[6], x[10], x[14]) CNHE_QR(x[3], x[7], x[11], x[15])
+        CNHE_QR(x[0], x[5], x[10], x[15]) CNHE_QR(x[1], x[6], x[11], x[12]) CNHE_QR(x[2], x[7], x[8], x[13]) CNHE_QR(x[3], x[4], x[9], x[14])
+    }
+    const int w = (int)(i & 7) * 2;
+    u32 lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j += 2)
+        if (j == w) { lo = x[j] + s[j]; hi = x[j + 1] + s[j + 1]; }
+    return ((u64)hi << 32) | lo;
+}
 __host__ __device__ __forceinline__ u64 rng64(u64 seed, u64 stream, u64 i) {
     return splitmix64(splitmix64(seed ^ (stream * 0xD1342543DE82EF95ULL)) + i);
+}
+__host__ __device__ __forceinline__ u64 rng64(const RngKey &rk, u64 stream, u64 i) {
+    return rk.secure ? chacha20_word(rk, stream, i) : rng64(rk.seed, stream, i);
 }
 __host__ __device__ __forceinline__ u64 stream_id(u64 purpose, u64 a, u64 b) { return (purpose << 48) | (a << 16) | b; }
 

@@ -273,7 +273,7 @@ __device__ __forceinline__ int draw_noise(u64 r) {
 }
 __device__ __forceinline__ u64 lift_small(int v, u64 p) { return v >= 0 ? (u64)v : p - (u64)(-v); }
 
-__global__ void __launch_bounds__(256) k_sample(u64 *__restrict__ out, int n, int kind, u64 seed, u64 stream0, u64 stream_step, int k, int logn,
+__global__ void __launch_bounds__(256) k_sample(u64 *__restrict__ out, int n, int kind, RngKey seed, u64 stream0, u64 stream_step, int k, int logn,
                                                const BehzConst *__restrict__ bc) {
     const int N = 1 << logn;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) k_decode_gather(const u64 *__restrict__ p
     values[i] = plain_ntt[c * N + index_map[j]];
 }
 // ct[c] holds u*pk (both parts, coefficient form); add e0 + Delta*m to part 0 and e1 to part 1
-__global__ void __launch_bounds__(256) k_encrypt_finish(u64 *ct, const u64 *__restrict__ plain, size_t plain_stride, int n, int coeffs, u64 seed,
+__global__ void __launch_bounds__(256) k_encrypt_finish(u64 *ct, const u64 *__restrict__ plain, size_t plain_stride, int n, int coeffs, RngKey seed,
                                                        u64 nonce0, int k, int logn, const BehzConst *__restrict__ bc, PlainConst pc) {
     const int N = 1 << logn;
     const size_t kN = (size_t)k * N;
@@ -407,7 +407,7 @@ cudaError_t launch_mac_layer_fp(const u64 *const *in_ptrs, const int *gather, co
     k_mac_layer_fp<<<grid, 128, 0, s>>>(in_ptrs, gather, tiles, wd, bias, K, out_ptrs, k, logn, bc, pc);
     return cudaGetLastError();
 }
-cudaError_t launch_sample(u64 *out, int n, int kind, u64 seed, u64 stream0, u64 stream_step, int k, int logn, const BehzConst *bc, cudaStream_t s) {
+cudaError_t launch_sample(u64 *out, int n, int kind, const RngKey &seed, u64 stream0, u64 stream_step, int k, int logn, const BehzConst *bc, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     k_sample<<<blocks_for(((size_t)n * k) << logn), 256, 0, s>>>(out, n, kind, seed, stream0, stream_step, k, logn, bc);
     return cudaGetLastError();
@@ -422,7 +422,7 @@ cudaError_t launch_decode_gather(const u64 *plain_ntt, u64 *values, int n, const
     k_decode_gather<<<blocks_for((size_t)n << logn), 256, 0, s>>>(plain_ntt, values, n, index_map, logn);
     return cudaGetLastError();
 }
-cudaError_t launch_encrypt_finish(u64 *ct, const u64 *plain, size_t plain_stride, int n, int coeffs, u64 seed, u64 nonce0, int k, int logn,
+cudaError_t launch_encrypt_finish(u64 *ct, const u64 *plain, size_t plain_stride, int n, int coeffs, const RngKey &seed, u64 nonce0, int k, int logn,
                                   const BehzConst *bc, PlainConst pc, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     k_encrypt_finish<<<blocks_for(((size_t)n * 2 * k) << logn), 256, 0, s>>>(ct, plain, plain_stride, n, coeffs, seed, nonce0, k, logn, bc, pc);

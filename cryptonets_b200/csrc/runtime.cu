@@ -7,9 +7,37 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <sys/random.h>
+
 #include "hostmath.h"
 
 namespace cnhe {
+
+// 256-bit ChaCha20 key straight from the kernel CSPRNG (getrandom(2)); no fallback: a context without entropy must not encrypt
+void rng_from_os(RngKey &rk) {
+    memset(&rk, 0, sizeof(rk));
+    unsigned char *p = reinterpret_cast<unsigned char *>(rk.key);
+    size_t got = 0;
+    while (got < sizeof(rk.key)) {
+        const ssize_t r = getrandom(p + got, sizeof(rk.key) - got, 0);
+        if (r <= 0) throw Error(-2, "getrandom() failed: no OS entropy for key generation / encryption");
+        got += (size_t)r;
+    }
+    rk.secure = 1;
+}
+const char *op_kind_name(int kind) {
+    static const char *names[] = {"Encryption", "Decryption", "Multiplication", "Relinarization", "PlainMultiplication", "ScalarMultiplication",
+                                  "Addition", "PlainAddition", "Subtraction", "PlainSubtraction", "Rotation", "ColumnRotation", "AddMany",
+                                  "AddManyItemCount"};
+    return kind >= 0 && kind < Context::OP_COUNT ? names[kind] : "?";
+}
+void Context::note(OpKind kind, int channel, int n, const u64 *first_out) {
+    op_count[kind] += (uint64_t)n;
+    if (!trace_noise || kind == OP_ADD_MANY_ITEMS) return;
+    int budget = -1;
+    if (first_out && channel >= 0 && channel < P && ch[channel].have_sk) budget = op_noise_budget(*this, channel, first_out);
+    trace.push_back({(int)kind, channel, n, budget});
+}
 
 void cuda_check(cudaError_t e, const char *what) {
     if (e != cudaSuccess) throw Error(-2, std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
@@ -129,12 +157,7 @@ DevBuf::~DevBuf() {
     cudaFreeAsync(p, stream);
 }
 
-static std::vector<BufRef> &temps_of(Context &c);
-struct TempStore {
-    std::map<Context *, std::vector<BufRef>> m;
-};
-static TempStore g_temps;
-static std::vector<BufRef> &temps_of(Context &c) { return g_temps.m[&c]; }
+static std::vector<BufRef> &temps_of(Context &c) { return c.temps; } // per context, guarded by the context mutex
 
 u64 *Context::ws_alloc(size_t words) {
     BufRef b = alloc(words ? words : 1);
@@ -217,7 +240,7 @@ Context::~Context() {
     for (cudaStream_t s : streams) cudaStreamSynchronize(s);
     if (copy_stream) cudaStreamSynchronize(copy_stream);
     recycle_on = false; // buffers released from here on go straight back to the driver
-    g_temps.m.erase(this);
+    temps.clear();
     ch.clear();
     drop_recycled();
     if (d_bc) cudaFree(d_bc);
@@ -552,6 +575,7 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
         Channel &ch = c.ch[ci];
         const u64 t = c.t[ci];
         ch.t = t;
+        rng_from_os(ch.rng); // encryption randomness of a context that only imports a public key is unpredictable too
         ch.mod_id = k + kb + ci;
         PlainConst &pc = ch.pc;
         memset(&pc, 0, sizeof(pc));
@@ -741,6 +765,7 @@ void op_multiply(Context &c, int ch, const std::vector<const u64 *> &a, const st
         const int m = std::min(wave, n - c0);
         multiply_chunk(c, ch, a, b, c0, m, out3 + (size_t)c0 * 3 * c.k * c.N);
     }
+    c.note(Context::OP_MULTIPLY, ch, n);
 }
 void op_relinearize(Context &c, int ch, const u64 *in3, int n, u64 *out2) {
     if (!c.ch[ch].have_rlk) throw Error(-3, "relinearization keys are missing");
@@ -749,6 +774,7 @@ void op_relinearize(Context &c, int ch, const u64 *in3, int n, u64 *out2) {
     // the size-3 layout [c0 c1 c2] is consumed in place: c2 is the key-switch target, (c0, c1) the base it is added to
     const size_t s3 = (size_t)3 * k * N;
     op_key_switch(c, in3 + (size_t)2 * k * N, s3, n, c.ch[ch].rlk->p, c.dm_relin, in3, s3, out2);
+    c.note(Context::OP_RELINEARIZE, ch, n, out2);
 }
 void op_multiply_relin(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out2) {
     if (!c.ch[ch].have_rlk) throw Error(-3, "relinearization keys are missing");
@@ -763,6 +789,8 @@ void op_multiply_relin(Context &c, int ch, const std::vector<const u64 *> &a, co
         const size_t s3 = (size_t)3 * k * N;
         op_key_switch(c, ct3 + (size_t)2 * k * N, s3, m, c.ch[ch].rlk->p, c.dm_relin, ct3, s3, out2 + (size_t)c0 * 2 * k * N);
     }
+    c.op_count[Context::OP_MULTIPLY] += (uint64_t)n;
+    c.note(Context::OP_RELINEARIZE, ch, n, out2);
 }
 
 u64 galois_elt_from_step(const Context &c, int steps) { // Evaluator::galois_elt_from_step: positive = rotate left
@@ -791,6 +819,7 @@ void op_apply_galois(Context &c, int ch, const u64 *in, int n, u64 elt, u64 *out
         c.check(launch_galois(in + (size_t)c0 * 2 * k * N, base, p1, m, einv, k, c.logN, c.d_bc, c.stream), "galois");
         op_key_switch(c, p1, (size_t)k * N, m, it->second->p, c.dm_galois, base, (size_t)2 * k * N, out + (size_t)c0 * 2 * k * N);
     }
+    c.note(elt == m2 - 1 ? Context::OP_ROTATE_COLUMNS : Context::OP_ROTATE_ROWS_HOP, ch, n, out);
 }
 static std::vector<int> naf(int value) { // non-adjacent form, least significant term first (SEAL util::naf)
     std::vector<int> res;
@@ -835,6 +864,7 @@ void op_multiply_plain_dense(Context &c, int ch, const u64 *ct, int n, const u64
     c.check(launch_ntt_forward(ct, tmp, n * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
     c.check(launch_dyadic_bcast(tmp, lifted, tmp, n, 2, 1, plain_per_ct ? 1 : 0, k, c.logN, c.d_bc, c.stream), "dyadic");
     c.check(launch_ntt_inverse(tmp, out, n * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_inverse");
+    c.note(Context::OP_MULTIPLY_PLAIN, ch, n, out);
 }
 // one ciphertext times n dense plaintexts: out[i] = ct * plain[i]   (row-major matrix x vector: every row against the same input)
 void op_multiply_plain_dense_bcast(Context &c, int ch, const u64 *ct, const u64 *plains, int n, u64 *out) {
@@ -852,6 +882,7 @@ void op_multiply_plain_dense_bcast(Context &c, int ch, const u64 *ct, const u64 
         c.check(launch_dyadic_bcast(ctn, lifted, dst, m, 2, 0, 1, k, c.logN, c.d_bc, c.stream), "dyadic");
         c.check(launch_ntt_inverse(dst, dst, m * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_inverse");
     }
+    c.note(Context::OP_MULTIPLY_PLAIN, ch, n, out);
 }
 void op_encode(Context &c, int ch, const u64 *values, int n, int count, u64 *plain) {
     c.check(launch_encode_scatter(values, plain, n, count, c.d_index_map, c.logN, c.stream), "encode_scatter");
@@ -862,6 +893,18 @@ void op_decode(Context &c, int ch, const u64 *plain, int n, u64 *values) {
     c.check(launch_ntt_forward(plain, tmp, n, c.logN, c.d_tabs, c.ch[ch].mod_id, 1, fp_range(c, c.ch[ch].mod_id, 1), c.stream), "ntt_forward(t)");
     c.check(launch_decode_gather(tmp, values, n, c.d_index_map, c.logN, c.stream), "decode_gather");
 }
+u64 take_nonces(Context &c, int chi, u64 n) {
+    Channel &ch = c.ch[chi];
+    if (n >= (1ULL << 31)) throw Error(-1, "too many encryptions in one call");
+    if (ch.nonce + n >= (1ULL << 32)) { // the stream id carries 32 bits of the counter
+        if (!ch.rng.secure) throw Error(-1, "deterministic (seeded, test-only) channel exhausted its 2^32 encryption nonces");
+        rng_from_os(ch.rng);
+        ch.nonce = 1;
+    }
+    const u64 n0 = ch.nonce;
+    ch.nonce += n;
+    return n0;
+}
 void op_encrypt(Context &c, int chi, const u64 *plain, size_t plain_stride, int n, int coeffs, u64 nonce0, u64 *ct) {
     Channel &ch = c.ch[chi];
     if (!ch.have_pk) throw Error(-3, "public key is missing");
@@ -870,15 +913,16 @@ void op_encrypt(Context &c, int chi, const u64 *plain, size_t plain_stride, int 
     for (int c0 = 0; c0 < n; c0 += 4 * c.chunk) {
         const int m = std::min(4 * c.chunk, n - c0);
         u64 *u = c.ws_alloc((size_t)m * k * N);
-        c.check(launch_sample(u, m, SAMPLE_TERNARY, ch.seed, stream_id(8, nonce0 + c0, 0), 1ULL << 16, k, c.logN, c.d_bc, c.stream), "sample");
+        c.check(launch_sample(u, m, SAMPLE_TERNARY, ch.rng, stream_id(8, nonce0 + c0, 0), 1ULL << 16, k, c.logN, c.d_bc, c.stream), "sample");
         c.check(launch_ntt_forward(u, u, m * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
         u64 *dst = ct + (size_t)c0 * 2 * k * N;
         c.check(launch_dyadic_bcast(ch.pk->p, u, dst, m, 2, 0, 1, k, c.logN, c.d_bc, c.stream), "dyadic");
         c.check(launch_ntt_inverse(dst, dst, m * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_inverse");
-        c.check(launch_encrypt_finish(dst, plain ? plain + (size_t)c0 * plain_stride : nullptr, plain_stride, m, plain ? coeffs : 0, ch.seed,
+        c.check(launch_encrypt_finish(dst, plain ? plain + (size_t)c0 * plain_stride : nullptr, plain_stride, m, plain ? coeffs : 0, ch.rng,
                                       nonce0 + c0, k, c.logN, c.d_bc, ch.pc, c.stream),
                 "encrypt_finish");
     }
+    c.note(Context::OP_ENCRYPT, chi, n, ct);
 }
 static void dot_with_secret(Context &c, int chi, const u64 *ct, int n, u64 *x) {
     Channel &ch = c.ch[chi];
@@ -896,6 +940,7 @@ void op_decrypt(Context &c, int chi, const u64 *ct, int n, u64 *plain) {
     u64 *x = c.ws_alloc((size_t)n * c.k * c.N);
     dot_with_secret(c, chi, ct, n, x);
     c.check(launch_decrypt_round(x, plain, n, c.k, c.logN, c.d_bc, c.ch[chi].pc, c.stream), "decrypt_round");
+    c.op_count[Context::OP_DECRYPT] += (uint64_t)n;
 }
 // Decryptor::invariant_noise_budget: bits(q) - bits(|t * (c0 + c1 s) mod q|_centred) - 1, composed on the host
 int op_noise_budget(Context &c, int chi, const u64 *ct) {
@@ -1012,8 +1057,8 @@ static void make_kskeys(Context &c, Channel &ch, const u64 *target_ntt, const Di
     const size_t N = c.N, kN = (size_t)k * N;
     // c1 = a (uniform), written in place: key d part 1
     u64 *e = c.ws_alloc((size_t)D * kN), *as = c.ws_alloc((size_t)D * kN), *a = c.ws_alloc((size_t)D * kN);
-    c.check(launch_sample(a, D, SAMPLE_UNIFORM, ch.seed, stream_id(purpose_a, key_tag * 256, 0), 1ULL << 16, k, c.logN, c.d_bc, c.stream), "sample");
-    c.check(launch_sample(e, D, SAMPLE_NOISE, ch.seed, stream_id(purpose_e, key_tag * 256, 0), 1ULL << 16, k, c.logN, c.d_bc, c.stream), "sample");
+    c.check(launch_sample(a, D, SAMPLE_UNIFORM, ch.rng, stream_id(purpose_a, key_tag * 256, 0), 1ULL << 16, k, c.logN, c.d_bc, c.stream), "sample");
+    c.check(launch_sample(e, D, SAMPLE_NOISE, ch.rng, stream_id(purpose_e, key_tag * 256, 0), 1ULL << 16, k, c.logN, c.d_bc, c.stream), "sample");
     c.check(launch_ntt_forward(e, e, D * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
     c.check(launch_dyadic_bcast(a, ch.sk->p, as, D, 1, 1, 0, k, c.logN, c.d_bc, c.stream), "dyadic");
     c.check(launch_ct_add(as, e, as, (size_t)D * kN, k, c.logN, c.d_bc, 0, c.stream), "ct_add");
@@ -1029,26 +1074,27 @@ static void make_kskeys(Context &c, Channel &ch, const u64 *target_ntt, const Di
     c.h2d(dfac, factors.data(), D * 8);
     c.check(launch_key_add_scaled(out, target_ntt, dfac, dm, k, c.logN, c.d_bc, c.stream), "key_add_scaled");
 }
-void keys_generate(Context &c, u64 seed) {
+static void keys_generate_impl(Context &c, bool secure, u64 seed) {
     const int k = c.k;
     const size_t N = c.N, kN = (size_t)k * N;
     for (int ci = 0; ci < c.P; ci++) {
         c.set_channel(ci);
         Channel &ch = c.ch[ci];
-        ch.seed = seed + (u64)ci;
+        if (secure) rng_from_os(ch.rng);
+        else { memset(&ch.rng, 0, sizeof(ch.rng)); ch.rng.seed = seed + (u64)ci; }
         ch.nonce = 1;
         size_t words;
         // secret key: ternary, kept in NTT form (and a coefficient-form copy for the Galois keys)
         BufRef &sk = key_slot(c, ci, 0, 0, words, true);
         u64 *sk_coeff = c.ws_alloc(kN);
-        c.check(launch_sample(sk_coeff, 1, SAMPLE_TERNARY, ch.seed, stream_id(1, 0, 0), 0, k, c.logN, c.d_bc, c.stream), "sample");
+        c.check(launch_sample(sk_coeff, 1, SAMPLE_TERNARY, ch.rng, stream_id(1, 0, 0), 0, k, c.logN, c.d_bc, c.stream), "sample");
         c.check(launch_ntt_forward(sk_coeff, sk->p, k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
         ch.have_sk = true;
         // public key (-(a s + e), a)
         BufRef &pk = key_slot(c, ci, 1, 0, words, true);
         u64 *e = c.ws_alloc(kN), *as = c.ws_alloc(kN);
-        c.check(launch_sample(pk->p + kN, 1, SAMPLE_UNIFORM, ch.seed, stream_id(2, 0, 0), 0, k, c.logN, c.d_bc, c.stream), "sample");
-        c.check(launch_sample(e, 1, SAMPLE_NOISE, ch.seed, stream_id(3, 0, 0), 0, k, c.logN, c.d_bc, c.stream), "sample");
+        c.check(launch_sample(pk->p + kN, 1, SAMPLE_UNIFORM, ch.rng, stream_id(2, 0, 0), 0, k, c.logN, c.d_bc, c.stream), "sample");
+        c.check(launch_sample(e, 1, SAMPLE_NOISE, ch.rng, stream_id(3, 0, 0), 0, k, c.logN, c.d_bc, c.stream), "sample");
         c.check(launch_ntt_forward(e, e, k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
         c.check(launch_dyadic_bcast(pk->p + kN, sk->p, as, 1, 1, 1, 0, k, c.logN, c.d_bc, c.stream), "dyadic");
         c.check(launch_ct_add(as, e, as, kN, k, c.logN, c.d_bc, 0, c.stream), "ct_add");
@@ -1079,5 +1125,8 @@ void keys_generate(Context &c, u64 seed) {
         ws_release_all(c);
     }
 }
+
+void keys_generate(Context &c, u64 seed) { keys_generate_impl(c, false, seed); }
+void keys_generate_secure(Context &c) { keys_generate_impl(c, true, 0); }
 
 } // namespace cnhe

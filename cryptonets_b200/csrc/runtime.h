@@ -43,8 +43,8 @@ struct Channel { // one plaintext modulus (one AtomicSealBfvEncryptedEnvironment
     bool have_sk = false, have_pk = false, have_rlk = false;
     BufRef sk, pk, rlk;
     std::map<u64, BufRef> glk;
-    u64 seed = 0;
-    u64 nonce = 1; // running encryption counter
+    RngKey rng;    // secure (ChaCha20 keyed from the OS) unless a deterministic test seed was requested explicitly
+    u64 nonce = 1; // running encryption counter (32 bits enter the stream id; a secure channel re-keys before it wraps)
     FloorConstF floor_f; // folded fast_floor constants for this t (valid when the context's fp_elementwise is set)
 };
 
@@ -92,6 +92,17 @@ struct Context {
     int export_next = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_join = nullptr;
     std::recursive_mutex mu;
+    std::vector<BufRef> temps; // workspace temporaries of the operation in flight (guarded by mu)
+    // ---- operation counters (the reference's OperationsCount, "HE Wrapper/AtomicSealBfvVector.cs:211-294") and the optional
+    // per-operation noise-budget trace (CryptoTracker.TestBudget, "HE Wrapper/CryptoTracker.cs:41-52")
+    enum OpKind { OP_ENCRYPT, OP_DECRYPT, OP_MULTIPLY, OP_RELINEARIZE, OP_MULTIPLY_PLAIN, OP_MULTIPLY_SCALAR, OP_ADD, OP_ADD_PLAIN, OP_SUB,
+                  OP_SUB_PLAIN, OP_ROTATE_ROWS_HOP, OP_ROTATE_COLUMNS, OP_ADD_MANY, OP_ADD_MANY_ITEMS, OP_COUNT };
+    uint64_t op_count[OP_COUNT] = {0};
+    bool trace_noise = false;
+    struct TraceRec { int kind, channel, n, budget; };
+    std::vector<TraceRec> trace;
+    // count `n` operations of `kind`; with tracing on, also record the invariant noise budget of the first output ciphertext
+    void note(OpKind kind, int channel, int n, const u64 *first_out = nullptr);
     int chunk = 1024; // ciphertexts per kernel wave (upper bound: wave() also keeps a wave's scratch under ~8 GiB)
     int wave(size_t words_per_ct) const { // ciphertexts per wave for an operation needing `words_per_ct` scratch words per ciphertext
         const size_t fit = ((size_t)1 << 30) / (words_per_ct ? words_per_ct : 1); // 2^30 words = 8 GiB
@@ -154,7 +165,10 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
 std::vector<u64> default_coeff_modulus(uint32_t N);
 
 // ---- keys
-void keys_generate(Context &c, u64 seed);
+void keys_generate(Context &c, u64 seed); // deterministic sampler: tests only
+void keys_generate_secure(Context &c);    // fresh OS entropy per channel
+void rng_from_os(RngKey &rk);
+const char *op_kind_name(int kind);
 BufRef &key_slot(Context &c, int channel, int what, u64 arg, size_t &words, bool create);
 
 // ---- ciphertext-array operations (all asynchronous on c.stream; device pointers)
@@ -180,6 +194,8 @@ void op_multiply_plain_dense_bcast(Context &c, int ch, const u64 *ct, const u64 
 void op_encode(Context &c, int ch, const u64 *values, int n, int count, u64 *plain);
 void op_decode(Context &c, int ch, const u64 *plain, int n, u64 *values);
 // plain [n][plain_stride] (first `coeffs` coefficients used) -> ct [n][2kN]; nonces nonce0..nonce0+n-1
+// reserve n consecutive encryption nonces of a channel (a secure channel re-keys from the OS before the 32-bit counter wraps)
+u64 take_nonces(Context &c, int ch, u64 n);
 void op_encrypt(Context &c, int ch, const u64 *plain, size_t plain_stride, int n, int coeffs, u64 nonce0, u64 *ct);
 void op_decrypt(Context &c, int ch, const u64 *ct, int n, u64 *plain);
 int op_noise_budget(Context &c, int ch, const u64 *ct);

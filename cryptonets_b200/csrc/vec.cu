@@ -129,8 +129,17 @@ extern "C" int cnhe_context_set_option(cnhe_ctx *h, const char *name, int64_t va
         CNHE_CUDA(cudaMemcpyAsync(c.d_bf, &c.h_bf, sizeof(BehzConstF), cudaMemcpyHostToDevice, c.stream));
         c.sync();
     } else if (n == "multi_stream") {
+        // buffers remember the stream they are released on: switching the stream mode with work or uploads in flight would let the
+        // recycler hand a block out while another stream still reads it.  Quiesce, drop the per-stream free lists, then switch.
+        for (const Context::UploadSlot &u : c.upload_slots)
+            if (u.busy) fail("multi_stream cannot change while imported batches are alive (dispose them first)");
         c.sync();
+        CNHE_CUDA(cudaStreamSynchronize(c.copy_stream));
+        c.drop_recycled();
         c.multi_stream = value != 0;
+    } else if (n == "trace_noise") {
+        c.trace_noise = value != 0;
+        c.trace.clear();
     } else if (n == "chunk") {
         if (value < 1 || value > 4096) fail("chunk must be in [1,4096]");
         c.chunk = (int)value;
@@ -148,10 +157,37 @@ extern "C" int cnhe_keys_generate(cnhe_ctx *h, uint64_t seed) {
     keys_generate(c, seed);
     API_END
 }
+extern "C" int cnhe_keys_generate_secure(cnhe_ctx *h) {
+    API_BEGIN(h)
+    keys_generate_secure(c);
+    API_END
+}
+// OperationsCount / CryptoTracker mirrors
+extern "C" int cnhe_op_counts(cnhe_ctx *h, uint64_t *out, int cap, int reset) {
+    API_BEGIN(h)
+    if (!out || cap < Context::OP_COUNT) fail("need room for CNHE_OP_COUNT counters");
+    for (int i = 0; i < Context::OP_COUNT; i++) out[i] = c.op_count[i];
+    if (reset) for (int i = 0; i < Context::OP_COUNT; i++) c.op_count[i] = 0;
+    API_END
+}
+extern "C" const char *cnhe_op_name(int kind) { return op_kind_name(kind); }
+extern "C" int cnhe_trace_read(cnhe_ctx *h, int32_t *out, size_t cap_records, size_t *n_records, int clear) {
+    API_BEGIN(h)
+    if (n_records) *n_records = c.trace.size();
+    if (out) {
+        const size_t n = std::min(cap_records, c.trace.size());
+        for (size_t i = 0; i < n; i++) {
+            out[4 * i] = c.trace[i].kind; out[4 * i + 1] = c.trace[i].channel; out[4 * i + 2] = c.trace[i].n; out[4 * i + 3] = c.trace[i].budget;
+        }
+    }
+    if (clear) c.trace.clear();
+    API_END
+}
 extern "C" int cnhe_keys_set_seed(cnhe_ctx *h, int channel, uint64_t seed) {
     API_BEGIN(h)
     if (channel < 0 || channel >= c.P) fail("bad channel");
-    c.ch[channel].seed = seed;
+    memset(&c.ch[channel].rng, 0, sizeof(RngKey)); // deterministic sampler (tests): see cnhe.h
+    c.ch[channel].rng.seed = seed;
     API_END
 }
 extern "C" int cnhe_keys_export(cnhe_ctx *h, int channel, int what, uint64_t arg, uint64_t *dst, size_t cap) {
@@ -398,14 +434,12 @@ static cnhe_vec *make_vector(Context &c, const double *v, uint64_t dim, double s
             u64 *plain = encrypt ? c.ws_alloc((size_t)blocks * N) : out->ptr(ch);
             op_encode(c, ch, dvals, blocks, (int)N, plain);
             if (encrypt) {
-                op_encrypt(c, ch, plain, N, blocks, (int)N, c.ch[ch].nonce, out->ptr(ch));
-                c.ch[ch].nonce += blocks;
+                op_encrypt(c, ch, plain, N, blocks, (int)N, take_nonces(c, ch, blocks), out->ptr(ch));
             }
         } else { // sparse encrypted: one constant-polynomial plaintext per element (AtomicSealBfvVector.cs:1135-1138)
             u64 *dvals = c.ws_alloc(dim);
             CNHE_CUDA(cudaMemcpyAsync(dvals, split[ch].data(), dim * 8, cudaMemcpyHostToDevice, c.stream));
-            op_encrypt(c, ch, dvals, 1, blocks, 1, c.ch[ch].nonce, out->ptr(ch));
-            c.ch[ch].nonce += blocks;
+            op_encrypt(c, ch, dvals, 1, blocks, 1, take_nonces(c, ch, blocks), out->ptr(ch));
         }
         c.sync(); // host staging buffers go out of scope
     }
@@ -448,8 +482,7 @@ extern "C" int cnhe_vecs_encrypt(cnhe_ctx *h, const double *v, int n, uint64_t d
         CNHE_CUDA(cudaMemcpyAsync(dvals, padded.data(), padded.size() * 8, cudaMemcpyHostToDevice, c.stream));
         op_encode(c, ch, dvals, n * bl, (int)N, plain);
         big[ch] = c.alloc((size_t)n * bl * c.ct_words());
-        op_encrypt(c, ch, plain, N, n * bl, (int)N, c.ch[ch].nonce, big[ch]->p);
-        c.ch[ch].nonce += (u64)n * bl;
+        op_encrypt(c, ch, plain, N, n * bl, (int)N, take_nonces(c, ch, (u64)n * bl), big[ch]->p);
         c.sync();
     }
     for (int i = 0; i < n; i++) {
@@ -692,6 +725,17 @@ extern "C" int cnhe_noise_budget(cnhe_ctx *h, const cnhe_vec *v, int channel, in
     API_END
 }
 
+// evaluator.Add/Sub/AddMany launches that also feed the operation counters / noise trace (OperationsCount, CryptoTracker)
+static void do_add(Context &c, int ch, const u64 *a, const u64 *b, u64 *out, size_t words, int sub) {
+    c.check(launch_ct_add(a, b, out, words, c.k, c.logN, c.d_bc, sub, c.stream), sub ? "ct_sub" : "ct_add");
+    c.note(sub ? Context::OP_SUB : Context::OP_ADD, ch, (int)(words / c.ct_words()), out);
+}
+static void do_add_many(Context &c, int ch, const u64 *const *d_ptrs, int n_in, u64 *out) {
+    c.check(launch_ct_add_many(d_ptrs, n_in, out, c.ct_words(), c.k, c.logN, c.d_bc, c.stream), "ct_add_many");
+    c.op_count[Context::OP_ADD_MANY_ITEMS] += (uint64_t)n_in;
+    c.note(Context::OP_ADD_MANY, ch, 1, out);
+}
+
 // ---------------------------------------------------------------------------------------------------- IVector operations
 static void check_pair(const cnhe_vec *a, const cnhe_vec *b) {
     if (a->dim != b->dim) fail("Dimensions do not match");
@@ -712,12 +756,13 @@ static cnhe_vec *addsub(Context &c, const cnhe_vec *a, const cnhe_vec *b, bool s
     for (int ch = 0; ch < c.P; ch++) {
         c.set_channel(ch);
         if (p->enc) {
-            c.check(launch_ct_add(a->ptr(ch), b->ptr(ch), o->ptr(ch), (size_t)e->blocks * c.ct_words(), c.k, c.logN, c.d_bc, sub, c.stream), "ct_add");
+            do_add(c, ch, a->ptr(ch), b->ptr(ch), o->ptr(ch), (size_t)e->blocks * c.ct_words(), sub);
         } else {
             const bool dense = p->format == CNHE_DENSE;
             c.check(launch_ct_add_plain(e->ptr(ch), o->ptr(ch), e->blocks, 2, p->ptr(ch), dense ? c.N : 1, dense ? (int)c.N : 1, c.k, c.logN, c.d_bc,
                                         c.ch[ch].pc, sub, c.stream),
                     "ct_add_plain");
+            c.note(sub ? Context::OP_SUB_PLAIN : Context::OP_ADD_PLAIN, ch, e->blocks, o->ptr(ch));
         }
     }
     return o;
@@ -756,6 +801,7 @@ static cnhe_vec *mul_sparse_dim_one(Context &c, const cnhe_vec *self, const cnhe
             u64 *d = c.ws_alloc(sc.size());
             CNHE_CUDA(cudaMemcpyAsync(d, sc.data(), sc.size() * 8, cudaMemcpyHostToDevice, c.stream));
             c.check(launch_ct_scale(self->ptr(ch), o->ptr(ch), self->blocks, 2, d, c.k, c.logN, c.d_bc, c.ch[ch].pc, c.stream), "ct_scale");
+            c.note(Context::OP_MULTIPLY_SCALAR, ch, self->blocks, o->ptr(ch));
             c.sync();
         } else { // plain blocks times the single ciphertext of s
             if (self->format != CNHE_DENSE) fail("unsupported plain format");
@@ -788,6 +834,7 @@ static cnhe_vec *pointwise_multiply(Context &c, const cnhe_vec *a, const cnhe_ve
             for (u64 s : p->scalars[ch])
                 if (s == 0) fail("plain cannot be zero (the result would be a transparent ciphertext)");
             c.check(launch_ct_scale(e->ptr(ch), o->ptr(ch), e->blocks, 2, p->ptr(ch), c.k, c.logN, c.d_bc, c.ch[ch].pc, c.stream), "ct_scale");
+            c.note(Context::OP_MULTIPLY_SCALAR, ch, e->blocks, o->ptr(ch));
         }
     }
     return guard.release();
@@ -817,19 +864,19 @@ static cnhe_vec *sum_all_slots(Context &c, const cnhe_vec *a, uint64_t length, i
         u64 *sum = o->ptr(ch);
         if (a->blocks > 1) { // AddMany over the blocks
             std::vector<const u64 *> ptrs = block_ptrs(a, ch);
-            c.check(launch_ct_add_many(upload_ptrs(c, ptrs), a->blocks, sum, ctw, c.k, c.logN, c.d_bc, c.stream), "ct_add_many");
+            do_add_many(c, ch, upload_ptrs(c, ptrs), a->blocks, sum);
         } else {
             CNHE_CUDA(cudaMemcpyAsync(sum, a->ptr(ch), ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
         }
         u64 *tmp = c.ws_alloc(ctw);
         if (len >= N / 2) {
             op_rotate_columns(c, ch, sum, 1, tmp);
-            c.check(launch_ct_add(sum, tmp, sum, ctw, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+            do_add(c, ch, sum, tmp, sum, ctw, 0);
             len = N / 2;
         }
         for (uint64_t steps = 1; steps < len; steps *= 2) { // RotateRowsAndAdd(sum, steps): RotateRows(c, -steps)
             op_rotate_rows(c, ch, sum, 1, -(int)steps, tmp);
-            c.check(launch_ct_add(sum, tmp, sum, ctw, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+            do_add(c, ch, sum, tmp, sum, ctw, 0);
         }
         if (force_column >= 0) { // one-hot mask (":936-945")
             if ((size_t)force_column >= N) fail("column out of range");
@@ -906,7 +953,7 @@ extern "C" int cnhe_vec_duplicate(cnhe_ctx *h, const cnhe_vec *a, uint64_t count
                 target -= (long long)N / 2;
             }
             op_rotate_rows(c, ch, rot_src, 1, -(int)target, tmp); // RotateRowsAndAdd(rotator, target, ...)
-            c.check(launch_ct_add(res, tmp, res, ctw, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+            do_add(c, ch, res, tmp, res, ctw, 0);
         }
     }
     *out = guard.release();
@@ -944,7 +991,7 @@ extern "C" int cnhe_vec_permute(cnhe_ctx *h, const cnhe_vec *a, const cnhe_vec *
             op_multiply_plain_dense(c, ch, a->ptr(ch), 1, selections[i]->ptr(ch), false, t);
             op_rotate_rows(c, ch, t, 1, shifts[i], r);
             if (!have) CNHE_CUDA(cudaMemcpyAsync(o->ptr(ch), r, ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
-            else c.check(launch_ct_add(o->ptr(ch), r, o->ptr(ch), ctw, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+            else do_add(c, ch, o->ptr(ch), r, o->ptr(ch), ctw, 0);
             have = true;
         }
     }
@@ -1007,7 +1054,7 @@ static void interleave_channel(Context &c, int ch, const std::vector<const cnhe_
                 u64 *v2 = c.ws_alloc(ctw);
                 CNHE_CUDA(cudaMemcpyAsync(v2, v, ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
                 op_multiply_plain_dense(c, ch, v, 1, ones_plain(upper_part), false, v);
-                c.check(launch_ct_add(v2, v, v2, ctw, c.k, c.logN, c.d_bc, 1, c.stream), "ct_sub");
+                do_add(c, ch, v2, v, v2, ctw, 1);
                 upper[start_block].push_back(v2);
                 if (end_block >= out_blocks) fail("not enough room for interleaving");
                 lower[end_block].push_back(v);
@@ -1019,7 +1066,7 @@ static void interleave_channel(Context &c, int ch, const std::vector<const cnhe_
                 u64 *v2 = c.ws_alloc(ctw);
                 CNHE_CUDA(cudaMemcpyAsync(v2, v, ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
                 op_multiply_plain_dense(c, ch, v, 1, ones_plain(upper_part), false, v);
-                c.check(launch_ct_add(v2, v, v2, ctw, c.k, c.logN, c.d_bc, 1, c.stream), "ct_sub");
+                do_add(c, ch, v2, v, v2, ctw, 1);
                 upper[start_block].push_back(v);
                 lower[start_block].push_back(v2);
             } else {
@@ -1030,12 +1077,12 @@ static void interleave_channel(Context &c, int ch, const std::vector<const cnhe_
     for (int i = 0; i < out_blocks; i++) {
         u64 *res = out + (size_t)i * ctw;
         if (lower[i].empty()) fail("an output block received no vector");
-        c.check(launch_ct_add_many(upload_ptrs(c, lower[i]), (int)lower[i].size(), res, ctw, c.k, c.logN, c.d_bc, c.stream), "ct_add_many");
+        do_add_many(c, ch, upload_ptrs(c, lower[i]), (int)lower[i].size(), res);
         if (!upper[i].empty()) {
             u64 *t = c.ws_alloc(ctw);
-            c.check(launch_ct_add_many(upload_ptrs(c, upper[i]), (int)upper[i].size(), t, ctw, c.k, c.logN, c.d_bc, c.stream), "ct_add_many");
+            do_add_many(c, ch, upload_ptrs(c, upper[i]), (int)upper[i].size(), t);
             op_rotate_columns(c, ch, t, 1, t);
-            c.check(launch_ct_add(res, t, res, ctw, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+            do_add(c, ch, res, t, res, ctw, 0);
         }
     }
 }
@@ -1118,7 +1165,15 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
             for (int kk = 0; kk < K; kk++) {
                 row[kk] = gather ? gather[(size_t)m * K + kk] : kk;
                 if (row[kk] >= n_in) fail("gather index out of range");
-                if (row[kk] >= 0 && weights[m]->scalars[0][kk] != 0) any = true;
+            }
+            // The reference skips zero plaintexts per plaintext modulus (IsZero, AtomicSealBfvVector.cs:468) and sums what is left, so an
+            // output whose taps are all = 0 modulo one of the t_c has an empty sum in that channel.  (Deviation, documented in DESIGN.md:
+            // padded taps are skipped here, while the reference multiplies a fresh encryption of zero by their weight.)
+            for (int ch = 0; ch < c.P; ch++) {
+                bool any_ch = false;
+                for (int kk = 0; kk < K; kk++) any_ch = any_ch || (row[kk] >= 0 && weights[m]->scalars[ch][kk] != 0);
+                any = any || any_ch;
+                if (!any_ch) fail("an output has no non-zero tap modulo one of the plaintext primes (the reference would sum an empty list)");
             }
             if (!any) fail("an output has no non-zero tap (the reference would sum an empty list)");
             auto it = groups.find(row);
@@ -1239,6 +1294,15 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
                         "mac_layer");
             c.prof_end();
         }
+        { // what the reference issues for this layer (AtomicSealBfvVector.cs:466-475, 497-505): MultiplyPlain per non-zero tap, AddMany per output
+            uint64_t taps = 0;
+            for (int m = 0; m < M; m++)
+                for (int kk = 0; kk < K; kk++) taps += (!gather || gather[(size_t)m * K + kk] >= 0) && weights[m]->scalars[ch][kk] != 0;
+            c.op_count[Context::OP_MULTIPLY_SCALAR] += taps * bl;
+            c.op_count[Context::OP_ADD_MANY_ITEMS] += taps * bl;
+            if (bias) c.op_count[Context::OP_ADD_PLAIN] += (uint64_t)M * bl;
+            c.note(Context::OP_ADD_MANY, ch, M * bl, big[ch]->p);
+        }
         if (bias && !const_bias) // generic AddPlain per output
             for (int m = 0; m < M; m++) {
                 u64 *o = big[ch]->p + (size_t)m * bl * c.ct_words();
@@ -1297,7 +1361,7 @@ extern "C" int cnhe_mat_mul_colmajor_sparse(cnhe_ctx *h, const cnhe_vec *const *
             for (int i = 0; i < bl; i++) {
                 std::vector<const u64 *> terms;
                 for (int kk = 0; kk < K; kk++) terms.push_back(prod + ((size_t)kk * bl + i) * ctw);
-                c.check(launch_ct_add_many(upload_ptrs(c, terms), K, o->block(ch, i), ctw, c.k, c.logN, c.d_bc, c.stream), "ct_add_many");
+                do_add_many(c, ch, upload_ptrs(c, terms), K, o->block(ch, i));
             }
             c.sync();
         }
@@ -1313,12 +1377,12 @@ static uint64_t sum_slots_batched(Context &c, int ch, u64 *cts, int n, uint64_t 
     u64 *tmp = c.ws_alloc(words);
     if (len >= N / 2) {
         op_rotate_columns(c, ch, cts, n, tmp);
-        c.check(launch_ct_add(cts, tmp, cts, words, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+        do_add(c, ch, cts, tmp, cts, words, 0);
         len = N / 2;
     }
     for (uint64_t steps = 1; steps < len; steps *= 2) {
         op_rotate_rows(c, ch, cts, n, -(int)steps, tmp);
-        c.check(launch_ct_add(cts, tmp, cts, words, c.k, c.logN, c.d_bc, 0, c.stream), "ct_add");
+        do_add(c, ch, cts, tmp, cts, words, 0);
     }
     return len;
 }
@@ -1369,7 +1433,7 @@ extern "C" int cnhe_mat_mul_rowmajor(cnhe_ctx *h, const cnhe_vec *const *rows, i
                 std::vector<const u64 *> terms;
                 if (!first) terms.push_back(o->ptr(ch));
                 for (int i = 0; i < m; i++) terms.push_back(prod + (size_t)i * ctw);
-                c.check(launch_ct_add_many(upload_ptrs(c, terms), (int)terms.size(), o->ptr(ch), ctw, c.k, c.logN, c.d_bc, c.stream), "ct_add_many");
+                do_add_many(c, ch, upload_ptrs(c, terms), (int)terms.size(), o->ptr(ch));
                 c.sync();
             }
             first = false;

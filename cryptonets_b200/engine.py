@@ -138,8 +138,36 @@ class Engine:
     def sync(self):
         check(self.L.cnhe_context_sync(self.h))
 
-    def keygen(self, seed):
-        check(self.L.cnhe_keys_generate(self.h, int(seed)))
+    def keygen(self, seed=None):
+        """seed=None: keys and all later encryption randomness from the OS CSPRNG (production).  An integer seed selects the deterministic
+        sampler shared with the CPU oracle -- tests only, the keys are predictable."""
+        if seed is None:
+            check(self.L.cnhe_keys_generate_secure(self.h))
+        else:
+            check(self.L.cnhe_keys_generate(self.h, int(seed)))
+
+    OP_NAMES = None
+
+    def op_counts(self, reset=False):
+        """Evaluator-level operation counters (the reference's OperationsCount)."""
+        n = 14
+        a = np.zeros(n, np.uint64)
+        check(self.L.cnhe_op_counts(self.h, _p(a), n, int(reset)))
+        if Engine.OP_NAMES is None:
+            Engine.OP_NAMES = [self.L.cnhe_op_name(i).decode() for i in range(n)]
+        return {nm: int(v) for nm, v in zip(Engine.OP_NAMES, a)}
+
+    def trace_noise(self, on=True):
+        self.set_option("trace_noise", 1 if on else 0)
+
+    def trace_read(self, clear=True):
+        """[(operation name, channel, count, noise budget of the first output or -1)] since the trace was last cleared."""
+        n = C.c_size_t()
+        check(self.L.cnhe_trace_read(self.h, None, 0, C.byref(n), 0))
+        a = np.zeros((max(n.value, 1), 4), np.int32)
+        check(self.L.cnhe_trace_read(self.h, a.ctypes.data_as(C.POINTER(C.c_int32)), n.value, C.byref(n), int(clear)))
+        self.op_counts()
+        return [(Engine.OP_NAMES[k], int(ch), int(cnt), int(b)) for k, ch, cnt, b in a[:n.value]]
 
     def galois_elts(self):
         a = np.zeros(self.n_galois, np.uint64)

@@ -211,8 +211,10 @@ class B200BfvFactory:
     DefaultDecompositionBitCount = 10
     DefaultGaloisDecompositionBitCount = 20
 
-    def __init__(self, primes=None, n=4096, DecompositionBitCount=10, GaloisDecompositionBitCount=20, SmallModulusCount=-1, seed=1,
+    def __init__(self, primes=None, n=4096, DecompositionBitCount=10, GaloisDecompositionBitCount=20, SmallModulusCount=-1, seed=None,
                  device=0, generate_keys=True):
+        """seed=None (default): keys and encryption randomness from the OS CSPRNG, as SEAL's KeyGenerator/Encryptor give the reference.
+        An integer seed selects the deterministic sampler shared with the CPU oracle: parity tests only."""
         if primes is None:
             primes, n = [40961, 65537, 114689, 147457, 188417], 4096  # IFactory.cs:247-253
         self.engine = Engine(primes, n, DecompositionBitCount, GaloisDecompositionBitCount, SmallModulusCount, device)

@@ -2,8 +2,9 @@
 
 cryptonets_mnist  <- `CryptoNets/CryptoNets.cs:12-75`   (config 2 of BASELINE.json)
 lola_small        <- `LowLatencyCryptoNets/LoLaCryptonets.cs:280-329` (config 3)
-Weights come from tests/golden/*.npz (extracted from the reference's shipped constants by tools/extract_reference_weights.py)
-or, when absent, from a seeded generator of the same shapes."""
+lola / lola_dense / lola_large / lola_cifar <- the other mains of `LoLaCryptonets.cs` and `CifarCryptoNet/LolaCifarCryptoNet.cs` (config 4)
+Trained parameters come from cryptonets_b200/models/*.npz (generated from the reference's shipped constants and CSV files by
+tools/extract_reference_weights.py) or, when a file is absent, from a seeded generator of the same shapes."""
 import os
 
 import numpy as np
@@ -13,7 +14,7 @@ from .layers import (ConvolutionEngine, EncryptLayer, LLConvReader, LLDenseLayer
                      LLPackedDenseLayer, LLPoolLayer, LLPreConvLayer, LLSingleLineReader, LLVectorizeLayer, MatrixSource, PoolLayer,
                      SquareActivation, TimingLayer)
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+_MODELS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
 CRYPTONETS_PRIMES = [549764251649, 549764284417]  # CryptoNets.cs:17
 LOLA_SMALL_PRIMES = [2277377, 2424833]            # LoLaCryptonets.cs:285
 LOLA_PRIMES = [557057, 638977, 737281, 786433]    # LoLaCryptonets.cs:208 (N=8192, default decomposition bit counts)
@@ -23,7 +24,7 @@ LOLA_LARGE_PRIMES = [2148728833, 2148794369, 2149810177]  # LoLaCryptonets.cs:33
 
 
 def load_weights(name, shapes, seed=0):
-    path = os.path.join(_GOLDEN, name)
+    path = os.path.join(_MODELS, name)
     if os.path.exists(path):
         z = np.load(path)
         return {k: z[k] for k in z.files}
@@ -134,9 +135,13 @@ def lola_dense(factory, images, weights=None):
     return dense9, reader
 
 
-def cifar_weights(seed=7):
-    """Synthetic weights with the shapes and the per-layer spread of the shipped `CifarWeight.csv` / `CifarBias.csv` (21 MB of text,
-    not copied into this repo): conv 83 x (3*8*8), conv-as-dense 112 x (83*10*10), dense 10 x 5488."""
+def cifar_weights(seed=7, synthetic=False):
+    """The shipped `CifarWeight.csv` / `CifarBias.csv` (models/lola_cifar_weights.npz): conv 83 x (3*8*8), conv-as-dense 112 x (83*10*10),
+    dense 10 x 5488.  synthetic=True (or a missing file): seeded weights with the same shapes and per-layer spread."""
+    path = os.path.join(_MODELS, "lola_cifar_weights.npz")
+    if not synthetic and os.path.exists(path):
+        z = np.load(path)
+        return {k: z[k].astype(np.float64) for k in z.files}
     rng = np.random.default_rng(seed)
 
     def draw(n, std, cap):
@@ -171,9 +176,13 @@ def lola_cifar(factory, images, weights=None):
     return dense6, reader
 
 
-def lola_large_weights(seed=9):
-    """Synthetic weights with the shapes and per-layer spread of the shipped `MnistLargeWeight.csv` / `MnistLargeBias.csv`:
-    conv 83 x (8*8), conv-as-dense 163 x (83*6*6), dense 10 x 2608."""
+def lola_large_weights(seed=9, synthetic=False):
+    """The shipped `MnistLargeWeight.csv` / `MnistLargeBias.csv` (models/lola_large_weights.npz): conv 83 x (8*8), conv-as-dense
+    163 x (83*6*6), dense 10 x 2608.  synthetic=True (or a missing file): seeded weights with the same shapes and spread."""
+    path = os.path.join(_MODELS, "lola_large_weights.npz")
+    if not synthetic and os.path.exists(path):
+        z = np.load(path)
+        return {k: z[k].astype(np.float64) for k in z.files}
     rng = np.random.default_rng(seed)
 
     def draw(n, std, cap):

@@ -61,17 +61,35 @@ int cnhe_context_plain_moduli(const cnhe_ctx *, uint64_t *out_P);
 int cnhe_context_bsk_moduli(const cnhe_ctx *, uint64_t *out, int *count);
 int cnhe_context_galois_elts(const cnhe_ctx *, uint64_t *out);
 /* options: "behz_centered_mtilde" (0/1), "chunk" (ciphertexts per multiply/key-switch wave), "multi_stream" (1: one CUDA
- * stream per plaintext modulus, default; 0: everything on one stream) */
+ * stream per plaintext modulus, default; 0: everything on one stream; refused while imported batches are alive),
+ * "trace_noise" (1: record the invariant noise budget after every evaluator-level operation, see cnhe_trace_read) */
 int cnhe_context_set_option(cnhe_ctx *, const char *name, int64_t value);
 int cnhe_context_sync(cnhe_ctx *);
 /* EncryptedSealBfvEnvironment.GenerateEncryptionKeys ("EncryptedSealBfvVector.cs:92-102") -> KeyGenerator, RelinKeys(dbc),
- * GaloisKeys(dbc) ("AtomicSealBfvVector.cs:62-74"); channel c is seeded with seed + c.  Device-side sampling. */
+ * GaloisKeys(dbc) ("AtomicSealBfvVector.cs:62-74"), sampled on the device.
+ * cnhe_keys_generate_secure: every channel draws a fresh 256-bit ChaCha20 key from the OS (getrandom) -- secret key, key masks and all
+ * later encryption randomness come from it (what SEAL's std::random_device gives the reference).  This is the production call.
+ * A context is born with such a key per channel, so encrypting under an imported public key is safe without any seeding call.
+ * cnhe_keys_generate(seed): DETERMINISTIC, TESTS ONLY -- the counter-based splitmix64 sampler shared with the CPU oracle (channel c uses
+ * seed + c), so keys and fresh ciphertexts are bit-comparable; its outputs are predictable from the public key. */
+int cnhe_keys_generate_secure(cnhe_ctx *);
 int cnhe_keys_generate(cnhe_ctx *, uint64_t seed);
 /* what: 0 secret key [k][N] (NTT form), 1 public key [2][k][N], 2 relin keys [D][2][k][N], 3 Galois key of element
  * `arg` [D][2][k][N].  Stand-in for the SEAL key streams of SaveToStream/LoadFromStream ("AtomicSealBfvVector.cs:93-130"). */
 int cnhe_keys_export(cnhe_ctx *, int channel, int what, uint64_t arg, uint64_t *dst, size_t cap_words);
 int cnhe_keys_import(cnhe_ctx *, int channel, int what, uint64_t arg, const uint64_t *src, size_t words);
-int cnhe_keys_set_seed(cnhe_ctx *, int channel, uint64_t seed); /* seed used by later encryptions of that channel */
+int cnhe_keys_set_seed(cnhe_ctx *, int channel, uint64_t seed); /* TESTS ONLY: later encryptions of that channel use the deterministic sampler */
+/* OperationsCount ("HE Wrapper/AtomicSealBfvVector.cs:211-294"): evaluator-level operations issued since creation / the last reset, in
+ * the order Encryption, Decryption, Multiplication, Relinarization, PlainMultiplication (dense plaintext), ScalarMultiplication (constant
+ * plaintext: SEAL's monomial multiply_plain), Addition, PlainAddition, Subtraction, PlainSubtraction, Rotation (row-rotation hops),
+ * ColumnRotation, AddMany, AddManyItemCount.  cnhe_op_name(i) names counter i. */
+#define CNHE_OP_COUNT 14
+int cnhe_op_counts(cnhe_ctx *, uint64_t *out, int cap, int reset);
+const char *cnhe_op_name(int kind);
+/* CryptoTracker.TestBudget ("HE Wrapper/CryptoTracker.cs:41-52") as a trace: with option "trace_noise" on, every evaluator-level
+ * operation appends (kind, channel, count, invariant noise budget of its first output ciphertext, -1 when not measured) -- four int32
+ * per record.  out may be NULL to query the record count. */
+int cnhe_trace_read(cnhe_ctx *, int32_t *out, size_t cap_records, size_t *n_records, int clear);
 
 /* ---- vectors: creation, metadata, disposal ---------------------------------------------------------------------- */
 /* IFactory.GetEncryptedVector / GetPlainVector ("HE Wrapper/IFactory.cs:311-328"): round(v*scale), CRT split over the

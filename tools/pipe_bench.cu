@@ -25,6 +25,25 @@ template <int KIND> __global__ void k(u64 *out, u64 seed) {
                 asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(e), "d"(f));
                 asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"((unsigned)a[i]), "r"(b));
             }
+            if (KIND == 9) asm volatile("cvt.rni.f64.f64 %0, %0;" : "+d"(d[i]));                       // FRND.F64: which pipe, what rate?
+            if (KIND == 10) { // DFMA + FRND.F64 on independent chains: do they overlap?
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(e), "d"(f));
+                double g = (double)a[i]; asm volatile("cvt.rni.f64.f64 %0, %0;" : "+d"(g)); a[i] = (u64)__double_as_longlong(g);
+            }
+            if (KIND == 11) { // the butterfly's ratio: 7 DFMA-pipe ops per rounding
+                double g = d[i];
+                asm volatile("cvt.rni.f64.f64 %0, %0;" : "+d"(g));
+#pragma unroll
+                for (int r = 0; r < 7; r++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(e), "d"(g));
+            }
+            if (KIND == 12) { long long x; asm volatile("cvt.rni.s64.f64 %0, %1;" : "=l"(x) : "d"(d[i])); asm volatile("cvt.rn.f64.s64 %0, %1;" : "=d"(d[i]) : "l"(x + 1)); }
+            if (KIND == 13) { // same 7:1 ratio with the magic-constant rounding (2 DP ops): the current butterfly
+                double g;
+                asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(g) : "d"(d[i]), "d"(f), "d"(6755399441055744.0));
+                asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(g) : "d"(-6755399441055744.0));
+#pragma unroll
+                for (int r = 0; r < 6; r++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(e), "d"(g));
+            }
             if (KIND == 8) { // DFMA + IADD3
                 asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(e), "d"(f));
                 unsigned x = (unsigned)a[i]; asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(b)); a[i] = x;
@@ -56,5 +75,7 @@ template <int KIND> void run(const char *name, int per_iter) {
 int main() {
     run<0>("IMAD.WIDE.U32", 1); run<1>("IMAD (lo32)", 1); run<2>("IADD3", 1); run<3>("DFMA", 1); run<4>("DADD", 1); run<5>("LOP3", 1);
     run<6>("mul.hi.u64", 1); run<7>("DFMA + IMAD.WIDE (2 instr)", 2); run<8>("DFMA + IADD3 (2 instr)", 2);
+    run<9>("FRND.F64 (cvt.rni.f64.f64)", 1); run<10>("DFMA + FRND.F64 (2 instr)", 2); run<11>("7 DFMA + 1 FRND (8 instr)", 8);
+    run<12>("F2I.S64.F64 + I2F.F64.S64", 2); run<13>("8 DP ops (magic rounding)", 8);
     return 0;
 }
