@@ -74,88 +74,166 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------------- CPU arm
-def cpu_sample(primes, threads, seed=0):
-    """One bounded sample of the workload on the CPU oracle; returns (estimated seconds per full batch, description)."""
-    from oracle.oracle_py import Oracle
-    from cryptonets_b200.layers import ConvolutionEngine
-    from cryptonets_b200.networks import cryptonets_weights, transpose
-    w = cryptonets_weights()
-    rng = np.random.default_rng(seed)
-    ce = ConvolutionEngine()
-    ce.InputShape, ce.KernelShape, ce.Stride, ce.Upperpadding, ce.MapCount = [28, 28], [5, 5], [2, 2], [1, 1], [5, 1]
-    ce.Prepare()
-    total = 0.0
-    s_conv = max(1, 845 // max(64, 2 * threads))
-    s_sq1 = max(1, 845 // max(32, 2 * threads))
-    s_d3 = max(1, 100 // max(16, min(100, threads)))
-    s_sq2 = max(1, 100 // max(16, min(100, 2 * threads)))
-    for t in primes:
-        o = Oracle(t, 8192, -1, 10, 20)
-        o.keygen(1)
-        ctw = o.ct_words
-        q = np.array(o.q, dtype=np.uint64)
+def host_threads():
+    """Threads the CPU arm may use: the scheduler affinity of this process (what `Defaults.ThreadCount = ProcessorCount` amounts to inside a
+    container), not the machine's logical CPU count."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
 
-        def rand_cts(n):
-            a = rng.integers(0, 1 << 43, (n, 2, o.k, 8192), dtype=np.uint64)
-            return (a % q[None, None, :, None]).reshape(n, ctw)
 
-        def lift(x):
-            x = np.rint(x)
-            return np.where(x < 0, x + t, x).astype(np.uint64)
+def host_info():
+    info = {"affinity_cpus": host_threads(), "logical_cpus": os.cpu_count()}
+    try:
+        with open("/proc/cpuinfo") as f:
+            models = [l.split(":", 1)[1].strip() for l in f if l.startswith("model name")]
+        info["cpu_model"] = models[0] if models else None
+    except Exception:
+        pass
+    try:
+        info["numa_nodes"] = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+    except Exception:
+        pass
+    try:
+        info["loadavg_1m"] = os.getloadavg()[0]
+    except Exception:
+        pass
+    return info
 
-        x = rand_cts(784)
-        gather = np.array([[ce.Location(c, off, ce.InputShape) for off in ce.Offsets] for c in ce.Corners] * 5, dtype=np.int32)
-        w0 = np.array([[w["Weights_0"][m * 26 + ce.Location(None, off, ce.KernelShape)] for off in ce.Offsets] for m in range(5)]) * 32
-        wconv = lift(np.repeat(w0, 169, axis=0))
-        bconv = lift(np.repeat(np.array([w["Weights_0"][(m + 1) * 26 - 1] for m in range(5)]) * 512, 169))
-        t0 = time.perf_counter()
-        o.mac_layer(x, gather, wconv, bconv, 845, 25, threads=threads, m_begin=0, m_step=s_conv)
-        total += (time.perf_counter() - t0) * s_conv
-        a1 = rand_cts(845)
-        t0 = time.perf_counter()
-        o.square_layer(a1, threads=threads, begin=0, step=s_sq1)
-        total += (time.perf_counter() - t0) * s_sq1
-        w1 = lift(transpose(w["Weights_1"], 845, 100).reshape(100, 845) * 1024)
-        b1 = lift(np.rint(w["Biases_2"] * 1000.0) % t)
-        t0 = time.perf_counter()
-        o.mac_layer(a1, None, w1, b1, 100, 845, threads=threads, m_begin=0, m_step=s_d3)
-        total += (time.perf_counter() - t0) * s_d3
-        a2 = rand_cts(100)
-        t0 = time.perf_counter()
-        o.square_layer(a2, threads=threads, begin=0, step=s_sq2)
-        total += (time.perf_counter() - t0) * s_sq2
-        w3 = lift(w["Weights_3"].reshape(10, 100) * 32)
-        b3 = lift(np.rint(w["Biases_3"] * 1000.0) % t)
-        t0 = time.perf_counter()
-        o.mac_layer(a2, None, w3, b3, 10, 100, threads=threads)
-        total += time.perf_counter() - t0
-    desc = ("per plaintext modulus: conv outputs every %d-th of 845, square1 every %d-th of 845, dense3 every %d-th of 100, square2 every "
-            "%d-th of 100, dense5 all 10; layer times scaled by the sampling stride" % (s_conv, s_sq1, s_d3, s_sq2))
-    return total, desc
+
+class CpuWorkload:
+    """The CryptoNets-MNIST batch on the CPU oracle (`oracle/`, the C++ restatement of the SEAL 3.2 path; the C#/SEAL reference cannot be
+    built here).  Inputs are uniform residues drawn from the same seed family as the GPU arm's images (ciphertext words are computationally
+    uniform; the arithmetic does not depend on their values); weights are the shipped ones.  Thread model: the oracle's parallel_for pulls
+    output indices dynamically, as `HE Wrapper/Utils.cs:46-88` does."""
+
+    LAYERS = ("conv1", "square2", "dense3", "square4", "dense5")
+
+    def __init__(self, primes, seed=20240917):
+        from oracle.oracle_py import Oracle
+        from cryptonets_b200.layers import ConvolutionEngine
+        from cryptonets_b200.networks import cryptonets_weights, transpose
+        w = cryptonets_weights()
+        ce = ConvolutionEngine()
+        ce.InputShape, ce.KernelShape, ce.Stride, ce.Upperpadding, ce.MapCount = [28, 28], [5, 5], [2, 2], [1, 1], [5, 1]
+        ce.Prepare()
+        self.ch = []
+        for ci, t in enumerate(primes):
+            o = Oracle(t, 8192, -1, 10, 20)
+            o.keygen(1)
+            rng = np.random.default_rng(seed + ci)
+            q = np.array(o.q, dtype=np.uint64)
+
+            def rand_cts(n, rng=rng, q=q, o=o):
+                a = rng.integers(0, 1 << 43, (n, 2, o.k, 8192), dtype=np.uint64)
+                return (a % q[None, None, :, None]).reshape(n, o.ct_words)
+
+            def lift(x, t=t):
+                x = np.rint(x)
+                return np.where(x < 0, x + t, x).astype(np.uint64)
+
+            d = dict(o=o, x=rand_cts(784), a1=rand_cts(845), a2=rand_cts(100))
+            d["gather"] = np.array([[ce.Location(c, off, ce.InputShape) for off in ce.Offsets] for c in ce.Corners] * 5, dtype=np.int32)
+            w0 = np.array([[w["Weights_0"][m * 26 + ce.Location(None, off, ce.KernelShape)] for off in ce.Offsets] for m in range(5)]) * 32
+            d["wconv"] = lift(np.repeat(w0, 169, axis=0))
+            d["bconv"] = lift(np.repeat(np.array([w["Weights_0"][(m + 1) * 26 - 1] for m in range(5)]) * 512, 169))
+            d["w1"] = lift(transpose(w["Weights_1"], 845, 100).reshape(100, 845) * 1024)
+            d["b1"] = lift(np.rint(w["Biases_2"] * 1000.0) % t)
+            d["w3"] = lift(w["Weights_3"].reshape(10, 100) * 32)
+            d["b3"] = lift(np.rint(w["Biases_3"] * 1000.0) % t)
+            # output buffers allocated (and their pages touched) once: the timed passes measure arithmetic, not the kernel's page faults
+            for name, n in (("o_conv", 845), ("o_sq1", 845), ("o_d3", 100), ("o_sq2", 100), ("o_d5", 10)):
+                d[name] = np.ones(n * o.ct_words, np.uint64)
+            self.ch.append(d)
+
+    def step(self, threads, strides=(1, 1, 1, 1, 1)):
+        """One pass over the batch; strides[i] > 1 computes every strides[i]-th output of layer i and scales its time.  Returns the
+        per-layer seconds (already scaled), summed over the plaintext moduli."""
+        sec = dict.fromkeys(self.LAYERS, 0.0)
+        for d in self.ch:
+            o = d["o"]
+            calls = (("conv1", lambda st: o.mac_layer(d["x"], d["gather"], d["wconv"], d["bconv"], 845, 25, threads=threads, m_begin=0, m_step=st, out=d["o_conv"])),
+                     ("square2", lambda st: o.square_layer(d["a1"], threads=threads, begin=0, step=st, out=d["o_sq1"])),
+                     ("dense3", lambda st: o.mac_layer(d["a1"], None, d["w1"], d["b1"], 100, 845, threads=threads, m_begin=0, m_step=st, out=d["o_d3"])),
+                     ("square4", lambda st: o.square_layer(d["a2"], threads=threads, begin=0, step=st, out=d["o_sq2"])),
+                     ("dense5", lambda st: o.mac_layer(d["a2"], None, d["w3"], d["b3"], 10, 100, threads=threads, m_begin=0, m_step=st, out=d["o_d5"])))
+            for (name, fn), st in zip(calls, strides):
+                t0 = time.perf_counter()
+                fn(st)
+                sec[name] += (time.perf_counter() - t0) * st
+        return sec
+
+    @staticmethod
+    def sample_strides(threads):
+        """Strides whose sampled item counts stay whole multiples of the thread count (no partial last wave that the scaling would
+        multiply): conv 845 and square 845 outputs, dense 100, square 100, dense 10."""
+        def stride(n):
+            waves_full = -(-n // threads)
+            if waves_full <= 2:
+                return 1
+            keep = 2 * threads  # two full waves
+            return max(1, n // keep)
+        return (stride(845), stride(845), stride(100), stride(100), 1)
+
+
+def cpu_measure(primes, threads, steps, warmup, budget_s=150.0, single_thread=True):
+    """Times `steps` passes after `warmup` untimed ones.  Every pass is the FULL batch (all 845/845/100/100/10 outputs of every layer)
+    when the run fits the time budget; otherwise the two big layers are sampled in whole thread-waves and the first timed pass is still a
+    full one, so the line reports how far the sampled estimate is from the full measurement."""
+    wl = CpuWorkload(primes)
+    t0 = time.perf_counter()
+    first = wl.step(threads)  # warm-up pass 1: full batch, also the size probe
+    first_s = time.perf_counter() - t0
+    full_total = sum(first.values())
+    use_full = full_total * (steps + warmup) <= budget_s
+    strides = (1, 1, 1, 1, 1) if use_full else CpuWorkload.sample_strides(threads)
+    for _ in range(max(0, warmup - 1)):
+        wl.step(threads, strides)
+    per_layer = dict.fromkeys(CpuWorkload.LAYERS, 0.0)
+    totals = []
+    for _ in range(steps):
+        sec = wl.step(threads, strides)
+        totals.append(sum(sec.values()))
+        for k_, v in sec.items():
+            per_layer[k_] += v / steps
+    mean_s = float(np.mean(totals))
+    info = {"mode": "full batch every step" if use_full else "sampled: strides %s per layer (conv1, square2, dense3, square4, dense5), whole thread-waves, times scaled by the stride" % (strides,),
+            "seconds_per_batch": mean_s, "per_layer_seconds": per_layer, "full_batch_probe_seconds": full_total, "probe_wall_seconds": first_s,
+            "sampled_vs_full": None if use_full else mean_s / full_total, "step_seconds_min_max": [float(np.min(totals)), float(np.max(totals))]}
+    if single_thread:  # one thread on a slice: 2 square outputs, 2 dense3 outputs, 8 conv outputs per modulus, scaled to the batch
+        st = (845 // 8, 845 // 2, 100 // 2, 100 // 2, 10 // 2)
+        sec1 = wl.step(1, st)
+        info["single_thread_seconds_per_batch"] = sum(sec1.values())
+        info["single_thread_images_per_s"] = BATCH / sum(sec1.values())
+        info["single_thread_sample"] = "1 thread, every %d/%d/%d/%d/%d-th output of the five layers, scaled" % st
+    return mean_s, info
+
+
+def cpu_line_config(plain_moduli, world):
+    return {"workload": WORKLOAD, "plain_moduli": plain_moduli, "parallelism": "replica-per-gpu x%d" % world,
+            "l2": "inputs larger than L2 (784 ct x 640 KiB per modulus)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    if args.workload != "cryptonets":
+        return run_reference_lola(args)
     from cryptonets_b200.networks import CRYPTONETS_PRIMES
     primes = CRYPTONETS_PRIMES[: args.plain_moduli]
-    threads = os.cpu_count() or 1
-    for _ in range(args.warmup):
-        cpu_sample(primes, threads)
-    times = []
-    desc = ""
-    for i in range(args.steps):
-        s, desc = cpu_sample(primes, threads, seed=i)
-        times.append(s)
-    sec = float(np.mean(times))
+    threads = host_threads()
+    sec, info = cpu_measure(primes, threads, args.steps, args.warmup, budget_s=float(os.environ.get("CNHE_CPU_BUDGET_S", "200")))
     value = BATCH / sec
     print(json.dumps({
         "impl": "reference", "metric": "encrypted images/sec (CryptoNets-MNIST, N=8192)", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic (uniform residues; shipped CryptoNets weights)",
-        "config": {"workload": WORKLOAD, "plain_moduli": len(primes), "note": "in-repo C++ oracle of the SEAL 3.2 path; the C#/SEAL reference cannot be built here"},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": desc},
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic (uniform residues from the GPU arm's seed family; shipped CryptoNets weights)",
+        "config": cpu_line_config(len(primes), world),
+        "notes": "in-repo C++ oracle of the SEAL 3.2 path on the host cores; the C#/SEAL reference cannot be built here",
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": info["mode"], "detail": info, "host": host_info()},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -345,20 +423,21 @@ def run_b200(args):
                 "launches_timed": fam["launches"], "algorithmic_bytes_per_launch": fam["bytes"] / max(1, fam["launches"]),
                 "avg_launch_ms": fam["ms"] / max(1, fam["launches"]), "share_of_step": fam["ms"] / ms if ms else None,
                 "families_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}
-        cpu_threads = os.cpu_count() or 1
-        cpu_sec, cpu_desc = cpu_sample(primes, cpu_threads)
+        cpu_threads = host_threads()
+        # bounded CPU leg beside the GPU number: one warm-up pass (full batch) + two timed passes, sampled if the host is slow
+        cpu_sec, cpu_info = cpu_measure(primes, cpu_threads, steps=2, warmup=1, budget_s=25.0, single_thread=False)
         out = {
             "metric": "encrypted images/sec (CryptoNets-MNIST, N=8192)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic MNIST-shaped uint8 images (80% zeros), shipped CryptoNets weights, device-generated keys",
-            "config": {"workload": WORKLOAD, "plain_moduli": len(primes), "parallelism": "replica-per-gpu x%d" % world,
-                       "l2": "inputs larger than L2 (784 ct x 640 KiB per modulus)"},
+            "config": cpu_line_config(len(primes), world),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(host_in.numel() * 8), "d2h_bytes_per_step": int(host_out.numel() * 8)},
             "value_two_streams": {"value": value_two_streams, "unit": "images/s", "ms_per_step": ms2 / args.steps,
                                   "note": "same steps, one CUDA stream per plaintext modulus; not used for the roofline"},
             "roofline": roof,
-            "cpu_baseline": {"value": BATCH / cpu_sec, "unit": "images/s", "cores": cpu_threads, "kind": "port", "sample": cpu_desc},
+            "cpu_baseline": {"value": BATCH / cpu_sec, "unit": "images/s", "cores": cpu_threads, "kind": "port", "sample": cpu_info["mode"],
+                             "detail": cpu_info, "host": host_info()},
             "readme_anchor_images_per_s": 320.0,
         }
     last.Dispose()
@@ -368,6 +447,208 @@ def run_b200(args):
         dist.destroy_process_group()
     if out is not None:
         print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------------------------------- LoLa workloads (configs 3, 4)
+def lola_workloads():
+    from cryptonets_b200 import networks as nets
+    return {
+        # name: (builder, plaintext primes, N, decomposition bit count, the reference's SmallModulusCount, image maker, description)
+        "lola_small": (nets.lola_small, nets.LOLA_SMALL_PRIMES, 8192, 40, 3, nets.synthetic_mnist,
+                       "LoLa-small MNIST N=8192 k=3 w=40 (LoLaCryptonets.cs:280-329): LLPoolLayer conv > vectorize > square > LLDenseLayer 845x10, 1 image/inference"),
+        "lola_cifar": (nets.lola_cifar, nets.CIFAR_PRIMES, 16384, 60, 8, nets.synthetic_cifar,
+                       "LoLa-CIFAR N=16384 k=8 w=60 (LolaCifarCryptoNet.cs:27-131): conv 83 maps > vectorize > square > dense 5488x16268 (rotate-and-sum) > square > dense 5488x10, 1 image/inference, shipped weights"),
+    }
+
+
+def _layer_chain(net):
+    out, p = [], net
+    while p is not None and hasattr(p, "Source"):
+        out.append(p)
+        p = p.Source
+    return out[::-1]
+
+
+def run_lola(args):
+    import torch
+    import torch.distributed as dist
+    from cryptonets_b200.he import B200BfvFactory, B200BfvMatrix, B200BfvVector
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    builder, primes, N, dbc, k, imgs_of, desc = lola_workloads()[args.workload]
+    f = B200BfvFactory(primes, N, DecompositionBitCount=dbc, GaloisDecompositionBitCount=dbc, SmallModulusCount=k, seed=1 + rank, device=local)
+    eng = f.engine
+    net, reader = builder(f, imgs_of(1, seed=20240917 + rank))  # every rank owns its own image (replicas over images)
+    net.PrepareNetwork()
+    chain = _layer_chain(net)
+    enc_layer, rest = chain[1], chain[2:]
+    plain_in = chain[0].GetNext()
+    xm = enc_layer.Apply(plain_in)  # the client's ciphertexts: before the reference's timer (TimingLayer after EncryptLayer)
+    eng.sync()
+
+    def forward(m):
+        first = m
+        for layer in rest:
+            nxt = layer.Apply(m)
+            if m is not first:
+                m.Dispose()
+            m = nxt
+        return m
+
+    def barrier():
+        eng.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.set_option("multi_stream", 0)
+    for _ in range(args.warmup):
+        forward(xm).Dispose()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.op_counts(reset=True)
+    launches0 = eng.launch_count()
+    eng.prof_enable(True)
+    eng.timer_start()
+    for _ in range(args.steps):
+        forward(xm).Dispose()
+    ms = eng.timer_stop_ms()
+    barrier()
+    prof = eng.prof_collect()
+    eng.prof_enable(False)
+    counts = {k_: v // args.steps for k_, v in eng.op_counts(reset=True).items()}
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop()
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = args.steps * world / (ms * 1e-3)
+
+    # ---- e2e: the image's ciphertexts come from pinned host memory every step, the score ciphertexts go back to the host
+    vecs = xm.vectors
+    n_in, blocks = len(vecs), vecs[0].vec.blocks
+    host_in = torch.empty(eng.P * n_in * blocks * eng.ct_words, dtype=torch.int64).pin_memory()
+    eng.export_raw_many([v.vec for v in vecs], host_in.data_ptr())
+    dim0, scale0, fmt0 = vecs[0].vec.dim, vecs[0].vec.scale, vecs[0].vec.format
+    probe = forward(xm)
+    out_words = eng.P * sum(v.vec.blocks for v in probe.vectors) * eng.ct_words
+    probe.Dispose()
+    host_out = torch.empty(out_words, dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        imported = eng.import_raw_many(host_in.data_ptr(), n_in, blocks, dim0, scale0, fmt0)
+        m = B200BfvMatrix(f, [B200BfvVector(f, v) for v in imported], xm.Format, CopyVectors=False)
+        out = forward(m)
+        m.Dispose()
+        ticket = eng.export_raw_many_async([v.vec for v in out.vectors], host_out.data_ptr())
+        out.Dispose()
+        eng.export_wait(ticket)
+
+    eng.set_option("multi_stream", 1)
+    for _ in range(max(2, args.warmup)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+    out = None
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        fam = prof["ntt_forward"]
+        achieved = fam["bytes"] / (fam["ms"] * 1e-3) / 1e9 if fam["ms"] > 0 else 0.0
+        cpu = lola_cpu_estimate(args.workload, counts)
+        out = {
+            "metric": "encrypted images/sec (%s, one image per inference)" % args.workload, "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "latency_ms": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic image (uniform uint8 pixels), shipped weights, device-generated keys",
+            "config": {"workload": desc, "plain_moduli": len(primes), "parallelism": "replica-per-gpu x%d" % world,
+                       "l2": "key-switching keys (%d Galois elements) and digit waves larger than L2" % eng.n_galois},
+            "clocks": clocks, "gpu_launches": int(launches), "operations_per_inference": counts,
+            "e2e": {"value": args.steps * world / e2e_s, "unit": "images/s", "h2d_bytes_per_step": int(host_in.numel() * 8),
+                    "d2h_bytes_per_step": int(host_out.numel() * 8)},
+            "roofline": {"bound": "fp64-issue (reported against hbm)", "kernel": "forward NTT family (digit transforms of the Galois / relinearisation key switch), 16*N algorithmic bytes per transform",
+                         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)", "traffic": None, "launches_timed": fam["launches"],
+                         "share_of_step": fam["ms"] / ms if ms else None, "families_ms_per_step": {k_: v["ms"] / args.steps for k_, v in prof.items()}},
+            "cpu_baseline": cpu,
+        }
+    xm.Dispose()
+    f.Dispose()
+    if world > 1:
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+def lola_cpu_estimate(workload, counts, threads=None):
+    """CPU leg for a LoLa inference: the CPU oracle (test infrastructure; timed here, never used for results) runs each evaluator operation
+    the network issues -- rotation hop, dense multiply_plain, multiply + relinearise -- on one thread, and the per-inference operation
+    counts of the GPU run (the reference's OperationsCount) scale them.  Dividing by the host's thread count assumes the reference's
+    ParallelProcessInEnv scales perfectly over the rows of every layer: an upper bound on what the CPU can do."""
+    from oracle.oracle_py import Oracle
+    _, primes, N, dbc, k, _, _ = lola_workloads()[workload]
+    threads = threads or host_threads()
+    t = primes[0]
+    o = Oracle(t, N, k, dbc, dbc)
+    o.keygen(1)
+    rng = np.random.default_rng(0)
+    q = np.array(o.q, dtype=np.uint64)
+    ct = (rng.integers(0, 1 << 62, (2, o.k, N), dtype=np.uint64) % q[None, :, None]).reshape(-1)
+    plain = rng.integers(0, t, N, dtype=np.uint64)
+
+    def best(fn, reps=3):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    per_op = {
+        "Rotation": best(lambda: o.rotate_rows(ct, 1)),
+        "ColumnRotation": best(lambda: o.rotate_columns(ct)),
+        "PlainMultiplication": best(lambda: o.multiply_plain(ct, plain)),
+        "Multiplication": best(lambda: o.relinearize(o.multiply(ct, ct))),  # Multiply + Relinearize (counted once: Relinarization follows every Multiplication)
+        "Addition": best(lambda: o.add(ct, ct)),
+        "ScalarMultiplication": best(lambda: o.mac_layer(ct, None, np.array([3], dtype=np.uint64), None, 1, 1, threads=1)),
+    }
+    per_op["Subtraction"] = per_op["AddManyItemCount"] = per_op["PlainAddition"] = per_op["Addition"]
+    one_thread = len(primes) * sum(per_op.get(name, 0.0) * n for name, n in counts.items())
+    sec = one_thread / threads
+    return {"value": 1.0 / sec, "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": "one-thread oracle time of each evaluator operation x the per-inference operation counts, divided by %d threads (ideal scaling: upper bound for the CPU)" % threads,
+            "single_thread_seconds_per_image": one_thread, "per_op_seconds": per_op, "host": host_info()}
+
+
+def run_reference_lola(args):
+    """CPU arm of a LoLa workload: needs the per-inference operation counts, which come from a recorded GPU run (profiles/) or, when none is
+    present, from the counts written next to this file by the B200 arm."""
+    path = os.path.join(ROOT, "profiles", "r02_opcounts_%s.json" % args.workload)
+    counts = json.load(open(path))
+    threads = host_threads()
+    cpu = lola_cpu_estimate(args.workload, counts, threads)
+    desc = lola_workloads()[args.workload][6]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    print(json.dumps({
+        "impl": "reference", "metric": "encrypted images/sec (%s, one image per inference)" % args.workload, "value": cpu["value"], "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": {"workload": desc, "plain_moduli": len(lola_workloads()[args.workload][1]),
+                                                                            "parallelism": "replica-per-gpu x%d" % world},
+        "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def run_microbench(args):
@@ -381,7 +662,7 @@ def run_microbench(args):
         PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     cases = [(4096, 2), (4096, 3), (8192, 2), (8192, 4), (8192, 5), (16384, 4), (16384, 6)]
     t = {4096: 40961, 8192: 65537, 16384: 65537}
     rng = np.random.default_rng(0)
@@ -443,12 +724,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--plain-moduli", type=int, default=2, choices=[1, 2])
-    ap.add_argument("--microbench", action="store_true", help="NTT / multiply+relinearise micro-benchmark (BASELINE config 5), one JSON line per case")
+    ap.add_argument("--workload", default="cryptonets", choices=["cryptonets", "lola_small", "lola_cifar", "microbench"],
+                    help="cryptonets = BASELINE config 2 (the headline metric); lola_small / lola_cifar = configs 3 / 4 (one image per inference); "
+                         "microbench = config 5 (one JSON line per case)")
+    ap.add_argument("--microbench", action="store_true", help="same as --workload microbench")
     args = ap.parse_args()
-    if args.microbench:
+    if args.microbench or args.workload == "microbench":
         run_microbench(args)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.workload != "cryptonets":
+        run_lola(args)
     else:
         run_b200(args)
 

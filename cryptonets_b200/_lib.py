@@ -25,6 +25,10 @@ _SIGS = {
     "cnhe_context_set_option": [C.c_void_p, C.c_char_p, i64],
     "cnhe_context_sync": [C.c_void_p],
     "cnhe_keys_generate": [C.c_void_p, u64],
+    "cnhe_keys_save": [C.c_void_p, i32, C.c_void_p, sz, C.POINTER(sz)],
+    "cnhe_context_load": [C.c_void_p, sz, i32, C.POINTER(C.c_void_p)],
+    "cnhe_vec_write": [C.c_void_p, VECP, C.c_void_p, sz, C.POINTER(sz)],
+    "cnhe_vec_read": [C.c_void_p, C.c_char_p, sz, C.POINTER(VECP), C.POINTER(sz)],
     "cnhe_keys_generate_secure": [C.c_void_p],
     "cnhe_op_counts": [C.c_void_p, U64P, i32, i32],
     "cnhe_op_name": [i32],
@@ -34,6 +38,8 @@ _SIGS = {
     "cnhe_keys_set_seed": [C.c_void_p, i32, u64],
     "cnhe_vec_encrypt": [C.c_void_p, DBLP, u64, C.c_double, i32, C.POINTER(VECP)],
     "cnhe_vec_plain": [C.c_void_p, DBLP, u64, C.c_double, i32, C.POINTER(VECP)],
+    "cnhe_vec_from_residues": [C.c_void_p, U64P, u64, C.c_double, i32, i32, C.POINTER(VECP)],
+    "cnhe_vec_decrypt_residues": [C.c_void_p, VECP, U64P, u64],
     "cnhe_vecs_encrypt": [C.c_void_p, DBLP, i32, u64, C.c_double, C.POINTER(VECP)],
     "cnhe_vec_decrypt": [C.c_void_p, VECP, DBLP, u64],
     "cnhe_vecs_decrypt": [C.c_void_p, C.POINTER(VECP), i32, DBLP, u64],

@@ -14,6 +14,9 @@ struct NttTab {
     DMod mod;
     // FP64 butterfly path (p < 2^50): the same twiddles as exact doubles, centred in (-p/2, p/2]
     const double *wd, *iwd;
+    // the 15N/16 twiddles of the four unit-stride stages, transposed for the persistent kernels: wd_hi[m * N/16 + j] is the m-th twiddle
+    // (m = 0..14: 1 + 2 + 4 + 8 per stage) of the 16-coefficient group j in the last forward pass; iwd_hi likewise for the first inverse pass
+    const double *wd_hi, *iwd_hi;
     double pd, pinv, inv_n_d;
     double inv_n_w_d;                   // iw[1] * N^-1 mod p, centred: the last inverse stage carries the N^-1 scaling
     int fp_ok;                          // 1 when the FP64 path is exact for this modulus and N

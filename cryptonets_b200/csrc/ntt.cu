@@ -13,6 +13,9 @@
 // Shared-memory layout: word i is stored at i ^ (((i>>4)&7)<<1) so that the unit-stride last pass (16 consecutive
 // words per thread, 16-byte accesses) and the strided passes (gap >= 16 words) are both bank-conflict free.
 #include <cstdlib>
+#include <cstring>
+
+#include <cuda.h> // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link dependency)
 
 #include "kernels.h"
 #include "fparith.cuh"
@@ -684,8 +687,13 @@ __device__ __forceinline__ void inv_first_fp(double *sm, const u64 *src, const N
 }
 // The last stage (one twiddle, iw[1]) carries N^-1: sums are multiplied by N^-1, differences by iw[1]*N^-1, so every output is a
 // fresh modular product in (-0.51p, 0.51p): written as is (OUT_F, lazy double) or sign-fixed on the integer pipe (canonical).
-template <int LOGN, int V0, int R, bool LAST, bool OUT_F, int NV = 1>
-__device__ __forceinline__ void inv_pass_fp(double *sm, const double *twc, u64 *dst, const u64 *base_add, const NttTab &tb, int vt, int vstride = 0) {
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+// `after_load` runs once every input of the call sits in registers (the persistent kernels release / refill the shared-memory slot there)
+template <int LOGN, int V0, int R, bool LAST, bool OUT_F, int NV = 1, class Hook = NoHook>
+__device__ __forceinline__ void inv_pass_fp(double *sm, const double *twc, u64 *dst, const u64 *base_add, const NttTab &tb, int vt, int vstride = 0,
+                                            Hook after_load = Hook()) {
     constexpr int N = 1 << LOGN, E = 1 << R;
     constexpr bool CACHED = (N >> V0) <= TWC; // stage v reads indices [N>>(v+1), N>>v)
     const double p = tb.pd, pinv = tb.pinv;
@@ -760,6 +768,7 @@ __device__ __forceinline__ void inv_pass_fp(double *sm, const double *twc, u64 *
 #pragma unroll
             for (int e = 0; e < E; e++) x[i][e] = sm[swz(bb[i] + (e << V0))];
         }
+        after_load();
 #pragma unroll
         for (int i = 0; i < NV; i++) {
 #pragma unroll
@@ -842,6 +851,392 @@ k_ntt_inverse_fp(const u64 *src, const u64 *base_add, int base_group, size_t bas
     }
 }
 
+// ================================================================ persistent TMA-staged transforms, N = 4096 / 8192
+// One persistent CTA per SM.  Each CTA is pinned to ONE modulus (CTA c serves the polynomials whose table index is c mod #moduli), so
+// the twiddles it needs never change: the 15N/16 twiddles of the four unit-stride stages -- the ones that used to be fetched from L2 by
+// every polynomial (as many bytes as the polynomial itself, and the top stall of the one-CTA-per-polynomial kernel) -- are staged into
+// shared memory ONCE per CTA with cp.async.bulk, transposed so that lane j reads word m*T + j (conflict-free), next to the 512 low
+// twiddles of the strided stages.  Polynomials arrive by cp.async.bulk.tensor (a 2-D tensor map over the source array, 128-byte rows,
+// SWIZZLE_128B -- exactly the XOR layout swz() the butterfly passes use, so the hardware produces the bank-conflict-free layout on the
+// way in), completing on an mbarrier.  Two groups of 8 warps each own one polynomial slot: three fat passes in place between named
+// barriers of the group, results written straight from registers, then one elected thread refills the slot with the group's next
+// polynomial.  No compute warp ever waits on HBM or L2 for data or twiddles, there is no CTA launch/exit (store drain) per polynomial,
+// and the groups run out of phase so that one group's shared-memory round trips and slot refill hide under the other's FP64 work.
+constexpr int WS_GROUPS = 2, WS_GROUP_THREADS = 256, WS_THREADS = WS_GROUPS * WS_GROUP_THREADS;
+enum WsMode { WS_CANON = 0, WS_LAZY = 1, WS_DIGIT = 2 }; // how the first pass reads the staged words
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(
+                     smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_rows(void *dst, const void *tmap, int row, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(tmap), "r"(0), "r"(row), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void ws_delay(unsigned ns) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < ns);
+}
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(WS_GROUP_THREADS) : "memory"); }
+
+struct WsJob {
+    long long row;  // first 128-byte row of the source polynomial in the tensor map
+    size_t dst_off; // destination offset in words
+    int shift;      // digit mode
+};
+struct WsArgs {
+    int n_polys, mod_base, mod_count; // plain: polynomial b uses table mod_base + b % mod_count, source row b * N/16, destination b * N
+    int D;                            // digit mode: b -> (c, d, l) as in k_ntt_forward_digits_fp, mod_count = k, mod_base = 0
+    long long ct_stride_rows;
+    unsigned char src[64], shift[64];
+    u64 mask;
+    // inverse: optional base added to the canonical result
+    const u64 *base_add;
+    int base_group;
+    size_t base_stride;
+    unsigned stagger_ns; // group 1 starts this much later than group 0 (the groups should not walk through the passes in lockstep)
+};
+template <int LOGN, int MODE>
+__device__ __forceinline__ WsJob ws_job(const WsArgs &a, int b) {
+    constexpr int N = 1 << LOGN;
+    WsJob j;
+    if constexpr (MODE == WS_DIGIT) {
+        const int l = b % a.mod_count, d = (b / a.mod_count) % a.D, c = b / (a.mod_count * a.D);
+        j.row = (long long)c * a.ct_stride_rows + (long long)a.src[d] * (N / 16);
+        j.dst_off = (((size_t)c * a.mod_count + l) * a.D + d) * N;
+        j.shift = a.shift[d];
+    } else {
+        j.row = (long long)b * (N / 16);
+        j.dst_off = (size_t)b * N;
+        j.shift = 0;
+    }
+    return j;
+}
+// stage polynomial `b` into a slot; called by one thread
+template <int LOGN, int MODE>
+__device__ __forceinline__ void ws_issue(const CUtensorMap *tmap, const WsArgs &a, double *slot, unsigned long long *full, int b) {
+    constexpr int N = 1 << LOGN;
+    constexpr int BOX_ROWS = 256, BOXES = (N / 16) / BOX_ROWS;
+    const WsJob j = ws_job<LOGN, MODE>(a, b);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the slot's previous contents were read through the generic proxy
+    mbar_expect_tx(full, (unsigned)(N * 8));
+#pragma unroll
+    for (int x = 0; x < BOXES; x++) tma_load_rows(slot + x * BOX_ROWS * 16, tmap, (int)(j.row + x * BOX_ROWS), full);
+}
+// first forward pass on the staged words: R stages on 2^R coefficients at stride N >> R, in place
+template <int LOGN, int R, int MODE>
+__device__ __forceinline__ void fwd_first_staged(double *sm, const double *twc, int shift, u64 mask, bool need_reduce, const NttTab &tb, int vt) {
+    constexpr int E = 1 << R, LG = LOGN - R;
+    const double p = tb.pd, pinv = tb.pinv;
+    double x[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const double raw = sm[swz(vt + (e << LG))];
+        if constexpr (MODE == WS_LAZY) x[e] = raw;
+        else {
+            u64 v = (u64)__double_as_longlong(raw);
+            if constexpr (MODE == WS_DIGIT) v = (v >> shift) & mask;
+            x[e] = u2d(v);
+            if (MODE == WS_DIGIT && need_reduce) x[e] = frecenter(x[e], p, pinv);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+        const int h = E >> (u + 1);
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            if (e & h) continue;
+            const double w = twc[(1 << u) + (e >> (R - u))];
+            const double t = fmodmul(x[e + h], w, p, pinv);
+            const double a = x[e];
+            x[e] = __dadd_rn(a, t);
+            x[e + h] = __dsub_rn(a, t);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) sm[swz(vt + (e << LG))] = x[e];
+}
+// last forward pass with the unit-stride twiddles resident in shared memory (hi[m * T + j], m = 0..14): NV 16-coefficient groups per
+// thread (j0, j0 + jstride, ..); all of them are read before `after_load` runs, so the slot can be refilled under the arithmetic
+template <int LOGN, int PASS, bool OUT_F, int NV, class Hook>
+__device__ __forceinline__ void fwd_last_staged(const double *sm, u64 *dst, const NttTab &tb, const double *hi, int j0, int jstride, Hook after_load) {
+    constexpr int T = (1 << LOGN) / 16;
+    const double p = tb.pd, pinv = tb.pinv;
+    const bool rc = (tb.fwd_recenter >> PASS) & 1;
+    const double2 *smv = reinterpret_cast<const double2 *>(sm);
+    double xs[NV][16];
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const int j = j0 + i * jstride, xr = j & 7;
+#pragma unroll
+        for (int ch = 0; ch < 8; ch++) {
+            double2 v = smv[j * 8 + (ch ^ xr)];
+            xs[i][2 * ch] = v.x;
+            xs[i][2 * ch + 1] = v.y;
+        }
+    }
+    after_load();
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+    const int j = j0 + i * jstride;
+    double (&x)[16] = xs[i];
+    if (rc) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) x[e] = frecenter(x[e], p, pinv);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int h = 8 >> u;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            if (e & h) continue;
+            const double w = hi[((1 << u) - 1 + (e >> (4 - u))) * T + j];
+            const double t = fmodmul(x[e + h], w, p, pinv);
+            const double a = x[e];
+            x[e] = __dadd_rn(a, t);
+            x[e + h] = __dsub_rn(a, t);
+        }
+    }
+    u64 *o = dst + 16 * j;
+    if constexpr (OUT_F) {
+        if (tb.fwd_out_rc) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) x[e] = frecenter(x[e], p, pinv);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; g++) stg256(o + 4 * g, lazy_bits(x[4 * g]), lazy_bits(x[4 * g + 1]), lazy_bits(x[4 * g + 2]), lazy_bits(x[4 * g + 3]));
+    } else {
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+            stg256(o + 4 * g, fcanon_u(x[4 * g], p, pinv), fcanon_u(x[4 * g + 1], p, pinv), fcanon_u(x[4 * g + 2], p, pinv), fcanon_u(x[4 * g + 3], p, pinv));
+    }
+    }
+}
+// first inverse pass on the staged words: stages 0..3 on 16 consecutive coefficients, in place; twiddles from the resident table
+template <int LOGN, bool IN_F>
+__device__ __forceinline__ void inv_first_staged(double *sm, const NttTab &tb, const double *hi, int j) {
+    constexpr int T = (1 << LOGN) / 16;
+    const double p = tb.pd, pinv = tb.pinv;
+    double2 *smv = reinterpret_cast<double2 *>(sm);
+    const int xr = j & 7;
+    double x[16];
+#pragma unroll
+    for (int ch = 0; ch < 8; ch++) {
+        const double2 v = smv[j * 8 + (ch ^ xr)];
+        if constexpr (IN_F) { x[2 * ch] = v.x; x[2 * ch + 1] = v.y; }
+        else { x[2 * ch] = u2d((u64)__double_as_longlong(v.x)); x[2 * ch + 1] = u2d((u64)__double_as_longlong(v.y)); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int h = 1 << u;
+        const bool rc = (tb.inv_recenter >> u) & 1;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            if (e & h) continue;
+            const double w = hi[((16 - (16 >> u)) + (e >> (u + 1))) * T + j];
+            const double a = x[e], bq = x[e + h];
+            x[e] = __dadd_rn(a, bq);
+            x[e + h] = fmodmul(__dsub_rn(a, bq), w, p, pinv);
+        }
+        if (rc) {
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                if (!(e & h)) x[e] = frecenter(x[e], p, pinv);
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 8; ch++) smv[j * 8 + (ch ^ xr)] = make_double2(x[2 * ch], x[2 * ch + 1]);
+}
+
+#define CNHE_WS_VT(COUNT, stmt) _Pragma("unroll") for (int vt = gt; vt < (COUNT); vt += WS_GROUP_THREADS) { stmt; }
+template <int LOGN>
+__host__ __device__ constexpr int ws_hi_words() { return 15 * (1 << LOGN) / 16; }
+template <int LOGN>
+__host__ __device__ constexpr int ws_smem_bytes() { return (WS_GROUPS * (1 << LOGN) + ws_hi_words<LOGN>() + TWC) * 8 + 64 + (int)sizeof(NttTab) + 1024; }
+
+// shared prologue: carve shared memory, stage the CTA's twiddle tables and the first polynomial of each group
+struct WsSmem {
+    double *slots, *hi, *lo; // slot g = slots + g * N (plain pointer arithmetic on the __shared__ symbol keeps the address space)
+    unsigned long long *full, *tbar, *empty;
+    NttTab *tab; // the CTA's modulus record, copied once: per-polynomial reads are LDS instead of (L1-missing) global loads
+};
+template <int LOGN>
+__device__ __forceinline__ WsSmem ws_carve(unsigned char *raw) {
+    constexpr int N = 1 << LOGN;
+    WsSmem w;
+    // SWIZZLE_128B wants 1024-byte aligned slots.  The padding is added to the __shared__ symbol itself (no integer round trip), so the
+    // compiler still knows every derived pointer is shared memory and emits LDS/STS instead of generic loads
+    const unsigned pad = (1024u - (smem_u32(raw) & 1023u)) & 1023u;
+    double *base = reinterpret_cast<double *>(raw + pad);
+    w.slots = base;
+    w.hi = base + (size_t)WS_GROUPS * N;
+    w.lo = w.hi + ws_hi_words<LOGN>();
+    w.full = reinterpret_cast<unsigned long long *>(w.lo + TWC);
+    w.tbar = w.full + WS_GROUPS;
+    w.empty = w.tbar + 1;
+    w.tab = reinterpret_cast<NttTab *>(w.empty + WS_GROUPS);
+    return w;
+}
+// which polynomials this CTA serves: class m = blockIdx % mc (its modulus), the r-th CTA of the S CTAs of that class takes j = r, r + S, ...
+struct WsWalk {
+    int m, mc, r, S;
+    __device__ __forceinline__ int poly(int s) const { return m + mc * (r + s * S); } // sequence number -> polynomial index (may run past n_polys)
+};
+__device__ __forceinline__ WsWalk ws_walk(int mc) {
+    WsWalk w;
+    w.mc = mc;
+    w.m = blockIdx.x % mc;
+    w.r = blockIdx.x / mc;
+    w.S = ((int)gridDim.x - w.m + mc - 1) / mc;
+    return w;
+}
+
+template <int LOGN, int MODE, bool OUT_F>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+k_ntt_forward_ws(const __grid_constant__ CUtensorMap tmap, u64 *dst, const NttTab *__restrict__ tabs, const WsArgs a) {
+    static_assert(LOGN == 12 || LOGN == 13, "the staged transform covers N = 4096 and 8192");
+    constexpr int N = 1 << LOGN;
+    extern __shared__ unsigned char ws_raw[];
+    const int tid = threadIdx.x;
+    {
+        const WsSmem sm_ = ws_carve<LOGN>(ws_raw);
+        const WsWalk walk = ws_walk(a.mod_count);
+        if (tid == 0) {
+            const NttTab &tb0 = tabs[a.mod_base + walk.m];
+            *sm_.tab = tb0;
+            for (int g = 0; g < WS_GROUPS; g++) { mbar_init(&sm_.full[g], 1); mbar_init(&sm_.empty[g], WS_GROUP_THREADS); }
+            mbar_init(sm_.tbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(sm_.tbar, (unsigned)((ws_hi_words<LOGN>() + TWC) * 8));
+            bulk_load(sm_.hi, tb0.wd_hi, ws_hi_words<LOGN>() * 8, sm_.tbar);
+            bulk_load(sm_.lo, tb0.wd, TWC * 8, sm_.tbar);
+            for (int g = 0; g < WS_GROUPS; g++)
+                if (walk.poly(g) < a.n_polys) ws_issue<LOGN, MODE>(&tmap, a, sm_.slots + (size_t)g * N, &sm_.full[g], walk.poly(g));
+        }
+        __syncthreads();
+        mbar_wait(sm_.tbar, 0);
+    }
+    const int g = tid / WS_GROUP_THREADS, gt = tid % WS_GROUP_THREADS;
+    if (g == 1 && a.stagger_ns) ws_delay(a.stagger_ns);
+    FwdSrc unused;
+    unused.src = nullptr; unused.digit = false; unused.need_reduce = false; unused.shift = 0; unused.mask = 0;
+#pragma unroll 1
+    for (int t = 0;; t++) {
+        // everything below is re-derived per polynomial on purpose: nothing but t stays live across the register-hungry radix-32 pass
+        const WsWalk walk = ws_walk(a.mod_count);
+        const int b = walk.poly(g + WS_GROUPS * t);
+        if (b >= a.n_polys) break;
+        const WsSmem sm_ = ws_carve<LOGN>(ws_raw);
+        const NttTab &tb = *sm_.tab;
+        double *sm = sm_.slots + (size_t)g * N;
+        const double *twc = sm_.lo, *hi = sm_.hi;
+        const bool need_reduce = MODE == WS_DIGIT && a.mask >= tb.mod.p;
+        const WsJob job = ws_job<LOGN, MODE>(a, b);
+        // once the last pass holds its inputs in registers the slot is dead: refill it with the group's next polynomial under the arithmetic
+        auto refill = [&]() { // every thread reports its reads done; only the elected thread waits for all of them before issuing the copy
+            mbar_arrive(&sm_.empty[g]);
+            const int nb = walk.poly(g + WS_GROUPS * (t + 1));
+            if (gt == 0 && nb < a.n_polys) {
+                mbar_wait(&sm_.empty[g], t & 1);
+                ws_issue<LOGN, MODE>(&tmap, a, sm, &sm_.full[g], nb);
+            }
+        };
+        mbar_wait(&sm_.full[g], t & 1);
+        if constexpr (LOGN == 13) {
+            CNHE_WS_VT(N / 32, (fwd_first_staged<13, 5, MODE>(sm, twc, job.shift, a.mask, need_reduce, tb, vt))); group_sync(g);
+            CNHE_WS_VT(N / 16, (fwd_pass_fp<13, 5, 4, false, 1, false>(sm, twc, unused, tb, vt))); group_sync(g);
+            fwd_last_staged<13, 2, OUT_F, 2>(sm, dst + job.dst_off, tb, hi, gt, WS_GROUP_THREADS, refill);
+        } else {
+            CNHE_WS_VT(N / 16, (fwd_first_staged<12, 4, MODE>(sm, twc, job.shift, a.mask, need_reduce, tb, vt))); group_sync(g);
+            CNHE_WS_VT(N / 16, (fwd_pass_fp<12, 4, 4, false, 1, false>(sm, twc, unused, tb, vt))); group_sync(g);
+            fwd_last_staged<12, 2, OUT_F, 1>(sm, dst + job.dst_off, tb, hi, gt, WS_GROUP_THREADS, refill);
+        }
+    }
+}
+template <int LOGN, bool IN_F, bool OUT_F>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+k_ntt_inverse_ws(const __grid_constant__ CUtensorMap tmap, u64 *dst, const NttTab *__restrict__ tabs, const WsArgs a) {
+    static_assert(LOGN == 12 || LOGN == 13, "the staged transform covers N = 4096 and 8192");
+    constexpr int N = 1 << LOGN;
+    extern __shared__ unsigned char ws_raw[];
+    const int tid = threadIdx.x;
+    {
+        const WsSmem sm_ = ws_carve<LOGN>(ws_raw);
+        const WsWalk walk = ws_walk(a.mod_count);
+        if (tid == 0) {
+            const NttTab &tb0 = tabs[a.mod_base + walk.m];
+            *sm_.tab = tb0;
+            for (int g = 0; g < WS_GROUPS; g++) { mbar_init(&sm_.full[g], 1); mbar_init(&sm_.empty[g], WS_GROUP_THREADS); }
+            mbar_init(sm_.tbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(sm_.tbar, (unsigned)((ws_hi_words<LOGN>() + TWC) * 8));
+            bulk_load(sm_.hi, tb0.iwd_hi, ws_hi_words<LOGN>() * 8, sm_.tbar);
+            bulk_load(sm_.lo, tb0.iwd, TWC * 8, sm_.tbar);
+            for (int g = 0; g < WS_GROUPS; g++)
+                if (walk.poly(g) < a.n_polys) ws_issue<LOGN, WS_CANON>(&tmap, a, sm_.slots + (size_t)g * N, &sm_.full[g], walk.poly(g));
+        }
+        __syncthreads();
+        mbar_wait(sm_.tbar, 0);
+    }
+    const int g = tid / WS_GROUP_THREADS, gt = tid % WS_GROUP_THREADS;
+    if (g == 1 && a.stagger_ns) ws_delay(a.stagger_ns);
+#pragma unroll 1
+    for (int t = 0;; t++) {
+        const WsWalk walk = ws_walk(a.mod_count);
+        const int b = walk.poly(g + WS_GROUPS * t);
+        if (b >= a.n_polys) break;
+        const WsSmem sm_ = ws_carve<LOGN>(ws_raw);
+        const NttTab &tb = *sm_.tab;
+        double *sm = sm_.slots + (size_t)g * N;
+        const double *twc = sm_.lo, *hi = sm_.hi;
+        u64 *d = dst + (size_t)b * N;
+        const u64 *ba = a.base_add ? a.base_add + (size_t)(b / a.base_group) * a.base_stride + (size_t)(b % a.base_group) * N : nullptr;
+        if (ba) { // consumed by the epilogue most of a transform from now: have it waiting in L2
+            const char *pb = reinterpret_cast<const char *>(ba);
+            for (int i = gt * 128; i < N * 8; i += WS_GROUP_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + i));
+        }
+        auto refill = [&]() {
+            mbar_arrive(&sm_.empty[g]);
+            const int nb = walk.poly(g + WS_GROUPS * (t + 1));
+            if (gt == 0 && nb < a.n_polys) {
+                mbar_wait(&sm_.empty[g], t & 1);
+                ws_issue<LOGN, WS_CANON>(&tmap, a, sm, &sm_.full[g], nb);
+            }
+        };
+        mbar_wait(&sm_.full[g], t & 1);
+        CNHE_WS_VT(N / 16, (inv_first_staged<LOGN, IN_F>(sm, tb, hi, vt))); group_sync(g);
+        if constexpr (LOGN == 13) {
+            CNHE_WS_VT(N / 16, (inv_pass_fp<13, 4, 4, false, false>(sm, twc, d, ba, tb, vt))); group_sync(g);
+            inv_pass_fp<13, 8, 5, true, OUT_F, 1>(sm, twc, d, ba, tb, gt, 0, refill); // one radix-32 group per thread
+        } else {
+            CNHE_WS_VT(N / 16, (inv_pass_fp<12, 4, 4, false, false>(sm, twc, d, ba, tb, vt))); group_sync(g);
+            inv_pass_fp<12, 8, 4, true, OUT_F, 1>(sm, twc, d, ba, tb, gt, 0, refill);
+        }
+    }
+}
+
 int ntt_pass_radices(int logn, int inverse, int *r) {
     static const int F[5][4] = {{2, 4, 4, 0}, {3, 4, 4, 0}, {4, 4, 4, 0}, {5, 4, 4, 0}, {5, 5, 4, 0}};
     static const int I[5][4] = {{4, 4, 2, 0}, {4, 4, 3, 0}, {4, 4, 4, 0}, {4, 4, 5, 0}, {4, 5, 5, 0}};
@@ -862,6 +1257,70 @@ static cudaError_t prep(K kern, int logn) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ntt_kernel_smem_bytes(logn));
 }
 
+// ---- host side of the staged transforms: tensor map over the source array, persistent grid of one CTA per SM
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// CNHE_NTT_WS=0 switches the persistent kernels off altogether; CNHE_NTT_WS_FWD / CNHE_NTT_WS_INV override one direction
+static bool ws_flag(const char *name, bool dflt) {
+    const char *all = getenv("CNHE_NTT_WS"), *one = getenv(name);
+    if (encode_tiled() == nullptr) return false;
+    if (one) return atoi(one) != 0;
+    if (all) return atoi(all) != 0;
+    return dflt;
+}
+static bool ws_enabled_fwd() {
+    static const bool on = ws_flag("CNHE_NTT_WS_FWD", true);
+    return on;
+}
+static bool ws_enabled_inv() {
+    static const bool on = ws_flag("CNHE_NTT_WS_INV", true);
+    return on;
+}
+static int sm_count() {
+    static int n = [] {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
+    return n;
+}
+// rows of 16 words (128 bytes) starting at `base`; boxes of 256 rows, hardware swizzle = swz()
+static cudaError_t make_row_map(CUtensorMap *m, const u64 *base, size_t words) {
+    const cuuint64_t dims[2] = {16, (cuuint64_t)(words / 16)};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {16, 256}, estr[2] = {1, 1};
+    if (words % 16 || dims[1] < 256 || (reinterpret_cast<uintptr_t>(base) & 15)) return cudaErrorInvalidValue;
+    const CUresult r = encode_tiled()(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<u64 *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+static unsigned ws_stagger_ns() {
+    static const unsigned v = getenv("CNHE_WS_STAGGER") ? (unsigned)atoi(getenv("CNHE_WS_STAGGER")) : 5000u;
+    return v;
+}
+template <class K>
+static cudaError_t ws_launch(K kern, int smem, const CUtensorMap &map, u64 *dst, const NttTab *tabs, const WsArgs &a0, cudaStream_t s) {
+    WsArgs a = a0;
+    a.stagger_ns = ws_stagger_ns();
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    int grid = sm_count();
+    if (a.mod_count <= grid) grid -= grid % a.mod_count; // equally many CTAs per modulus: every CTA is pinned to one
+    if (a.n_polys < grid) grid = a.n_polys;
+    kern<<<grid, WS_THREADS, smem, s>>>(map, dst, tabs, a);
+    return cudaGetLastError();
+}
+
 #define CNHE_DISPATCH_LOGN(logn, ...)                                                                                 \
     switch (logn) {                                                                                                     \
     case 10: { constexpr int L = 10; __VA_ARGS__; } break;                                                                     \
@@ -880,6 +1339,18 @@ cudaError_t launch_ntt_forward(const u64 *src, u64 *dst, int n_polys, int logn, 
     if (fp & NTT_FP) {
         const bool lazy = (fp & (NTT_IN_F | NTT_OUT_F)) == (NTT_IN_F | NTT_OUT_F);
         if (!lazy && (fp & (NTT_IN_F | NTT_OUT_F))) return cudaErrorInvalidValue; // only canonical->canonical and lazy->lazy are built
+        if ((logn == 12 || logn == 13) && ws_enabled_fwd()) {
+            CUtensorMap map;
+            cudaError_t e = make_row_map(&map, src, (size_t)n_polys << logn);
+            if (e != cudaSuccess) return e;
+            WsArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n_polys = n_polys; a.mod_base = mod_base; a.mod_count = mod_count;
+            if (logn == 13) return lazy ? ws_launch(k_ntt_forward_ws<13, WS_LAZY, true>, ws_smem_bytes<13>(), map, dst, tabs, a, s)
+                                        : ws_launch(k_ntt_forward_ws<13, WS_CANON, false>, ws_smem_bytes<13>(), map, dst, tabs, a, s);
+            return lazy ? ws_launch(k_ntt_forward_ws<12, WS_LAZY, true>, ws_smem_bytes<12>(), map, dst, tabs, a, s)
+                        : ws_launch(k_ntt_forward_ws<12, WS_CANON, false>, ws_smem_bytes<12>(), map, dst, tabs, a, s);
+        }
         CNHE_DISPATCH_LOGN(logn, {
             if (lazy) {
                 cudaError_t e = prep(k_ntt_forward_fp<L, true, true>, L);
@@ -905,6 +1376,20 @@ cudaError_t launch_ntt_forward_digits(const u64 *target, size_t ct_stride, u64 *
     if (n_ct <= 0) return cudaSuccess;
     if (fp & NTT_FP) {
         if (fp & NTT_IN_F) return cudaErrorInvalidValue; // digits are cut from canonical words
+        if ((logn == 12 || logn == 13) && ws_enabled_fwd() && ct_stride % 16 == 0) {
+            CUtensorMap map;
+            cudaError_t e = make_row_map(&map, target, (size_t)(n_ct - 1) * ct_stride + ((size_t)k << logn));
+            if (e != cudaSuccess) return e;
+            WsArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n_polys = n_ct * dm.D * k; a.mod_base = 0; a.mod_count = k; a.D = dm.D; a.ct_stride_rows = (long long)(ct_stride / 16); a.mask = dm.mask;
+            memcpy(a.src, dm.src, 64); memcpy(a.shift, dm.shift, 64);
+            const bool of = fp & NTT_OUT_F;
+            if (logn == 13) return of ? ws_launch(k_ntt_forward_ws<13, WS_DIGIT, true>, ws_smem_bytes<13>(), map, dst, tabs, a, s)
+                                      : ws_launch(k_ntt_forward_ws<13, WS_DIGIT, false>, ws_smem_bytes<13>(), map, dst, tabs, a, s);
+            return of ? ws_launch(k_ntt_forward_ws<12, WS_DIGIT, true>, ws_smem_bytes<12>(), map, dst, tabs, a, s)
+                      : ws_launch(k_ntt_forward_ws<12, WS_DIGIT, false>, ws_smem_bytes<12>(), map, dst, tabs, a, s);
+        }
         CNHE_DISPATCH_LOGN(logn, {
             if (fp & NTT_OUT_F) {
                 cudaError_t e = prep(k_ntt_forward_digits_fp<L, true>, L);
@@ -941,6 +1426,22 @@ static cudaError_t launch_inv(const u64 *src, const u64 *base, int base_group, s
     if (fp & NTT_FP) {
         const bool in_f = fp & NTT_IN_F, out_f = fp & NTT_OUT_F;
         if (out_f && (!in_f || base)) return cudaErrorInvalidValue; // built: canonical->canonical, lazy->lazy, lazy->canonical(+base)
+        if ((logn == 12 || logn == 13) && ws_enabled_inv()) {
+            CUtensorMap map;
+            cudaError_t e = make_row_map(&map, src, (size_t)n_polys << logn);
+            if (e != cudaSuccess) return e;
+            WsArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n_polys = n_polys; a.mod_base = mod_base; a.mod_count = mod_count;
+            a.base_add = base; a.base_group = base_group; a.base_stride = base_stride;
+            if (logn == 13)
+                return out_f  ? ws_launch(k_ntt_inverse_ws<13, true, true>, ws_smem_bytes<13>(), map, dst, tabs, a, s)
+                       : in_f ? ws_launch(k_ntt_inverse_ws<13, true, false>, ws_smem_bytes<13>(), map, dst, tabs, a, s)
+                              : ws_launch(k_ntt_inverse_ws<13, false, false>, ws_smem_bytes<13>(), map, dst, tabs, a, s);
+            return out_f  ? ws_launch(k_ntt_inverse_ws<12, true, true>, ws_smem_bytes<12>(), map, dst, tabs, a, s)
+                   : in_f ? ws_launch(k_ntt_inverse_ws<12, true, false>, ws_smem_bytes<12>(), map, dst, tabs, a, s)
+                          : ws_launch(k_ntt_inverse_ws<12, false, false>, ws_smem_bytes<12>(), map, dst, tabs, a, s);
+        }
         CNHE_DISPATCH_LOGN(logn, {
             cudaError_t e = out_f  ? launch_inv_fp<L, true, true>(src, base, base_group, base_stride, dst, n_polys, tabs, mod_base, mod_count, s)
                             : in_f ? launch_inv_fp<L, true, false>(src, base, base_group, base_stride, dst, n_polys, tabs, mod_base, mod_count, s)

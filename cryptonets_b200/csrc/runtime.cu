@@ -1,6 +1,7 @@
 // Host runtime of libcnhe (see runtime.h).  Product code: builds every table with hostmath.h, never touches oracle/.
 #include "runtime.h"
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 
 #include <algorithm>
@@ -31,12 +32,18 @@ const char *op_kind_name(int kind) {
                                   "AddManyItemCount"};
     return kind >= 0 && kind < Context::OP_COUNT ? names[kind] : "?";
 }
-void Context::note(OpKind kind, int channel, int n, const u64 *first_out) {
+void Context::note(OpKind kind, int channel, int n, const u64 *first_out, const u64 *in0, const u64 *in1, double aux) {
     op_count[kind] += (uint64_t)n;
     if (!trace_noise || kind == OP_ADD_MANY_ITEMS) return;
     int budget = -1;
-    if (first_out && channel >= 0 && channel < P && ch[channel].have_sk) budget = op_noise_budget(*this, channel, first_out);
-    trace.push_back({(int)kind, channel, n, budget});
+    const int b0 = in0 ? known_budget(in0) : -1, b1 = in1 ? known_budget(in1) : -1; // before the output (possibly in place) is re-measured
+    if (first_out && channel >= 0 && channel < P && ch[channel].have_sk) {
+        budget = op_noise_budget(*this, channel, first_out);
+        // the call wrote n ciphertexts starting here: whatever was recorded for these addresses (recycled blocks) is stale now
+        budget_of.erase(budget_of.lower_bound(first_out), budget_of.lower_bound(first_out + (size_t)n * ct_words()));
+        budget_of[first_out] = budget;
+    }
+    trace.push_back({(int)kind, channel, n, budget, b0, b1, (int)std::lround(aux * 1000.0), 0});
 }
 
 void cuda_check(cudaError_t e, const char *what) {
@@ -435,14 +442,14 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
     for (u64 p : c.q) moduli.push_back(p);
     for (u64 p : c.bsk) moduli.push_back(p);
     for (u64 p : c.t) moduli.push_back(p);
-    std::vector<u64> host((size_t)n_mod * 6 * N);
+    std::vector<u64> host((size_t)n_mod * 8 * N, 0);
     CNHE_CUDA(cudaMalloc((void **)&c.d_table_mem, host.size() * sizeof(u64)));
     c.h_tabs.resize(n_mod);
     for (int m = 0; m < n_mod; m++) {
         const u64 p = moduli[m];
         const u64 psi = hm::minimal_primitive_root(2ULL * N, p), ipsi = hm::inv(psi, p);
-        u64 *w = &host[((size_t)m * 6 + 0) * N], *ws = w + N, *iw = ws + N, *iws = iw + N;
-        double *wd = reinterpret_cast<double *>(iws + N), *iwd = wd + N;
+        u64 *w = &host[((size_t)m * 8 + 0) * N], *ws = w + N, *iw = ws + N, *iws = iw + N;
+        double *wd = reinterpret_cast<double *>(iws + N), *iwd = wd + N, *wd_hi = iwd + N, *iwd_hi = wd_hi + N;
         u64 a = 1, b = 1;
         for (u64 i = 0; i < N; i++) {
             const u64 r = hm::bit_reverse(i, logN);
@@ -453,11 +460,25 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
             a = hm::mul(a, psi, p);
             b = hm::mul(b, ipsi, p);
         }
+        { // transposed unit-stride twiddles (see NttTab::wd_hi)
+            const u64 T = N / 16;
+            const int S0 = logN - 4;
+            for (u64 j = 0; j < T; j++) {
+                for (int u = 0; u < 4; u++)
+                    for (int i = 0; i < (1 << u); i++) wd_hi[(u64)((1 << u) - 1 + i) * T + j] = wd[((u64)1 << (S0 + u)) + (j << u) + i];
+                for (int i = 0; i < 8; i++) iwd_hi[(u64)i * T + j] = iwd[(N >> 1) + (j << 3) + i];
+                for (int i = 0; i < 4; i++) iwd_hi[(u64)(8 + i) * T + j] = iwd[(N >> 2) + (j << 2) + i];
+                for (int i = 0; i < 2; i++) iwd_hi[(u64)(12 + i) * T + j] = iwd[(N >> 3) + (j << 1) + i];
+                iwd_hi[(u64)14 * T + j] = iwd[(N >> 4) + j];
+            }
+        }
         NttTab &tb = c.h_tabs[m];
-        u64 *base = c.d_table_mem + (size_t)m * 6 * N;
+        u64 *base = c.d_table_mem + (size_t)m * 8 * N;
         tb.w = base; tb.ws = base + N; tb.iw = base + 2 * (size_t)N; tb.iws = base + 3 * (size_t)N;
         tb.wd = reinterpret_cast<const double *>(base + 4 * (size_t)N);
         tb.iwd = reinterpret_cast<const double *>(base + 5 * (size_t)N);
+        tb.wd_hi = reinterpret_cast<const double *>(base + 6 * (size_t)N);
+        tb.iwd_hi = reinterpret_cast<const double *>(base + 7 * (size_t)N);
         tb.inv_n = hm::inv(N % p, p);
         tb.inv_n_s = hm::shoup(tb.inv_n, p);
         tb.mod = make_dmod(p);
@@ -790,7 +811,7 @@ void op_multiply_relin(Context &c, int ch, const std::vector<const u64 *> &a, co
         op_key_switch(c, ct3 + (size_t)2 * k * N, s3, m, c.ch[ch].rlk->p, c.dm_relin, ct3, s3, out2 + (size_t)c0 * 2 * k * N);
     }
     c.op_count[Context::OP_MULTIPLY] += (uint64_t)n;
-    c.note(Context::OP_RELINEARIZE, ch, n, out2);
+    c.note(Context::OP_RELINEARIZE, ch, n, out2, a[0], b[0]);
 }
 
 u64 galois_elt_from_step(const Context &c, int steps) { // Evaluator::galois_elt_from_step: positive = rotate left
@@ -819,7 +840,7 @@ void op_apply_galois(Context &c, int ch, const u64 *in, int n, u64 elt, u64 *out
         c.check(launch_galois(in + (size_t)c0 * 2 * k * N, base, p1, m, einv, k, c.logN, c.d_bc, c.stream), "galois");
         op_key_switch(c, p1, (size_t)k * N, m, it->second->p, c.dm_galois, base, (size_t)2 * k * N, out + (size_t)c0 * 2 * k * N);
     }
-    c.note(elt == m2 - 1 ? Context::OP_ROTATE_COLUMNS : Context::OP_ROTATE_ROWS_HOP, ch, n, out);
+    c.note(elt == m2 - 1 ? Context::OP_ROTATE_COLUMNS : Context::OP_ROTATE_ROWS_HOP, ch, n, out, in);
 }
 static std::vector<int> naf(int value) { // non-adjacent form, least significant term first (SEAL util::naf)
     std::vector<int> res;
@@ -835,7 +856,7 @@ static std::vector<int> naf(int value) { // non-adjacent form, least significant
 void op_rotate_rows(Context &c, int ch, const u64 *in, int n, int steps, u64 *out) { // Evaluator::rotate_internal
     const size_t words = (size_t)n * c.ct_words();
     if (steps == 0) {
-        if (in != out) CNHE_CUDA(cudaMemcpyAsync(out, in, words * 8, cudaMemcpyDeviceToDevice, c.stream));
+        if (in != out) { CNHE_CUDA(cudaMemcpyAsync(out, in, words * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(out, in); }
         return;
     }
     const u64 elt = galois_elt_from_step(c, steps);
@@ -849,7 +870,7 @@ void op_rotate_rows(Context &c, int ch, const u64 *in, int n, int steps, u64 *ou
         op_rotate_rows(c, ch, cur, n, hops[h], nxt);
         cur = nxt;
     }
-    if (cur != out) CNHE_CUDA(cudaMemcpyAsync(out, cur, words * 8, cudaMemcpyDeviceToDevice, c.stream));
+    if (cur != out) { CNHE_CUDA(cudaMemcpyAsync(out, cur, words * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(out, cur); }
 }
 void op_rotate_columns(Context &c, int ch, const u64 *in, int n, u64 *out) { op_apply_galois(c, ch, in, n, 2ULL * c.N - 1, out); }
 
@@ -864,7 +885,7 @@ void op_multiply_plain_dense(Context &c, int ch, const u64 *ct, int n, const u64
     c.check(launch_ntt_forward(ct, tmp, n * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_forward");
     c.check(launch_dyadic_bcast(tmp, lifted, tmp, n, 2, 1, plain_per_ct ? 1 : 0, k, c.logN, c.d_bc, c.stream), "dyadic");
     c.check(launch_ntt_inverse(tmp, out, n * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_inverse");
-    c.note(Context::OP_MULTIPLY_PLAIN, ch, n, out);
+    c.note(Context::OP_MULTIPLY_PLAIN, ch, n, out, ct);
 }
 // one ciphertext times n dense plaintexts: out[i] = ct * plain[i]   (row-major matrix x vector: every row against the same input)
 void op_multiply_plain_dense_bcast(Context &c, int ch, const u64 *ct, const u64 *plains, int n, u64 *out) {
@@ -882,7 +903,7 @@ void op_multiply_plain_dense_bcast(Context &c, int ch, const u64 *ct, const u64 
         c.check(launch_dyadic_bcast(ctn, lifted, dst, m, 2, 0, 1, k, c.logN, c.d_bc, c.stream), "dyadic");
         c.check(launch_ntt_inverse(dst, dst, m * 2 * k, c.logN, c.d_tabs, 0, k, fp_range(c, 0, k), c.stream), "ntt_inverse");
     }
-    c.note(Context::OP_MULTIPLY_PLAIN, ch, n, out);
+    c.note(Context::OP_MULTIPLY_PLAIN, ch, n, out, ct);
 }
 void op_encode(Context &c, int ch, const u64 *values, int n, int count, u64 *plain) {
     c.check(launch_encode_scatter(values, plain, n, count, c.d_index_map, c.logN, c.stream), "encode_scatter");

@@ -99,10 +99,19 @@ struct Context {
                   OP_SUB_PLAIN, OP_ROTATE_ROWS_HOP, OP_ROTATE_COLUMNS, OP_ADD_MANY, OP_ADD_MANY_ITEMS, OP_COUNT };
     uint64_t op_count[OP_COUNT] = {0};
     bool trace_noise = false;
-    struct TraceRec { int kind, channel, n, budget; };
+    struct TraceRec { int kind, channel, n, budget, in0, in1, aux_milli, reserved; };
     std::vector<TraceRec> trace;
-    // count `n` operations of `kind`; with tracing on, also record the invariant noise budget of the first output ciphertext
-    void note(OpKind kind, int channel, int n, const u64 *first_out = nullptr);
+    std::map<const u64 *, int> budget_of; // tracing only: last measured budget of the ciphertext at a device address
+    // count `n` operations of `kind`; with tracing on, also record the invariant noise budget of the first output ciphertext next to the
+    // budgets its first input ciphertexts had (so that every operation can be checked against the analytic noise model on its own) and
+    // an operation-specific `aux` value (log2 of the scalar / of the root-sum-square weight of a MAC output)
+    void note(OpKind kind, int channel, int n, const u64 *first_out = nullptr, const u64 *in0 = nullptr, const u64 *in1 = nullptr, double aux = 0);
+    void note_copy(const u64 *dst, const u64 *src) { // a device-to-device copy of a ciphertext keeps its budget
+        if (!trace_noise) return;
+        auto it = budget_of.find(src);
+        if (it != budget_of.end()) budget_of[dst] = it->second; else budget_of.erase(dst);
+    }
+    int known_budget(const u64 *p) const { auto it = budget_of.find(p); return it == budget_of.end() ? -1 : it->second; }
     int chunk = 1024; // ciphertexts per kernel wave (upper bound: wave() also keeps a wave's scratch under ~8 GiB)
     int wave(size_t words_per_ct) const { // ciphertexts per wave for an operation needing `words_per_ct` scratch words per ciphertext
         const size_t fit = ((size_t)1 << 30) / (words_per_ct ? words_per_ct : 1); // 2^30 words = 8 GiB

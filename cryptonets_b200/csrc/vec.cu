@@ -9,57 +9,18 @@
 #include <cstring>
 #include <unordered_map>
 
-#include "../../include/cnhe.h"
 #include "hostmath.h"
-#include "runtime.h"
+#include "vec.h"
 
-using namespace cnhe;
 typedef unsigned __int128 u128;
 
-struct cnhe_ctx {
-    Context *c;
-};
-
-struct cnhe_vec {
-    Context *ctx = nullptr;
-    uint64_t dim = 0;
-    double scale = 1.0;
-    int format = CNHE_DENSE;
-    bool enc = false;
-    int blocks = 0; // ciphertexts / plaintexts per channel
-    std::vector<BufRef> buf; // per channel: enc -> blocks*2kN words, plain dense -> blocks*N words, plain sparse -> `blocks` scalars
-    std::vector<size_t> off;
-    std::vector<std::vector<u64>> scalars; // plain sparse: host copy of the constants (mod t)
-    bool is_const = false;                 // plain dense whose every plaintext is a constant polynomial
-    std::vector<u64> const_val;            // per channel constant (mod t) when is_const
-
-    u64 *ptr(int ch) const { return buf[ch]->p + off[ch]; }
-    size_t unit() const { return enc ? ctx->ct_words() : (format == CNHE_DENSE ? (size_t)ctx->N : 1); }
-    u64 *block(int ch, int b) const { return ptr(ch) + (size_t)b * unit(); }
-};
-
 static thread_local std::string g_err;
-static int set_err(int code, const std::string &m) {
+int set_err(int code, const std::string &m) {
     g_err = m;
     return code;
 }
 extern "C" const char *cnhe_last_error(void) { return g_err.c_str(); }
-extern "C" const char *cnhe_version(void) { return "cnhe-b200 0.1 (sm_100a)"; }
-
-#define API_BEGIN(CTX)                                                                                                 \
-    if (!(CTX)) return set_err(CNHE_ERR_INVALID, "null context");                                                      \
-    Context &c = *(CTX)->c;                                                                                            \
-    try {                                                                                                              \
-        std::lock_guard<std::recursive_mutex> lock(c.mu);                                                              \
-        CNHE_CUDA(cudaSetDevice(c.device));                                                                            \
-        c.set_channel(0);                                                                                              \
-        ws_release_all(c);
-#define API_END                                                                                                        \
-    }                                                                                                                  \
-    catch (const Error &e) { return set_err(e.code, e.what()); }                                                      \
-    catch (const std::exception &e) { return set_err(CNHE_ERR_INVALID, e.what()); }                                   \
-    return CNHE_OK;
-static void fail(const char *m) { throw Error(CNHE_ERR_INVALID, m); }
+extern "C" const char *cnhe_version(void) { return "cnhe-b200 0.2 (sm_100a)"; }
 
 // ---------------------------------------------------------------------------------------------------- context & keys
 extern "C" int cnhe_context_create_custom(const uint64_t *plain_primes, int P, uint32_t N, const uint64_t *coeff, int k, int dbc_relin,
@@ -140,6 +101,7 @@ extern "C" int cnhe_context_set_option(cnhe_ctx *h, const char *name, int64_t va
     } else if (n == "trace_noise") {
         c.trace_noise = value != 0;
         c.trace.clear();
+        if (!c.trace_noise) c.budget_of.clear();
     } else if (n == "chunk") {
         if (value < 1 || value > 4096) fail("chunk must be in [1,4096]");
         c.chunk = (int)value;
@@ -176,11 +138,10 @@ extern "C" int cnhe_trace_read(cnhe_ctx *h, int32_t *out, size_t cap_records, si
     if (n_records) *n_records = c.trace.size();
     if (out) {
         const size_t n = std::min(cap_records, c.trace.size());
-        for (size_t i = 0; i < n; i++) {
-            out[4 * i] = c.trace[i].kind; out[4 * i + 1] = c.trace[i].channel; out[4 * i + 2] = c.trace[i].n; out[4 * i + 3] = c.trace[i].budget;
-        }
+        static_assert(sizeof(Context::TraceRec) == 8 * sizeof(int32_t), "trace record layout");
+        memcpy(out, c.trace.data(), n * sizeof(Context::TraceRec));
     }
-    if (clear) c.trace.clear();
+    if (clear) { c.trace.clear(); }
     API_END
 }
 extern "C" int cnhe_keys_set_seed(cnhe_ctx *h, int channel, uint64_t seed) {
@@ -341,7 +302,7 @@ extern "C" int cnhe_raw_elapsed_ms(cnhe_ctx *h, float *ms) {
 }
 
 // ---------------------------------------------------------------------------------------------------- vector helpers
-static cnhe_vec *new_vec(Context &c, uint64_t dim, double scale, int format, bool enc, int blocks) {
+cnhe_vec *new_vec(Context &c, uint64_t dim, double scale, int format, bool enc, int blocks) {
     cnhe_vec *v = new cnhe_vec();
     v->ctx = &c;
     v->dim = dim;
@@ -353,14 +314,14 @@ static cnhe_vec *new_vec(Context &c, uint64_t dim, double scale, int format, boo
     v->off.assign(c.P, 0);
     return v;
 }
-static void alloc_channels(cnhe_vec *v) {
+void alloc_channels(cnhe_vec *v) {
     for (int ch = 0; ch < v->ctx->P; ch++) {
         v->ctx->set_channel(ch);
         v->buf[ch] = v->ctx->alloc((size_t)v->blocks * v->unit());
     }
 }
 static cnhe_vec *alias_of(const cnhe_vec *a) { return new cnhe_vec(*a); } // shares the reference-counted buffers
-static void same_ctx(Context &c, const cnhe_vec *v) {
+void same_ctx(Context &c, const cnhe_vec *v) {
     if (!v) fail("null vector");
     if (v->ctx != &c) fail("vector belongs to another context");
 }
@@ -401,13 +362,21 @@ static void join_values(Context &c, const std::vector<std::vector<u64>> &split, 
     }
 }
 
+static cnhe_vec *make_vector_split(Context &c, const std::vector<std::vector<u64>> &split, const double *v, uint64_t dim, double scale, int format,
+                                   bool encrypt);
 static cnhe_vec *make_vector(Context &c, const double *v, uint64_t dim, double scale, int format, bool encrypt) {
     if (!v && dim) fail("null values");
     if (format != CNHE_DENSE && format != CNHE_SPARSE) fail("bad format");
     if (scale == 0) scale = 1; // AtomicSealBfvVector.cs:1120
-    const size_t N = c.N;
     std::vector<std::vector<u64>> split;
     split_values(c, v, dim, scale, split);
+    return make_vector_split(c, split, v, dim, scale, format, encrypt);
+}
+// `split`: per plaintext modulus the residues of the (already scaled and rounded) values; `v` (may be null) only feeds the
+// all-slots-equal shortcut of plain dense vectors
+static cnhe_vec *make_vector_split(Context &c, const std::vector<std::vector<u64>> &split, const double *v, uint64_t dim, double scale, int format,
+                                   bool encrypt) {
+    const size_t N = c.N;
     const int blocks = format == CNHE_DENSE ? (int)((dim + N - 1) / N) : (int)dim;
     if (blocks < 1) fail("empty vector");
     cnhe_vec *out = new_vec(c, dim, scale, format, encrypt, blocks);
@@ -443,7 +412,7 @@ static cnhe_vec *make_vector(Context &c, const double *v, uint64_t dim, double s
         }
         c.sync(); // host staging buffers go out of scope
     }
-    if (!encrypt && format == CNHE_DENSE && dim % N == 0) { // every slot equal => every plaintext is the constant polynomial
+    if (v && !encrypt && format == CNHE_DENSE && dim % N == 0) { // every slot equal => every plaintext is the constant polynomial
         bool all_eq = true;
         for (uint64_t j = 1; j < dim && all_eq; j++) all_eq = v[j] == v[0];
         if (all_eq) {
@@ -457,6 +426,21 @@ static cnhe_vec *make_vector(Context &c, const double *v, uint64_t dim, double s
 extern "C" int cnhe_vec_encrypt(cnhe_ctx *h, const double *v, uint64_t dim, double scale, int format, cnhe_vec **out) {
     API_BEGIN(h)
     *out = make_vector(c, v, dim, scale, format, true);
+    API_END
+}
+// BigInteger entry points of the factory ("HE Wrapper/IFactory.cs:29,43" -> EncryptedSealBfvVector(IEnumerable<BigInteger>, ...),
+// "EncryptedSealBfvVector.cs:188-199"): the host reduces each big integer modulo every plaintext prime (SplitBigNumbers, ":367-379")
+extern "C" int cnhe_vec_from_residues(cnhe_ctx *h, const uint64_t *residues, uint64_t dim, double scale, int format, int encrypt, cnhe_vec **out) {
+    API_BEGIN(h)
+    if (!residues || !out || dim < 1) fail("bad arguments");
+    if (format != CNHE_DENSE && format != CNHE_SPARSE) fail("bad format");
+    std::vector<std::vector<u64>> split(c.P, std::vector<u64>(dim));
+    for (int ch = 0; ch < c.P; ch++)
+        for (uint64_t j = 0; j < dim; j++) {
+            split[ch][j] = residues[(size_t)ch * dim + j];
+            if (split[ch][j] >= c.t[ch]) fail("residue not reduced modulo its plaintext prime");
+        }
+    *out = make_vector_split(c, split, nullptr, dim, scale == 0 ? 1 : scale, format, encrypt != 0);
     API_END
 }
 extern "C" int cnhe_vec_plain(cnhe_ctx *h, const double *v, uint64_t dim, double scale, int format, cnhe_vec **out) {
@@ -533,6 +517,20 @@ extern "C" int cnhe_vec_decrypt(cnhe_ctx *h, const cnhe_vec *v, double *out, uin
         decrypt_channel(c, v, ch, split[ch]);
     }
     join_values(c, split, v->dim, v->scale, out);
+    API_END
+}
+// DecryptFullPrecision ("EncryptedSealBfvVector.cs:343-348"): the residues of every channel, for the caller's BigInteger CRT join
+// (JoinSplitNumbers, ":397-411"); out is [P][dim]
+extern "C" int cnhe_vec_decrypt_residues(cnhe_ctx *h, const cnhe_vec *v, uint64_t *out, uint64_t cap) {
+    API_BEGIN(h)
+    same_ctx(c, v);
+    if (!out || cap < v->dim * (uint64_t)c.P) fail("destination too small");
+    for (int ch = 0; ch < c.P; ch++) {
+        c.set_channel(ch);
+        std::vector<u64> r;
+        decrypt_channel(c, v, ch, r);
+        memcpy(out + (size_t)ch * v->dim, r.data(), v->dim * 8);
+    }
     API_END
 }
 extern "C" int cnhe_vecs_decrypt(cnhe_ctx *h, const cnhe_vec *const *vecs, int n, double *out, uint64_t dim) {
@@ -725,15 +723,28 @@ extern "C" int cnhe_noise_budget(cnhe_ctx *h, const cnhe_vec *v, int channel, in
     API_END
 }
 
+static double log2_centred(u64 v, u64 t) { // log2 |v| of a residue mod t read as a centred integer
+    const double d = v > t / 2 ? (double)(t - v) : (double)v;
+    return d > 0 ? std::log2(d) : 0;
+}
 // evaluator.Add/Sub/AddMany launches that also feed the operation counters / noise trace (OperationsCount, CryptoTracker)
 static void do_add(Context &c, int ch, const u64 *a, const u64 *b, u64 *out, size_t words, int sub) {
     c.check(launch_ct_add(a, b, out, words, c.k, c.logN, c.d_bc, sub, c.stream), sub ? "ct_sub" : "ct_add");
-    c.note(sub ? Context::OP_SUB : Context::OP_ADD, ch, (int)(words / c.ct_words()), out);
+    c.note(sub ? Context::OP_SUB : Context::OP_ADD, ch, (int)(words / c.ct_words()), out, a, b);
 }
-static void do_add_many(Context &c, int ch, const u64 *const *d_ptrs, int n_in, u64 *out) {
-    c.check(launch_ct_add_many(d_ptrs, n_in, out, c.ct_words(), c.k, c.logN, c.d_bc, c.stream), "ct_add_many");
+static void do_add_many(Context &c, int ch, const std::vector<const u64 *> &terms, u64 *out) {
+    const int n_in = (int)terms.size();
+    c.check(launch_ct_add_many(upload_ptrs(c, terms), n_in, out, c.ct_words(), c.k, c.logN, c.d_bc, c.stream), "ct_add_many");
     c.op_count[Context::OP_ADD_MANY_ITEMS] += (uint64_t)n_in;
-    c.note(Context::OP_ADD_MANY, ch, 1, out);
+    double aux = 0; // tracing: log2 of the root-sum-square of the items' noise peaks 2^-(budget+1), i.e. the model's prediction input
+    if (c.trace_noise) {
+        double ss = 0;
+        bool all = true;
+        for (const u64 *t : terms) { const int b = c.known_budget(t); if (b < 0) { all = false; break; } ss += std::exp2(-2.0 * (b + 1)); }
+        aux = all && ss > 0 ? 0.5 * std::log2(ss) : 0;
+    }
+    c.note(Context::OP_ADD_MANY, ch, 1, out, terms.empty() ? nullptr : terms[0], nullptr, aux);
+    if (c.trace_noise && !c.trace.empty()) c.trace.back().n = n_in;
 }
 
 // ---------------------------------------------------------------------------------------------------- IVector operations
@@ -762,7 +773,7 @@ static cnhe_vec *addsub(Context &c, const cnhe_vec *a, const cnhe_vec *b, bool s
             c.check(launch_ct_add_plain(e->ptr(ch), o->ptr(ch), e->blocks, 2, p->ptr(ch), dense ? c.N : 1, dense ? (int)c.N : 1, c.k, c.logN, c.d_bc,
                                         c.ch[ch].pc, sub, c.stream),
                     "ct_add_plain");
-            c.note(sub ? Context::OP_SUB_PLAIN : Context::OP_ADD_PLAIN, ch, e->blocks, o->ptr(ch));
+            c.note(sub ? Context::OP_SUB_PLAIN : Context::OP_ADD_PLAIN, ch, e->blocks, o->ptr(ch), e->ptr(ch));
         }
     }
     return o;
@@ -801,13 +812,13 @@ static cnhe_vec *mul_sparse_dim_one(Context &c, const cnhe_vec *self, const cnhe
             u64 *d = c.ws_alloc(sc.size());
             CNHE_CUDA(cudaMemcpyAsync(d, sc.data(), sc.size() * 8, cudaMemcpyHostToDevice, c.stream));
             c.check(launch_ct_scale(self->ptr(ch), o->ptr(ch), self->blocks, 2, d, c.k, c.logN, c.d_bc, c.ch[ch].pc, c.stream), "ct_scale");
-            c.note(Context::OP_MULTIPLY_SCALAR, ch, self->blocks, o->ptr(ch));
+            c.note(Context::OP_MULTIPLY_SCALAR, ch, self->blocks, o->ptr(ch), self->ptr(ch), nullptr, log2_centred(sc[0], c.t[ch]));
             c.sync();
         } else { // plain blocks times the single ciphertext of s
             if (self->format != CNHE_DENSE) fail("unsupported plain format");
             u64 *rep = c.ws_alloc((size_t)self->blocks * c.ct_words());
             for (int b = 0; b < self->blocks; b++)
-                CNHE_CUDA(cudaMemcpyAsync(rep + (size_t)b * c.ct_words(), s->block(ch, 0), c.ct_words() * 8, cudaMemcpyDeviceToDevice, c.stream));
+                { CNHE_CUDA(cudaMemcpyAsync(rep + (size_t)b * c.ct_words(), s->block(ch, 0), c.ct_words() * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(rep + (size_t)b * c.ct_words(), s->block(ch, 0)); }
             op_multiply_plain_dense(c, ch, rep, self->blocks, self->ptr(ch), true, o->ptr(ch));
         }
     }
@@ -834,7 +845,7 @@ static cnhe_vec *pointwise_multiply(Context &c, const cnhe_vec *a, const cnhe_ve
             for (u64 s : p->scalars[ch])
                 if (s == 0) fail("plain cannot be zero (the result would be a transparent ciphertext)");
             c.check(launch_ct_scale(e->ptr(ch), o->ptr(ch), e->blocks, 2, p->ptr(ch), c.k, c.logN, c.d_bc, c.ch[ch].pc, c.stream), "ct_scale");
-            c.note(Context::OP_MULTIPLY_SCALAR, ch, e->blocks, o->ptr(ch));
+            c.note(Context::OP_MULTIPLY_SCALAR, ch, e->blocks, o->ptr(ch), e->ptr(ch), nullptr, log2_centred(p->scalars[ch][0], c.t[ch]));
         }
     }
     return guard.release();
@@ -864,9 +875,9 @@ static cnhe_vec *sum_all_slots(Context &c, const cnhe_vec *a, uint64_t length, i
         u64 *sum = o->ptr(ch);
         if (a->blocks > 1) { // AddMany over the blocks
             std::vector<const u64 *> ptrs = block_ptrs(a, ch);
-            do_add_many(c, ch, upload_ptrs(c, ptrs), a->blocks, sum);
+            do_add_many(c, ch, ptrs, sum);
         } else {
-            CNHE_CUDA(cudaMemcpyAsync(sum, a->ptr(ch), ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+            CNHE_CUDA(cudaMemcpyAsync(sum, a->ptr(ch), ctw * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(sum, a->ptr(ch));
         }
         u64 *tmp = c.ws_alloc(ctw);
         if (len >= N / 2) {
@@ -939,7 +950,7 @@ extern "C" int cnhe_vec_duplicate(cnhe_ctx *h, const cnhe_vec *a, uint64_t count
     for (int ch = 0; ch < c.P; ch++) {
         c.set_channel(ch);
         u64 *res = o->ptr(ch), *rotator = c.ws_alloc(ctw), *tmp = c.ws_alloc(ctw);
-        CNHE_CUDA(cudaMemcpyAsync(res, a->ptr(ch), ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+        CNHE_CUDA(cudaMemcpyAsync(res, a->ptr(ch), ctw * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(res, a->ptr(ch));
         const u64 *rot_src = a->ptr(ch);
         bool column_rotated = false;
         for (uint64_t i = 1; i < count; i++) {
@@ -990,7 +1001,7 @@ extern "C" int cnhe_vec_permute(cnhe_ctx *h, const cnhe_vec *a, const cnhe_vec *
             if (!selections[i]) continue;
             op_multiply_plain_dense(c, ch, a->ptr(ch), 1, selections[i]->ptr(ch), false, t);
             op_rotate_rows(c, ch, t, 1, shifts[i], r);
-            if (!have) CNHE_CUDA(cudaMemcpyAsync(o->ptr(ch), r, ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+            if (!have) { CNHE_CUDA(cudaMemcpyAsync(o->ptr(ch), r, ctw * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(o->ptr(ch), r); }
             else do_add(c, ch, o->ptr(ch), r, o->ptr(ch), ctw, 0);
             have = true;
         }
@@ -1008,7 +1019,7 @@ extern "C" int cnhe_vecs_generate_sparse_of_array(cnhe_ctx *h, const cnhe_vec *c
     for (int ch = 0; ch < c.P; ch++) {
         c.set_channel(ch);
         for (int i = 0; i < n; i++)
-            CNHE_CUDA(cudaMemcpyAsync(o->block(ch, i), vecs[i]->block(ch, 0), c.ct_words() * 8, cudaMemcpyDeviceToDevice, c.stream));
+            { CNHE_CUDA(cudaMemcpyAsync(o->block(ch, i), vecs[i]->block(ch, 0), c.ct_words() * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(o->block(ch, i), vecs[i]->block(ch, 0)); }
     }
     *out = o;
     API_END
@@ -1040,7 +1051,7 @@ static void interleave_channel(Context &c, int ch, const std::vector<const cnhe_
         u64 *v = c.ws_alloc(ctw);
         const u64 *src = vecs[kk]->block(ch, 0);
         if (in_block == 0) {
-            CNHE_CUDA(cudaMemcpyAsync(v, src, ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+            CNHE_CUDA(cudaMemcpyAsync(v, src, ctw * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(v, src);
             lower[start_block].push_back(v);
         } else if (in_block + abs_shift < half) {
             op_rotate_rows(c, ch, src, 1, -(int)this_shift, v);
@@ -1052,7 +1063,7 @@ static void interleave_channel(Context &c, int ch, const std::vector<const cnhe_
             } else { // straddles the upper half of this block and the lower half of the next
                 const int upper_part = (in_block + abs_shift) - block_size;
                 u64 *v2 = c.ws_alloc(ctw);
-                CNHE_CUDA(cudaMemcpyAsync(v2, v, ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+                CNHE_CUDA(cudaMemcpyAsync(v2, v, ctw * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(v2, v);
                 op_multiply_plain_dense(c, ch, v, 1, ones_plain(upper_part), false, v);
                 do_add(c, ch, v2, v, v2, ctw, 1);
                 upper[start_block].push_back(v2);
@@ -1064,7 +1075,7 @@ static void interleave_channel(Context &c, int ch, const std::vector<const cnhe_
             const int upper_part = (in_block + abs_shift) - half;
             if (upper_part > 0) {
                 u64 *v2 = c.ws_alloc(ctw);
-                CNHE_CUDA(cudaMemcpyAsync(v2, v, ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+                CNHE_CUDA(cudaMemcpyAsync(v2, v, ctw * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(v2, v);
                 op_multiply_plain_dense(c, ch, v, 1, ones_plain(upper_part), false, v);
                 do_add(c, ch, v2, v, v2, ctw, 1);
                 upper[start_block].push_back(v);
@@ -1077,10 +1088,10 @@ static void interleave_channel(Context &c, int ch, const std::vector<const cnhe_
     for (int i = 0; i < out_blocks; i++) {
         u64 *res = out + (size_t)i * ctw;
         if (lower[i].empty()) fail("an output block received no vector");
-        do_add_many(c, ch, upload_ptrs(c, lower[i]), (int)lower[i].size(), res);
+        do_add_many(c, ch, lower[i], res);
         if (!upper[i].empty()) {
             u64 *t = c.ws_alloc(ctw);
-            do_add_many(c, ch, upload_ptrs(c, upper[i]), (int)upper[i].size(), t);
+            do_add_many(c, ch, upper[i], t);
             op_rotate_columns(c, ch, t, 1, t);
             do_add(c, ch, res, t, res, ctw, 0);
         }
@@ -1301,7 +1312,10 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
             c.op_count[Context::OP_MULTIPLY_SCALAR] += taps * bl;
             c.op_count[Context::OP_ADD_MANY_ITEMS] += taps * bl;
             if (bias) c.op_count[Context::OP_ADD_PLAIN] += (uint64_t)M * bl;
-            c.note(Context::OP_ADD_MANY, ch, M * bl, big[ch]->p);
+            double ss = 0; // output 0: root-sum-square of its centred weights (the noise gain of the scalar MAC under independent inputs)
+            for (int kk = 0; kk < K; kk++)
+                if (!gather || gather[kk] >= 0) ss += wdh[kk] * wdh[kk];
+            c.note(Context::OP_ADD_MANY, ch, M * bl, big[ch]->p, in[gather ? std::max(gather[0], 0) : 0]->block(ch, 0), nullptr, ss > 0 ? 0.5 * std::log2(ss) : 0);
         }
         if (bias && !const_bias) // generic AddPlain per output
             for (int m = 0; m < M; m++) {
@@ -1354,14 +1368,14 @@ extern "C" int cnhe_mat_mul_colmajor_sparse(cnhe_ctx *h, const cnhe_vec *const *
                 for (int kk = 0; kk < K; kk++) {
                     u64 *rep = c.ws_alloc((size_t)bl * ctw);
                     for (int i = 0; i < bl; i++)
-                        CNHE_CUDA(cudaMemcpyAsync(rep + (size_t)i * ctw, sparse->block(ch, kk), ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+                        { CNHE_CUDA(cudaMemcpyAsync(rep + (size_t)i * ctw, sparse->block(ch, kk), ctw * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(rep + (size_t)i * ctw, sparse->block(ch, kk)); }
                     op_multiply_plain_dense(c, ch, rep, bl, cols[kk]->ptr(ch), true, prod + (size_t)kk * bl * ctw);
                 }
             }
             for (int i = 0; i < bl; i++) {
                 std::vector<const u64 *> terms;
                 for (int kk = 0; kk < K; kk++) terms.push_back(prod + ((size_t)kk * bl + i) * ctw);
-                do_add_many(c, ch, upload_ptrs(c, terms), K, o->block(ch, i));
+                do_add_many(c, ch, terms, o->block(ch, i));
             }
             c.sync();
         }
@@ -1433,7 +1447,7 @@ extern "C" int cnhe_mat_mul_rowmajor(cnhe_ctx *h, const cnhe_vec *const *rows, i
                 std::vector<const u64 *> terms;
                 if (!first) terms.push_back(o->ptr(ch));
                 for (int i = 0; i < m; i++) terms.push_back(prod + (size_t)i * ctw);
-                do_add_many(c, ch, upload_ptrs(c, terms), (int)terms.size(), o->ptr(ch));
+                do_add_many(c, ch, terms, o->ptr(ch));
                 c.sync();
             }
             first = false;

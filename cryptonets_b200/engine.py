@@ -90,12 +90,24 @@ class Vec:
 class Engine:
     """One cnhe_ctx: parameters, device tables and keys for P plaintext moduli (== EncryptedSealBfvFactory)."""
 
-    def __init__(self, plain_primes, N, dbc_relin=10, dbc_galois=20, small_modulus_count=-1, device=0, coeff_moduli=None):
+    def __init__(self, plain_primes, N=0, dbc_relin=10, dbc_galois=20, small_modulus_count=-1, device=0, coeff_moduli=None, archive=None):
+        """archive: bytes of a key archive (cnhe_keys_save / EncryptedSealBfvEnvironment.Save): parameters and keys come from it."""
         self.L = _lib.lib()
         self._live = weakref.WeakSet()
-        pp = _u64(plain_primes)
         h = C.c_void_p()
-        if coeff_moduli is None:
+        if archive is not None:
+            buf = (C.c_ubyte * len(archive)).from_buffer_copy(archive)
+            check(self.L.cnhe_context_load(buf, len(archive), device, C.byref(h)))
+            self.h = h
+            P = C.c_int()
+            check(self.L.cnhe_context_info(self.h, None, None, C.byref(P), None, None, None))
+            pp = np.zeros(P.value, np.uint64)
+            check(self.L.cnhe_context_plain_moduli(self.h, _p(pp)))
+        else:
+            pp = _u64(plain_primes)
+        if archive is not None:
+            pass
+        elif coeff_moduli is None:
             check(self.L.cnhe_context_create(_p(pp), len(pp), N, dbc_relin, dbc_galois, small_modulus_count, device, C.byref(h)))
         else:
             cm = _u64(coeff_moduli)
@@ -161,13 +173,37 @@ class Engine:
         self.set_option("trace_noise", 1 if on else 0)
 
     def trace_read(self, clear=True):
-        """[(operation name, channel, count, noise budget of the first output or -1)] since the trace was last cleared."""
+        """[(operation name, channel, count, budget of the first output, budgets of its first two inputs (-1 unknown), aux)] since the trace
+        was last cleared (see cnhe_trace_read in include/cnhe.h)."""
         n = C.c_size_t()
         check(self.L.cnhe_trace_read(self.h, None, 0, C.byref(n), 0))
-        a = np.zeros((max(n.value, 1), 4), np.int32)
+        a = np.zeros((max(n.value, 1), 8), np.int32)
         check(self.L.cnhe_trace_read(self.h, a.ctypes.data_as(C.POINTER(C.c_int32)), n.value, C.byref(n), int(clear)))
         self.op_counts()
-        return [(Engine.OP_NAMES[k], int(ch), int(cnt), int(b)) for k, ch, cnt, b in a[:n.value]]
+        return [(Engine.OP_NAMES[r[0]], int(r[1]), int(r[2]), int(r[3]), int(r[4]), int(r[5]), r[6] / 1000.0) for r in a[:n.value]]
+
+    def save_keys(self, with_private_keys=False):
+        """The key archive of EncryptedSealBfvEnvironment.Save as bytes."""
+        n = C.c_size_t()
+        check(self.L.cnhe_keys_save(self.h, int(with_private_keys), None, 0, C.byref(n)))
+        buf = (C.c_ubyte * n.value)()
+        check(self.L.cnhe_keys_save(self.h, int(with_private_keys), buf, n.value, C.byref(n)))
+        return bytes(buf)
+
+    def write_vector(self, vec):
+        """EncryptedSealBfvVector.Write: the text form of one vector."""
+        n = C.c_size_t()
+        check(self.L.cnhe_vec_write(self.h, vec.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        check(self.L.cnhe_vec_write(self.h, vec.h, buf, n.value, C.byref(n)))
+        return buf.raw[: n.value].decode("ascii")
+
+    def read_vector(self, text):
+        """EncryptedSealBfvVector.Read; returns (Vec, characters consumed)."""
+        raw = text.encode("ascii") if isinstance(text, str) else text
+        out, used = VECP(), C.c_size_t()
+        check(self.L.cnhe_vec_read(self.h, raw, len(raw), C.byref(out), C.byref(used)))
+        return Vec(self, out), used.value
 
     def galois_elts(self):
         a = np.zeros(self.n_galois, np.uint64)
@@ -217,6 +253,18 @@ class Engine:
         out = np.zeros(vec.dim, np.float64)
         check(self.L.cnhe_vec_decrypt(self.h, vec.h, out.ctypes.data_as(DBLP), out.size))
         return out
+
+    def decrypt_residues(self, vec):
+        """Per-channel residues [P][dim] of the decryption (DecryptFullPrecision joins them with big integers)."""
+        out = np.zeros((self.P, vec.dim), np.uint64)
+        check(self.L.cnhe_vec_decrypt_residues(self.h, vec.h, _p(out), out.size))
+        return out
+
+    def from_residues(self, residues, scale=1.0, fmt=DENSE, encrypt=True):
+        r = _u64(residues).reshape(self.P, -1)
+        out = VECP()
+        check(self.L.cnhe_vec_from_residues(self.h, _p(r), r.shape[1], float(scale), fmt, int(encrypt), C.byref(out)))
+        return Vec(self, out)
 
     def dispose_many(self, vecs):
         """Release a list of Vec handles with one ABI call."""

@@ -44,6 +44,10 @@ class B200BfvVector:
             self.vec.dispose()
             self.vec = None
 
+    def Write(self, writer):
+        """IVector.Write(StreamWriter) (`EncryptedSealBfvVector.cs:428-437`)."""
+        writer.write(self.eng.write_vector(self.vec))
+
     def RegisterScale(self, scale):
         self.vec.register_scale(scale)
 
@@ -52,6 +56,18 @@ class B200BfvVector:
 
     def Decrypt(self, env=None):
         return self.eng.decrypt(self.vec)
+
+    def DecryptFullPrecision(self, env=None):
+        """IVector.DecryptFullPrecision (`EncryptedSealBfvVector.cs:343-348,397-411`): exact integers (Python ints stand in for BigInteger),
+        the CRT join of the per-modulus residues, centred when the vector is signed; NOT divided by Scale (the reference does not)."""
+        f, res = self.factory, self.eng.decrypt_residues(self.vec)
+        out = []
+        for j in range(res.shape[1]):
+            x = sum(int(c) * int(res[i, j]) for i, c in enumerate(f.preComputedCoefficients)) % f.bigFactor
+            if self.IsSigned and x * 2 > f.bigFactor:
+                x -= f.bigFactor
+            out.append(x)
+        return out
 
     def Add(self, v, env=None):
         return self._wrap(self.eng.add(self.vec, v.vec))
@@ -100,6 +116,14 @@ class B200BfvMatrix:
     BlockSize = property(lambda s: s.eng.N)
     IsEncrypted = property(lambda s: all(v.IsEncrypted for v in s.vectors))
     Data = property(lambda s: s.vectors)
+
+    def Write(self, writer):
+        """IMatrix.Write(StreamWriter) (`EncryptedSealBfvMatrix.cs:199-208`)."""
+        nl = "\r\n"
+        writer.write("<Start LargeEncryptedMatrix>" + nl + EMatrixFormat(self.Format).name + nl + str(len(self.vectors)) + nl)
+        for v in self.vectors:
+            v.Write(writer)
+        writer.write("<End LargeEncryptedMatrix>" + nl)
 
     def Dispose(self):
         if self.vectors is not None and not self.DataDisposedExternaly:
@@ -205,6 +229,18 @@ class B200BfvMatrix:
         return B200BfvVector(self.factory, self.eng.interleave([v.vec for v in self.vectors], shift))
 
 
+def _read_block(reader, end_marker):
+    """lines of a text stream up to and including the line `end_marker`"""
+    out = []
+    while True:
+        line = reader.readline()
+        if not line:
+            raise Exception("Bad stream format.")
+        out.append(line)
+        if line.rstrip("\r\n") == end_marker:
+            return "".join(out)
+
+
 class B200BfvFactory:
     """IFactory (`HE Wrapper/IFactory.cs:20-130`); constructor arguments of EncryptedSealBfvFactory (`:247-260`)."""
 
@@ -215,11 +251,16 @@ class B200BfvFactory:
                  device=0, generate_keys=True):
         """seed=None (default): keys and encryption randomness from the OS CSPRNG, as SEAL's KeyGenerator/Encryptor give the reference.
         An integer seed selects the deterministic sampler shared with the CPU oracle: parity tests only."""
-        if primes is None:
-            primes, n = [40961, 65537, 114689, 147457, 188417], 4096  # IFactory.cs:247-253
-        self.engine = Engine(primes, n, DecompositionBitCount, GaloisDecompositionBitCount, SmallModulusCount, device)
-        if generate_keys:
-            self.engine.keygen(seed)
+        if isinstance(primes, (str, bytes, bytearray)):  # EncryptedSealBfvFactory(fileName) (IFactory.cs:262-265): parameters and keys from a key archive
+            data = open(primes, "rb").read() if isinstance(primes, str) else bytes(primes)
+            self.engine = Engine(None, archive=data, device=device)
+            primes = self.engine.primes
+        else:
+            if primes is None:
+                primes, n = [40961, 65537, 114689, 147457, 188417], 4096  # IFactory.cs:247-253
+            self.engine = Engine(primes, n, DecompositionBitCount, GaloisDecompositionBitCount, SmallModulusCount, device)
+            if generate_keys:
+                self.engine.keygen(seed)
         self._env = B200BfvEnvironment(self)
         big = 1
         for p in primes:
@@ -235,10 +276,19 @@ class B200BfvFactory:
     def FreeComputationEnv(self, env):
         pass
 
-    def GetPlainVector(self, v, fmt, scale):
+    def _big(self, v, fmt, encrypt):  # the IEnumerable<BigInteger> overloads (IFactory.cs:29,43): SplitBigNumbers on exact integers
+        vals = [int(x) % self.bigFactor for x in v]
+        res = np.array([[x % int(p) for x in vals] for p in self.engine.primes], dtype=np.uint64)
+        return B200BfvVector(self, self.engine.from_residues(res, 1.0, int(fmt), encrypt))
+
+    def GetPlainVector(self, v, fmt, scale=None):
+        if scale is None:
+            return self._big(v, fmt, False)
         return B200BfvVector(self, self.engine.plain(np.asarray(v, dtype=np.float64), scale, int(fmt)))
 
-    def GetEncryptedVector(self, v, fmt, scale):
+    def GetEncryptedVector(self, v, fmt, scale=None):
+        if scale is None:
+            return self._big(v, fmt, True)
         return B200BfvVector(self, self.engine.encrypt(np.asarray(v, dtype=np.float64), scale, int(fmt)))
 
     def CopyVector(self, v):
@@ -259,6 +309,33 @@ class B200BfvFactory:
 
     def GetMatrix(self, vectors, fmt, CopyVectors=True):
         return B200BfvMatrix(self, vectors, fmt, CopyVectors=CopyVectors)
+
+    # ---- wire formats (IFactory.cs:474-495; SEAL streams unpinned, see csrc/wire.cu)
+    def Save(self, target, withPrivateKeys=False):
+        """IFactory.Save(stream | fileName, withPrivateKeys): the ZIP key archive."""
+        data = self.engine.save_keys(withPrivateKeys)
+        if isinstance(target, str):
+            with open(target, "wb") as f:
+                f.write(data)
+        else:
+            target.write(data)
+        return target
+
+    def LoadVector(self, reader):
+        """IFactory.LoadVector(StreamReader): `reader` is a text stream positioned at "<Start LargeEncryptedVector>"."""
+        text = _read_block(reader, "<End LargeEncryptedVector>")
+        vec, _ = self.engine.read_vector(text)
+        return B200BfvVector(self, vec)
+
+    def LoadMatrix(self, reader):  # EncryptedSealBfvMatrix.Read (EncryptedSealBfvMatrix.cs:182-197)
+        if reader.readline().rstrip("\r\n") != "<Start LargeEncryptedMatrix>":
+            raise Exception("Bad stream format.")
+        fmt = EMatrixFormat[reader.readline().strip()]
+        n = int(reader.readline())
+        vecs = [self.LoadVector(reader) for _ in range(n)]
+        if reader.readline().rstrip("\r\n") != "<End LargeEncryptedMatrix>":
+            raise Exception("Bad stream format.")
+        return B200BfvMatrix(self, vecs, fmt, CopyVectors=False)
 
     def GetValueFromString(self, s):  # IFactory.cs:395-403
         f = [int(x) for x in s.split(",")]

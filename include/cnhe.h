@@ -87,9 +87,27 @@ int cnhe_keys_set_seed(cnhe_ctx *, int channel, uint64_t seed); /* TESTS ONLY: l
 int cnhe_op_counts(cnhe_ctx *, uint64_t *out, int cap, int reset);
 const char *cnhe_op_name(int kind);
 /* CryptoTracker.TestBudget ("HE Wrapper/CryptoTracker.cs:41-52") as a trace: with option "trace_noise" on, every evaluator-level
- * operation appends (kind, channel, count, invariant noise budget of its first output ciphertext, -1 when not measured) -- four int32
- * per record.  out may be NULL to query the record count. */
+ * operation appends a record of eight int32: kind, channel, count, invariant noise budget of its first output ciphertext (-1 when not
+ * measured), the budgets its first and second input ciphertexts had when they were last measured (-1 unknown), an operation-specific
+ * auxiliary value in thousandths (log2 |scalar| of a constant multiply, log2 of the root-sum-square weight of a MAC output, log2 of the
+ * root-sum-square input noise of an AddMany) and a reserved word.  out may be NULL to query the record count.  Switching the option off
+ * forgets the per-ciphertext budgets. */
 int cnhe_trace_read(cnhe_ctx *, int32_t *out, size_t cap_records, size_t *n_records, int clear);
+
+/* ---- wire / on-disk formats.  The containers are the reference's; the SEAL 3.2 binary streams inside them are
+ * restated from knowledge of SEAL 3.2.x and are UNPINNED against the real binary (see csrc/wire.cu for every layout).
+ * cnhe_keys_save: EncryptedSealBfvEnvironment.Save ("HE Wrapper/EncryptedSealBfvVector.cs:104-134", IFactory.Save "IFactory.cs:484-495"):
+ *   ZIP archive with one `environmentNNN` entry per plaintext modulus = AtomicSealBfvEncryptedEnvironment.SaveToStream
+ *   ("AtomicSealBfvVector.cs:93-104").  dst may be NULL to query the size.
+ * cnhe_context_load: the factory's file constructor (EncryptedSealBfvFactory(fileName), LoadFromStream "AtomicSealBfvVector.cs:106-131"):
+ *   parameters (N, coefficient moduli, plaintext moduli, decomposition bit counts) and keys come from the archive; a context loaded
+ *   from an archive without secret keys can encrypt and evaluate but not decrypt.
+ * cnhe_vec_write / cnhe_vec_read: EncryptedSealBfvVector.Write / Read (":414-439", "AtomicSealBfvVector.cs:1273-1345"), the text form
+ *   IFactory.LoadVector / LoadMatrix parse ("IFactory.cs:474-483"; a matrix is the reference's three header lines around its vectors). */
+int cnhe_keys_save(cnhe_ctx *, int with_private_keys, uint8_t *dst, size_t cap, size_t *needed);
+int cnhe_context_load(const uint8_t *archive, size_t len, int device, cnhe_ctx **out);
+int cnhe_vec_write(cnhe_ctx *, const cnhe_vec *, char *dst, size_t cap, size_t *needed);
+int cnhe_vec_read(cnhe_ctx *, const char *text, size_t len, cnhe_vec **out, size_t *consumed);
 
 /* ---- vectors: creation, metadata, disposal ---------------------------------------------------------------------- */
 /* IFactory.GetEncryptedVector / GetPlainVector ("HE Wrapper/IFactory.cs:311-328"): round(v*scale), CRT split over the
@@ -97,11 +115,17 @@ int cnhe_trace_read(cnhe_ctx *, int32_t *out, size_t cap_records, size_t *n_reco
  * polynomial per element (sparse) ("AtomicSealBfvVector.cs:1114-1142"), Encryptor.Encrypt (":1202-1216"). */
 int cnhe_vec_encrypt(cnhe_ctx *, const double *v, uint64_t dim, double scale, int format, cnhe_vec **out);
 int cnhe_vec_plain(cnhe_ctx *, const double *v, uint64_t dim, double scale, int format, cnhe_vec **out);
+/* the BigInteger overloads IFactory.GetPlainVector / GetEncryptedVector(IEnumerable<BigInteger>, format) ("IFactory.cs:29,43";
+ * "EncryptedSealBfvVector.cs:188-199"): residues [P][dim], already reduced modulo each plaintext prime by the caller (SplitBigNumbers) */
+int cnhe_vec_from_residues(cnhe_ctx *, const uint64_t *residues, uint64_t dim, double scale, int format, int encrypt, cnhe_vec **out);
 /* batched form of IFactory.GetEncryptedMatrix ("IFactory.cs:353-380"): n dense vectors of `dim` values, v row-major [n][dim] */
 int cnhe_vecs_encrypt(cnhe_ctx *, const double *v, int n, uint64_t dim, double scale, cnhe_vec **out);
 /* IVector.Decrypt ("EncryptedSealBfvVector.cs:332-337,381-395"; "AtomicSealBfvVector.cs:1030-1067") */
 int cnhe_vec_decrypt(cnhe_ctx *, const cnhe_vec *, double *out, uint64_t cap);
 int cnhe_vecs_decrypt(cnhe_ctx *, const cnhe_vec *const *vecs, int n, double *out /*[n][dim]*/, uint64_t dim);
+/* IVector.DecryptFullPrecision ("EncryptedSealBfvVector.cs:343-348"): per-channel residues [P][dim]; the caller joins them with big
+ * integers (JoinSplitNumbers ":397-411") */
+int cnhe_vec_decrypt_residues(cnhe_ctx *, const cnhe_vec *, uint64_t *out, uint64_t cap_words);
 int cnhe_vec_copy(cnhe_ctx *, const cnhe_vec *, cnhe_vec **out); /* IFactory.CopyVector */
 int cnhe_vec_destroy(cnhe_vec *);
 /* Dispose of n vectors in one call (the Dispose loop of EncryptedSealBfvMatrix, EncryptedSealBfvMatrix.cs Dispose); null entries are skipped. */

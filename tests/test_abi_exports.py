@@ -41,3 +41,16 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_py" not in text and "bfv_oracle" not in text and "liboracle" not in text, f
+
+
+def test_csharp_shim_matches_the_header_and_the_reference_interfaces():
+    """integration/B200Native.cs (the shim a maintainer adds next to HE Wrapper/IFactory.cs) cannot be compiled here; its [DllImport]
+    block must at least agree with include/cnhe.h in names, arity and marshalled types, and the three classes must carry every
+    member of IVector / IMatrix / IFactory / IComputationEnvironment."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("check_csharp_bindings", os.path.join(ROOT, "tools", "check_csharp_bindings.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    errors, n = mod.check()
+    assert not errors, errors
+    assert n >= 78

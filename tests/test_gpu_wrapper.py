@@ -212,3 +212,81 @@ def test_pipelined_import_export_and_batched_dispose(F):
     again = eng.import_raw_many(host.data_ptr(), n, 1, eng.N, 3.0)    # slots are reusable after their release
     assert np.array_equal(eng.export_raw_many(again).reshape(-1), words.reshape(-1))
     eng.dispose_many(again)
+
+
+def test_plain_columns_times_encrypted_scalars(F):
+    """DenseMatrixBySparseVectorMultiply, third mode (AtomicSealBfvVector.cs:476-485): plain dense columns x an ENCRYPTED sparse vector --
+    MultiplyPlain(sparse.enc[k], column k) per column, AddMany."""
+    from cryptonets_b200.interfaces import EMatrixFormat, EVectorFormat
+    m = np.array([[1, -2, 3], [4, 5, -6], [7, 8, 9], [-10, 11, 12]], dtype=np.float64)
+    s = np.array([3, -4, 5], dtype=np.float64)
+    pm = F.GetPlainMatrix(m, EMatrixFormat.ColumnMajor, 2)
+    es = F.GetEncryptedVector(s, EVectorFormat.sparse, 3)
+    out = pm.Mul(es)
+    assert out.IsEncrypted and out.Scale == 6 and out.Dim == 4
+    assert np.array_equal(np.asarray(out.Decrypt()), m @ s)
+    # the same product with the roles swapped (encrypted columns x plain scalars) decrypts to the same values
+    em = F.GetEncryptedMatrix(m, EMatrixFormat.ColumnMajor, 2)
+    assert np.array_equal(np.asarray(em.Mul(F.GetPlainVector(s, EVectorFormat.sparse, 3)).Decrypt()), m @ s)
+
+
+def test_permute_with_encrypted_selection_is_rejected_like_seal(F):
+    """Permute's ct x ct branch (AtomicSealBfvVector.cs:1455-1458) multiplies WITHOUT relinearising and then rotates the size-3 product;
+    SEAL 3.2's rotate_rows throws "encrypted size must be 2" on it, and so does the library."""
+    from cryptonets_b200.interfaces import EVectorFormat
+    v = F.GetEncryptedVector(np.arange(1, 11, dtype=np.float64), EVectorFormat.dense, 1)
+    s1 = np.zeros(10)
+    s1[[1, 4]] = 1
+    enc_sel = F.GetEncryptedVector(s1, EVectorFormat.dense, 1)
+    with pytest.raises(Exception, match="encrypted size must be 2"):
+        v.Permute([enc_sel], [1], 5)
+
+
+def test_concurrent_callers(F):
+    """The reference calls the evaluator from up to ThreadCount threads at once (Utils.cs:68-86).  Four host threads hammer one context
+    (serialised by its mutex) while a fifth drives a second context on the same GPU; every result must be exact."""
+    import threading
+    from cryptonets_b200.he import B200BfvFactory
+    from cryptonets_b200.interfaces import EVectorFormat
+    rng = np.random.default_rng(7)
+    data = [rng.integers(-50, 50, 64).astype(np.float64) for _ in range(4)]
+    errors = []
+
+    def worker(i, factory):
+        try:
+            a = data[i]
+            for _ in range(6):
+                e = factory.GetEncryptedVector(a, EVectorFormat.dense, 1)
+                sq = e.PointwiseMultiply(e)
+                tot = sq.Add(e).SumAllSlots()
+                assert np.array_equal(np.asarray(sq.Decrypt()), a * a)
+                assert tot.Decrypt()[0] == float((a * a + a).sum())
+                for x in (e, sq, tot):
+                    x.Dispose()
+        except Exception as ex:  # pragma: no cover
+            errors.append((i, repr(ex)))
+
+    F2 = B200BfvFactory([40961, 65537], 4096, seed=3)
+    try:
+        threads = [threading.Thread(target=worker, args=(i, F)) for i in range(4)] + [threading.Thread(target=worker, args=(0, F2))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    finally:
+        F2.Dispose()
+    assert not errors, errors
+
+
+def test_big_integer_vectors_and_full_precision(F):
+    """IFactory.GetEncryptedVector(IEnumerable<BigInteger>) / IVector.DecryptFullPrecision (IFactory.cs:43, EncryptedSealBfvVector.cs:188-199,
+    343-348): values beyond 2^53 survive exactly (the product of the five default primes is ~2^81)."""
+    from cryptonets_b200.interfaces import EVectorFormat
+    big = [3 * 10 ** 20 + 7, -(2 ** 70) - 12345, 0, 999]
+    e = F.GetEncryptedVector(big, EVectorFormat.dense)
+    assert e.DecryptFullPrecision() == big
+    p = F.GetPlainVector([5, -6, 7, 8], EVectorFormat.dense)
+    prod = e.PointwiseMultiply(p)
+    assert prod.DecryptFullPrecision() == [big[0] * 5, big[1] * -6, 0, 999 * 8]
+    s = F.GetEncryptedVector([2 ** 60, -3], EVectorFormat.sparse)
+    assert s.DecryptFullPrecision() == [2 ** 60, -3]

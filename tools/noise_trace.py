@@ -80,11 +80,10 @@ def run(name, k, mtilde, seed=5, weights="shipped"):
             eng.sync()
             dt = time.time() - t0
             ops = eng.trace_read(clear=True)
-            eng.trace_noise(False)
             budgets = [eng.noise_budget(v.vec, ch, b) for v in ma.vectors for ch in range(eng.P) for b in range(v.vec.blocks)]
             got, want = np.asarray(ma.Decrypt(), dtype=np.float64), np.asarray(mb.Decrypt(), dtype=np.float64)
             equal = bool(got.shape == want.shape and np.allclose(got, want, rtol=1e-9, atol=1e-9))
-            eng.trace_noise(True)
+            eng.trace_read(clear=True)  # decryptions are not evaluator operations
             rec["layers"].append(dict(layer=type(A).__name__, seconds=dt, ops=ops, out_budget_min=int(min(budgets)), out_budget_max=int(max(budgets)),
                                       n_out_ct=len(budgets), equals_raw=equal, mac_gain=mac_gain(A, primes), counts=eng.op_counts(reset=True)))
             print("%-12s k=%d %-24s budget %3d..%3d  == Raw: %s  (%d ops, %.2fs)" % (name, k, type(A).__name__, min(budgets), max(budgets), equal,
