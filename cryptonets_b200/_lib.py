@@ -73,6 +73,7 @@ _SIGS = {
     "cnhe_vecs_generate_sparse_of_array": [C.c_void_p, C.POINTER(VECP), i32, C.POINTER(VECP)],
     "cnhe_mat_mul_colmajor_sparse": [C.c_void_p, C.POINTER(VECP), i32, VECP, C.POINTER(VECP)],
     "cnhe_mat_mul_rowmajor": [C.c_void_p, C.POINTER(VECP), i32, VECP, i32, C.POINTER(VECP)],
+    "cnhe_mat_mul_rowmajor_shard": [C.c_void_p, C.POINTER(VECP), i32, VECP, i32, i32, i32, C.POINTER(VECP)],
     "cnhe_layer_conv_dense": [C.c_void_p, C.POINTER(VECP), i32, C.POINTER(C.c_int32), C.POINTER(VECP), C.POINTER(VECP), i32, i32,
                               C.POINTER(VECP)],
     "cnhe_layer_square": [C.c_void_p, C.POINTER(VECP), i32, C.POINTER(VECP)],

@@ -1277,14 +1277,11 @@ static bool ws_flag(const char *name, bool dflt) {
     if (all) return atoi(all) != 0;
     return dflt;
 }
-static bool ws_enabled_fwd() {
-    static const bool on = ws_flag("CNHE_NTT_WS_FWD", true);
-    return on;
-}
-static bool ws_enabled_inv() {
-    static const bool on = ws_flag("CNHE_NTT_WS_INV", true);
-    return on;
-}
+// Measured on B200 (profiles/r02_ntt_ws_ab.txt): the persistent inverse transform is 20-25 % faster than one CTA per polynomial
+// (0.53-0.60 of the HBM roofline against 0.43-0.49); the persistent forward transform only draws level (0.50 against 0.52, and 12 % slower
+// in its digit-cutting form), so the forward direction keeps the per-polynomial kernel unless CNHE_NTT_WS_FWD=1 asks for the staged one.
+static bool ws_enabled_fwd() { return ws_flag("CNHE_NTT_WS_FWD", false); } // read per launch: tests flip it inside one process
+static bool ws_enabled_inv() { return ws_flag("CNHE_NTT_WS_INV", true); }
 static int sm_count() {
     static int n = [] {
         int dev = 0, v = 148;

@@ -625,7 +625,7 @@ extern "C" int cnhe_vec_import_raw(cnhe_ctx *h, const uint64_t *src, int blocks,
     const size_t words = (size_t)blocks * c.ct_words();
     for (int ch = 0; ch < c.P; ch++) {
         c.set_channel(ch);
-        CNHE_CUDA(cudaMemcpyAsync(o->ptr(ch), src + (size_t)ch * words, words * 8, cudaMemcpyHostToDevice, c.stream));
+        CNHE_CUDA(cudaMemcpyAsync(o->ptr(ch), src + (size_t)ch * words, words * 8, cudaMemcpyDefault, c.stream)); // host or device source
     }
     c.sync();
     *out = o;
@@ -1404,8 +1404,17 @@ static uint64_t sum_slots_batched(Context &c, int ch, u64 *cts, int n, uint64_t 
 // GenerateSparseOfArray, or (ForceDenseFormat) a one-hot mask per row and the sum of all rows.  All rows go through each stage
 // together instead of one DotProduct per row.
 extern "C" int cnhe_mat_mul_rowmajor(cnhe_ctx *h, const cnhe_vec *const *rows, int n_rows, const cnhe_vec *v, int force_dense, cnhe_vec **out) {
+    return cnhe_mat_mul_rowmajor_shard(h, rows, n_rows, v, force_dense, 0, n_rows, out);
+}
+// The same product for a contiguous SLICE of the matrix rows (rows[i] is global row first_row + i of a matrix with total_rows rows):
+// the unit of the intra-inference multi-GPU split (CIFAR's 5488 dense rows over 4 GPUs).  ForceDense: the one-hot masks sit
+// at the global columns, so the partial results of the ranks add up to the full product (the reference sums the masked rows too,
+// EncryptedSealBfvMatrix.cs:92-116); otherwise the output holds this slice's sparse elements only.
+extern "C" int cnhe_mat_mul_rowmajor_shard(cnhe_ctx *h, const cnhe_vec *const *rows, int n_rows, const cnhe_vec *v, int force_dense, int first_row,
+                                           int total_rows, cnhe_vec **out) {
     API_BEGIN(h)
     if (n_rows < 1) fail("empty matrix");
+    if (first_row < 0 || first_row + n_rows > total_rows) fail("row slice out of range");
     same_ctx(c, v);
     if (!v->enc) fail("at least one parameter has to be encrypted");
     if (v->format != CNHE_DENSE) fail("Expecting dense vector format");
@@ -1418,9 +1427,9 @@ extern "C" int cnhe_mat_mul_rowmajor(cnhe_ctx *h, const cnhe_vec *const *rows, i
         if (rows[r]->scale != rows[0]->scale) fail("row scales differ");
     }
     const size_t N = c.N, ctw = c.ct_words();
-    if (force_dense && (size_t)n_rows > N) fail("column out of range");
+    if (force_dense && (size_t)total_rows > N) fail("column out of range");
     const int out_blocks = force_dense ? 1 : n_rows;
-    cnhe_vec *o = new_vec(c, (uint64_t)n_rows, v->scale * rows[0]->scale, force_dense ? CNHE_DENSE : CNHE_SPARSE, true, out_blocks);
+    cnhe_vec *o = new_vec(c, (uint64_t)(force_dense ? total_rows : n_rows), v->scale * rows[0]->scale, force_dense ? CNHE_DENSE : CNHE_SPARSE, true, out_blocks);
     std::unique_ptr<cnhe_vec> guard(o);
     alloc_channels(o);
     const int RC = 1024; // rows per wave
@@ -1439,7 +1448,7 @@ extern "C" int cnhe_mat_mul_rowmajor(cnhe_ctx *h, const cnhe_vec *const *rows, i
             if (force_dense) {
                 // one-hot masks for columns r0..r0+m (EncryptedSealBfvMatrix.cs:96, AtomicSealBfvVector.cs:936-945)
                 std::vector<u64> onehot((size_t)m * N, 0);
-                for (int i = 0; i < m; i++) onehot[(size_t)i * N + (r0 + i)] = 1;
+                for (int i = 0; i < m; i++) onehot[(size_t)i * N + (first_row + r0 + i)] = 1;
                 u64 *dv = c.ws_alloc((size_t)m * N), *masks = c.ws_alloc((size_t)m * N);
                 CNHE_CUDA(cudaMemcpyAsync(dv, onehot.data(), onehot.size() * 8, cudaMemcpyHostToDevice, c.stream));
                 op_encode(c, ch, dv, m, (int)N, masks);

@@ -287,6 +287,12 @@ class Engine:
         check(self.L.cnhe_vec_import_raw(self.h, _p(a), blocks, int(dim), float(scale), fmt, C.byref(out)))
         return Vec(self, out)
 
+    def import_raw_ptr(self, ptr, blocks, dim, scale=1.0, fmt=DENSE):
+        """One vector from raw words at a host OR device address, layout [P][blocks][2kN] (multi-GPU exchanges hand over device buffers)."""
+        out = VECP()
+        check(self.L.cnhe_vec_import_raw(self.h, C.cast(int(ptr), U64P), int(blocks), int(dim), float(scale), fmt, C.byref(out)))
+        return Vec(self, out)
+
     def import_raw_many(self, host_ptr_or_array, n, blocks, dim, scale=1.0, fmt=DENSE):
         """host layout [P][n][blocks][2kN]; accepts a numpy array or a raw host address (e.g. a pinned torch tensor's data_ptr())."""
         if isinstance(host_ptr_or_array, int):
@@ -407,6 +413,11 @@ class Engine:
     def mat_mul_rowmajor(self, rows, v, force_dense=False):
         out = VECP()
         check(self.L.cnhe_mat_mul_rowmajor(self.h, _vec_array(rows), len(rows), v.h, int(force_dense), C.byref(out)))
+        return Vec(self, out)
+
+    def mat_mul_rowmajor_shard(self, rows, v, force_dense, first_row, total_rows):
+        out = VECP()
+        check(self.L.cnhe_mat_mul_rowmajor_shard(self.h, _vec_array(rows), len(rows), v.h, int(force_dense), int(first_row), int(total_rows), C.byref(out)))
         return Vec(self, out)
 
     def layer_conv_dense(self, inputs, gather, weights, bias, M, K):

@@ -142,6 +142,13 @@ class B200BfvMatrix:
         rows = self.eng.decrypt_many([v.vec for v in self.vectors])
         return rows if self.Format == EMatrixFormat.RowMajor else rows.T
 
+    def MulRows(self, v, ForceDenseFormat, first_row, total_rows):
+        """Row-major product for a slice of the rows held by this matrix (global rows first_row..): the per-rank piece of a row-sharded
+        dense layer (cnhe_mat_mul_rowmajor_shard; cryptonets_b200/parallel.py combines the pieces)."""
+        if self.Format != EMatrixFormat.RowMajor:
+            raise Exception("MulRows expects a RowMajor matrix")
+        return B200BfvVector(self.factory, self.eng.mat_mul_rowmajor_shard([r.vec for r in self.vectors], v.vec, ForceDenseFormat, first_row, total_rows))
+
     def Mul(self, v, env=None, ForceDenseFormat=False):
         f = self.factory
         if self.Format == EMatrixFormat.ColumnMajor:

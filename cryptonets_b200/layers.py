@@ -485,6 +485,8 @@ class LLDenseLayer(BaseLayer):
         self.ForceDenseFormat = False
         self.WeightsMatrix = None
         self.BiasVector = None
+        self.Shard = None  # (rank, world, process group): split the rows of this layer over the ranks of ONE inference
+        self._first_row = 0
         super().__init__(**kw)
 
     def GetOutputScale(self):
@@ -499,6 +501,12 @@ class LLDenseLayer(BaseLayer):
         rows = len(self.Bias)
         w = np.asarray(self.Weights, dtype=np.float64).reshape(rows, -1)
         bscale = self.Source.GetOutputScale() * self.WeightsScale
+        if self.Shard is not None and self.InputFormat == EVectorFormat.dense and not isinstance(f, RawFactory):
+            from .parallel import row_slice
+            self._first_row, count = row_slice(rows, self.Shard[0], self.Shard[1])
+            w = w[self._first_row:self._first_row + count]  # this rank encodes and holds its slice of the rows only
+        else:
+            self.Shard = None
         if self.InputFormat == EVectorFormat.dense:
             self.BiasVector = f.GetPlainVector(np.asarray(self.Bias), EVectorFormat.dense if self.ForceDenseFormat else EVectorFormat.sparse, bscale)
             self.WeightsMatrix = f.GetPlainMatrix(w, EMatrixFormat.RowMajor, self.WeightsScale)
@@ -514,7 +522,19 @@ class LLDenseLayer(BaseLayer):
         if m.ColumnCount > 1:
             raise Exception("Expecting only one column")
         env = self.Factory.AllocateComputationEnv()
-        mul = self.WeightsMatrix.Mul(m.GetColumn(0), env, self.ForceDenseFormat)
+        if self.Shard is not None:
+            from . import parallel
+            rank, world, group = self.Shard
+            rows = len(self.Bias)
+            part = self.WeightsMatrix.MulRows(m.GetColumn(0), self.ForceDenseFormat, self._first_row, rows)
+            if self.ForceDenseFormat:  # partial sums at their global columns: all-gather + local modular adds
+                mul = parallel.allreduce_ciphertext_sum(self.Factory, part, group)
+            else:                      # this rank's sparse elements: concatenate the slices
+                mul = parallel.allgather_sparse_elements(self.Factory, part, [parallel.row_slice(rows, r, world)[1] for r in range(world)], group)
+            if mul is not part:
+                part.Dispose()
+        else:
+            mul = self.WeightsMatrix.Mul(m.GetColumn(0), env, self.ForceDenseFormat)
         res = mul.Add(self.BiasVector, env)
         mul.Dispose()
         return self.Factory.GetMatrix([res], EMatrixFormat.ColumnMajor, CopyVectors=False)

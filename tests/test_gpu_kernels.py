@@ -308,3 +308,37 @@ def test_dense_layer_on_tensor_cores(pair):
         del os.environ["CNHE_MAC_NO_IMMA"]
     for m in range(M):
         assert np.array_equal(outs2[m].export_raw(0, 0), want[m]), m
+
+
+@pytest.mark.parametrize("fwd,inv", [("1", "1"), ("0", "0"), ("1", "0"), ("0", "1")])
+def test_persistent_and_per_polynomial_transforms_agree(pair, fwd, inv, monkeypatch):
+    """The transforms exist twice for N = 4096 / 8192: one CTA per polynomial, and persistent CTAs fed by TMA (cp.async.bulk.tensor)
+    with the unit-stride twiddles resident in shared memory.  Every combination of the two (forward / inverse; the defaults are the
+    per-polynomial forward and the persistent inverse) must give the oracle's words: plain transforms on a batch that gives every CTA
+    several polynomials, the digit-cutting forward inside relinearise, and the lazy-double variants inside multiply."""
+    eng, orc, name = pair
+    monkeypatch.setenv("CNHE_NTT_WS_FWD", fwd)
+    monkeypatch.setenv("CNHE_NTT_WS_INV", inv)
+    rng = np.random.default_rng(11)
+    N, k, kt = eng.N, eng.k, eng.k + eng.kb
+    tab = _mod_table(eng, orc)
+    n = 64 * kt + 3  # more polynomials than CTAs x 2 groups for some moduli, ragged tail
+    polys = np.stack([rng.integers(0, tab[b % kt][0], N, dtype=np.uint64) for b in range(n)])
+    d, out = eng.dev_from(polys), eng.dev_alloc(polys.size)
+    eng.raw_ntt(d, out, n, 0, kt, False)
+    got = eng.dev_download(out, polys.size).reshape(polys.shape)
+    for b in list(range(0, n, 37)) + [n - 1]:
+        p, o, oid = tab[b % kt]
+        assert np.array_equal(got[b], o.ntt(oid, polys[b])), b
+    eng.raw_ntt(out, out, n, 0, kt, True)
+    assert np.array_equal(eng.dev_download(out, polys.size).reshape(polys.shape), polys)
+    eng.dev_free(d)
+    eng.dev_free(out)
+    m = 5
+    _, cts = _fresh_cts(orc, m, 21)
+    a, o2 = eng.dev_from(cts), eng.dev_alloc(m * 2 * k * N)
+    eng.raw_multiply_relin(0, a, a, m, o2)
+    want = np.stack([orc.relinearize(orc.multiply(cts[i], cts[i])) for i in range(m)])
+    assert np.array_equal(eng.dev_download(o2, m * 2 * k * N).reshape(m, -1), want)
+    eng.dev_free(a)
+    eng.dev_free(o2)
