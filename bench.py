@@ -283,11 +283,14 @@ def run_b200(args):
     from cryptonets_b200.interfaces import EMatrixFormat
     from cryptonets_b200.networks import CRYPTONETS_PRIMES, synthetic_mnist
 
+    from cryptonets_b200 import parallel
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # host threads and (first-touch) pinned staging buffers next to the GPU they feed: the 8-GPU e2e number moves 1 GB per step per rank
+    numa = parallel.bind_to_gpu_numa(local) if os.environ.get("CNHE_NUMA_BIND", "1") != "0" else {"bound": False}
+    torch.cuda.set_device(local)
     if world > 1:
-        torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     primes = CRYPTONETS_PRIMES[: args.plain_moduli]
     f = B200BfvFactory(primes, BATCH, seed=1 + rank, device=local)
@@ -309,8 +312,17 @@ def run_b200(args):
     # the device-resident number is taken on ONE stream so that the per-kernel CUDA-event times are not inflated by kernels of the
     # other plaintext-modulus channel running concurrently; warm up in the same mode (the block recycler is per stream)
     eng.set_option("multi_stream", 0)
+    # the one exchange of the path: every batch's score ciphertexts (10 ct x P) are all-gathered over NVLink, on the device, inside the
+    # timed region (cryptonets_b200/parallel.py); with one rank it degenerates to the packing copy
+    gatherer = parallel.ScoreGatherer(eng, 10, torch.device("cuda", local))
+
+    def step_resident():
+        out_ = forward(layers, xm)
+        gatherer.gather([v.vec for v in out_.vectors])
+        return out_
+
     for _ in range(args.warmup):
-        forward(layers, xm).Dispose()
+        step_resident().Dispose()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:  # one nvidia-smi loop per job, on the rank that reports
@@ -322,8 +334,9 @@ def run_b200(args):
     for _ in range(args.steps):
         if last is not None:
             last.Dispose()
-        last = forward(layers, xm)
+        last = step_resident()
     ms = eng.timer_stop_ms()
+    gatherer.finish()
     barrier()
     prof = eng.prof_collect()
     eng.prof_enable(False)
@@ -333,28 +346,17 @@ def run_b200(args):
         tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
-        # the one exchange of the path: all-gather of the score ciphertexts (10 ct x P) over NVLink
-        per = 10 * eng.ct_words
-        mine = torch.empty(eng.P * per, dtype=torch.int64, device="cuda")
-        for ch in range(eng.P):
-            for j, v in enumerate(last.vectors):
-                p, wds = v.vec.device_ptr(ch)
-                eng.dev_copy(mine.data_ptr() + 8 * (ch * per + j * eng.ct_words), p, wds)
-        eng.sync()
-        gathered = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)
-        torch.cuda.synchronize()
     value = BATCH * args.steps * world / (ms * 1e-3)
 
     # informational: the same K steps with one CUDA stream per plaintext-modulus channel (the two channels' kernels overlap each other's
     # tails; per-launch event times are then inflated by the concurrency, which is why the roofline above is taken on one stream)
     eng.set_option("multi_stream", 1)
     for _ in range(2):
-        forward(layers, xm).Dispose()
+        step_resident().Dispose()
     barrier()
     eng.timer_start()
     for _ in range(args.steps):
-        forward(layers, xm).Dispose()
+        step_resident().Dispose()
     ms2 = eng.timer_stop_ms()
     barrier()
     if world > 1:
@@ -384,6 +386,7 @@ def run_b200(args):
             cur = nxt
             out = forward(layers, cur)
             cur.Dispose()
+            gatherer.gather([v.vec for v in out.vectors])  # NVLink all-gather of this batch's scores, queued behind its kernels
             ticket = eng.export_raw_many_async([v.vec for v in out.vectors], host_outs[s_ & 1].data_ptr())
             out.Dispose()  # stream-ordered: released after the copies above
             if s_ + 1 < steps:
@@ -392,6 +395,7 @@ def run_b200(args):
                 eng.export_wait(pending)
             pending = ticket
         eng.export_wait(pending)
+        gatherer.finish()
 
     eng.set_option("multi_stream", int(os.environ.get("CNHE_E2E_MULTI_STREAM", "1")))
     e2e_run(max(8, args.warmup))  # reaches the steady state of the upload slots and of the block recycler at pipeline depth 2
@@ -412,7 +416,9 @@ def run_b200(args):
         fam = prof["ntt_forward"]
         # dominant family: forward NTT (incl. the digit-decomposing variant of relinearisation)
         achieved = fam["bytes"] / (fam["ms"] * 1e-3) / 1e9 if fam["ms"] > 0 else 0.0
-        roof = {"bound": "hbm", "kernel": "k_ntt_forward_fp / k_ntt_forward_digits_fp (N=8192), 16*N algorithmic bytes per transform", "achieved": achieved,
+        # the forward transform is limited by FP64 issue (8 DP instructions per butterfly: 100 % of the pipe = 0.85 of this HBM figure), not by
+        # HBM itself; it is reported against the measured HBM copy bandwidth because that is the roofline SURVEY.md 8d prescribes
+        roof = {"bound": "fp64-issue (reported against hbm)", "kernel": "k_ntt_forward_fp / k_ntt_forward_digits_fp (N=8192), 16*N algorithmic bytes per transform", "achieved": achieved,
                 "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)",
                 # ncu (profiles/r01_square_path_v2_ncu.txt): one k_ntt_forward_digits_fp launch of 16000 transforms moved 42.3 MB + 995.9 MB of
@@ -423,6 +429,8 @@ def run_b200(args):
                 "launches_timed": fam["launches"], "algorithmic_bytes_per_launch": fam["bytes"] / max(1, fam["launches"]),
                 "avg_launch_ms": fam["ms"] / max(1, fam["launches"]), "share_of_step": fam["ms"] / ms if ms else None,
                 "families_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}
+        if numa.get("previous_cpus"):  # the CPU leg uses every core the job may use, not just the GPU's NUMA node
+            os.sched_setaffinity(0, numa["previous_cpus"])
         cpu_threads = host_threads()
         # bounded CPU leg beside the GPU number: one warm-up pass (full batch) + two timed passes, sampled if the host is slow
         cpu_sec, cpu_info = cpu_measure(primes, cpu_threads, steps=2, warmup=1, budget_s=25.0, single_thread=False)
@@ -431,7 +439,9 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic MNIST-shaped uint8 images (80% zeros), shipped CryptoNets weights, device-generated keys",
             "config": cpu_line_config(len(primes), world),
-            "clocks": clocks, "gpu_launches": int(launches),
+            "clocks": clocks, "gpu_launches": int(launches), "numa": {k_: v for k_, v in numa.items() if k_ != "previous_cpus"},
+            "collective": {"op": "all_gather_into_tensor (NCCL) of the score ciphertexts, every step, inside both timed regions",
+                           "bytes_per_rank_per_step": int(eng.P * 10 * eng.ct_words * 8)},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(host_in.numel() * 8), "d2h_bytes_per_step": int(host_out.numel() * 8)},
             "value_two_streams": {"value": value_two_streams, "unit": "images/s", "ms_per_step": ms2 / args.steps,
                                   "note": "same steps, one CUDA stream per plaintext modulus; not used for the roofline"},
@@ -476,13 +486,21 @@ def run_lola(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
     if world > 1:
-        torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     builder, primes, N, dbc, k, imgs_of, desc = lola_workloads()[args.workload]
-    f = B200BfvFactory(primes, N, DecompositionBitCount=dbc, GaloisDecompositionBitCount=dbc, SmallModulusCount=k, seed=1 + rank, device=local)
+    # --shard-rows (lola_cifar): ALL ranks work on the same image -- same keys, same input ciphertexts (the seeded sampler makes them
+    # identical without any exchange) -- and split the 5488 rows of the big dense layer (strong scaling of one inference's latency);
+    # default: every rank owns its own image (replicas over images, weak scaling)
+    shard = args.shard_rows and world > 1 and args.workload == "lola_cifar"
+    f = B200BfvFactory(primes, N, DecompositionBitCount=dbc, GaloisDecompositionBitCount=dbc, SmallModulusCount=k, seed=1 if shard else 1 + rank,
+                       device=local)
     eng = f.engine
-    net, reader = builder(f, imgs_of(1, seed=20240917 + rank))  # every rank owns its own image (replicas over images)
+    if shard:
+        net, reader = builder(f, imgs_of(1, seed=20240917), shard=(rank, world, None))
+    else:
+        net, reader = builder(f, imgs_of(1, seed=20240917 + rank))
     net.PrepareNetwork()
     chain = _layer_chain(net)
     enc_layer, rest = chain[1], chain[2:]
@@ -529,7 +547,14 @@ def run_lola(args):
         tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
-    value = args.steps * world / (ms * 1e-3)
+    images_per_step = 1 if shard else world
+    value = args.steps * images_per_step / (ms * 1e-3)
+    if rank == 0:  # per-inference evaluator-operation counts: the CPU arm (`--impl reference --workload ...`) scales its per-op timings by them
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_opcounts_%s.json" % args.workload), "w") as fo:
+                json.dump(counts, fo)
+        except OSError:
+            pass
 
     # ---- e2e: the image's ciphertexts come from pinned host memory every step, the score ciphertexts go back to the host
     vecs = xm.vectors
@@ -573,12 +598,13 @@ def run_lola(args):
         out = {
             "metric": "encrypted images/sec (%s, one image per inference)" % args.workload, "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "latency_ms": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "scaling": "strong" if shard else "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic image (uniform uint8 pixels), shipped weights, device-generated keys",
-            "config": {"workload": desc, "plain_moduli": len(primes), "parallelism": "replica-per-gpu x%d" % world,
+            "config": {"workload": desc, "plain_moduli": len(primes),
+                       "parallelism": ("rows of the 5488-row dense layer sharded x%d (one image)" % world) if shard else "replica-per-gpu x%d" % world,
                        "l2": "key-switching keys (%d Galois elements) and digit waves larger than L2" % eng.n_galois},
             "clocks": clocks, "gpu_launches": int(launches), "operations_per_inference": counts,
-            "e2e": {"value": args.steps * world / e2e_s, "unit": "images/s", "h2d_bytes_per_step": int(host_in.numel() * 8),
+            "e2e": {"value": args.steps * images_per_step / e2e_s, "unit": "images/s", "h2d_bytes_per_step": int(host_in.numel() * 8),
                     "d2h_bytes_per_step": int(host_out.numel() * 8)},
             "roofline": {"bound": "fp64-issue (reported against hbm)", "kernel": "forward NTT family (digit transforms of the Galois / relinearisation key switch), 16*N algorithmic bytes per transform",
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
@@ -728,6 +754,7 @@ def main():
                     help="cryptonets = BASELINE config 2 (the headline metric); lola_small / lola_cifar = configs 3 / 4 (one image per inference); "
                          "microbench = config 5 (one JSON line per case)")
     ap.add_argument("--microbench", action="store_true", help="same as --workload microbench")
+    ap.add_argument("--shard-rows", action="store_true", help="lola_cifar on several GPUs: one image, the big dense layer's rows split over the ranks")
     args = ap.parse_args()
     if args.microbench or args.workload == "microbench":
         run_microbench(args)

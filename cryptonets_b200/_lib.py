@@ -24,6 +24,9 @@ _SIGS = {
     "cnhe_context_galois_elts": [C.c_void_p, U64P],
     "cnhe_context_set_option": [C.c_void_p, C.c_char_p, i64],
     "cnhe_context_sync": [C.c_void_p],
+    "cnhe_context_stream": [C.c_void_p, i32, U64P],
+    "cnhe_context_join_streams": [C.c_void_p],
+    "cnhe_context_fork_streams": [C.c_void_p],
     "cnhe_keys_generate": [C.c_void_p, u64],
     "cnhe_keys_save": [C.c_void_p, i32, C.c_void_p, sz, C.POINTER(sz)],
     "cnhe_context_load": [C.c_void_p, sz, i32, C.POINTER(C.c_void_p)],

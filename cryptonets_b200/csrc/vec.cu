@@ -108,6 +108,25 @@ extern "C" int cnhe_context_set_option(cnhe_ctx *h, const char *name, int64_t va
     } else fail("unknown option");
     API_END
 }
+// Interop with the caller's own GPU work (NCCL collectives, torch copies): the CUDA stream of a plaintext-modulus channel, and the two
+// fences of the per-channel streams -- join: stream 0 waits for the tail of every channel; fork: every channel waits for stream 0.
+// A caller that enqueues on stream 0 between a join and a fork is ordered after everything queued so far and before everything queued later.
+extern "C" int cnhe_context_stream(cnhe_ctx *h, int channel, uint64_t *stream) {
+    API_BEGIN(h)
+    if (channel < 0 || channel >= c.P || !stream) fail("bad arguments");
+    *stream = (uint64_t)c.streams[c.multi_stream ? channel : 0];
+    API_END
+}
+extern "C" int cnhe_context_join_streams(cnhe_ctx *h) {
+    API_BEGIN(h)
+    c.join_streams();
+    API_END
+}
+extern "C" int cnhe_context_fork_streams(cnhe_ctx *h) {
+    API_BEGIN(h)
+    c.fork_streams();
+    API_END
+}
 extern "C" int cnhe_context_sync(cnhe_ctx *h) {
     API_BEGIN(h)
     c.sync();

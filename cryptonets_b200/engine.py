@@ -150,6 +150,18 @@ class Engine:
     def sync(self):
         check(self.L.cnhe_context_sync(self.h))
 
+    def stream(self, channel=0):
+        """cudaStream_t (as an integer) of a channel: wrap it with torch.cuda.ExternalStream to order torch / NCCL work with the library's."""
+        s = C.c_uint64()
+        check(self.L.cnhe_context_stream(self.h, int(channel), C.byref(s)))
+        return s.value
+
+    def join_streams(self):
+        check(self.L.cnhe_context_join_streams(self.h))
+
+    def fork_streams(self):
+        check(self.L.cnhe_context_fork_streams(self.h))
+
     def keygen(self, seed=None):
         """seed=None: keys and all later encryption randomness from the OS CSPRNG (production).  An integer seed selects the deterministic
         sampler shared with the CPU oracle -- tests only, the keys are predictable."""

@@ -155,7 +155,7 @@ def synthetic_cifar(n_images, seed=20240917):
     return np.random.default_rng(seed).integers(0, 256, (n_images, 3 * 32 * 32)).astype(np.float64)
 
 
-def lola_cifar(factory, images, weights=None):
+def lola_cifar(factory, images, weights=None, shard=None):
     """LoLa-CIFAR (`CifarCryptoNet/LolaCifarCryptoNet.cs:27-131`): 3x32x32 image as an im2col matrix [196 x 192], conv 83 maps,
     square, the second convolution as a 5488 x 16268 row-major dense layer (rotate-and-sum per row), square, dense 5488 -> 10."""
     w = weights or cifar_weights()
@@ -169,8 +169,10 @@ def lola_cifar(factory, images, weights=None):
     ce = ConvolutionEngine()
     ce.InputShape, ce.KernelShape, ce.Stride, ce.MapCount = [83, 14, 14], [83, 10, 10], [83, 2, 2], [112, 1, 1]
     ce.Upperpadding, ce.Lowerpadding = [0, 4, 4], [0, 4, 4]
+    # shard = (rank, world, process group): the 5488 rows of the big dense layer are split over the ranks of ONE inference;
+    # every rank holds the same keys and input ciphertexts, the partial products are summed through cryptonets_b200/parallel.py
     dense4 = LLDenseLayer(Source=act3, WeightsScale=512.0, Weights=ce.GetDenseWeights(w["Weights_1"]), Bias=ce.GetDenseBias(w["Biases_1"]),
-                          InputFormat=EVectorFormat.dense, ForceDenseFormat=True)
+                          InputFormat=EVectorFormat.dense, ForceDenseFormat=True, Shard=shard)
     act5 = SquareActivation(Source=dense4)
     dense6 = LLDenseLayer(Source=act5, Weights=w["Weights_2"], Bias=w["Biases_2"], WeightsScale=512.0, InputFormat=EVectorFormat.dense)
     return dense6, reader

@@ -68,28 +68,51 @@ def device_view(ptr, words, device):
 
 
 class ScoreGatherer:
-    """All-gather of a batch's score ciphertexts over NVLink (the one exchange of the replicated path), issued for a batch whose kernels
-    are known to have finished (bench.py calls it right after that batch's export ticket completed), so it runs on torch's stream
-    concurrently with the next batch's kernels on the library's streams."""
+    """All-gather of a batch's score ciphertexts over NVLink -- the one exchange of the replicated path -- ordered on the device, without a
+    host synchronisation and without coupling the plaintext-modulus channels to each other: every channel packs its own score ciphertexts
+    on ITS stream (torch.cuda.ExternalStream over cnhe_context_stream), a side stream waits for those copies (events) and runs the NCCL
+    collective, so the vectors may be disposed right after and the next batch's kernels never wait for it.  Two buffer sets alternate; a
+    channel touching a set again first waits for the collective that read it two batches ago."""
 
     def __init__(self, eng, n_vectors, device, group=None):
-        self.eng, self.group = eng, group
+        self.eng, self.group, self.device = eng, group, device
         self.per = n_vectors * eng.ct_words
-        self.mine = torch.empty(eng.P * self.per, dtype=torch.int64, device=device)
-        self.all = torch.empty(world_size(group) * eng.P * self.per, dtype=torch.int64, device=device)
-        self.device = device
+        self.mine = [torch.empty(eng.P * self.per, dtype=torch.int64, device=device) for _ in range(2)]
+        self.all = [torch.empty(world_size(group) * eng.P * self.per, dtype=torch.int64, device=device) for _ in range(2)]
+        self.side = torch.cuda.Stream(device=device)
+        self.done = [None, None]
+        self.turn = 0
 
     def gather(self, vecs):
-        """vecs: the score vectors of one finished batch (one slab per channel: views handed out by the layer call)."""
+        """vecs: the score vectors of the batch just queued (views of one slab per channel handed out by the layer call)."""
+        i = self.turn
+        self.turn ^= 1
+        mine, out = self.mine[i], self.all[i]
+        chans = {}
         for ch in range(self.eng.P):
-            for j, v in enumerate(vecs):
-                p, wds = v.device_ptr(ch)
-                self.mine[ch * self.per + j * wds: ch * self.per + (j + 1) * wds].copy_(device_view(p, wds, self.device), non_blocking=True)
-        if world_size(self.group) > 1:
-            dist.all_gather_into_tensor(self.all, self.mine, group=self.group)
-        else:
-            self.all.copy_(self.mine)
-        return self.all
+            chans.setdefault(self.eng.stream(ch), []).append(ch)  # single-stream mode: every channel reports stream 0
+        for sptr, chs in chans.items():
+            ext = torch.cuda.ExternalStream(sptr, device=self.device)
+            if self.done[i] is not None:
+                ext.wait_event(self.done[i])
+            with torch.cuda.stream(ext):
+                for ch in chs:
+                    for j, v in enumerate(vecs):
+                        p, wds = v.device_ptr(ch)
+                        mine[ch * self.per + j * wds: ch * self.per + (j + 1) * wds].copy_(device_view(p, wds, self.device), non_blocking=True)
+            self.side.wait_stream(ext)
+        with torch.cuda.stream(self.side):
+            if world_size(self.group) > 1:
+                dist.all_gather_into_tensor(out, mine, group=self.group)
+            else:
+                out.copy_(mine, non_blocking=True)
+            self.done[i] = torch.cuda.Event()
+            self.done[i].record(self.side)
+        return out
+
+    def finish(self):
+        """host-side wait for the collectives queued so far (end of a timed region)"""
+        self.side.synchronize()
 
 
 def allreduce_ciphertext_sum(factory, vec, group=None):
@@ -168,7 +191,8 @@ def gpu_numa_node(index):
 
 def bind_to_gpu_numa(index):
     """Pin this process (and what it allocates from now on, first-touch: the pinned staging buffers) to the CPUs of the GPU's NUMA node.
-    Returns a description for the bench record; a no-op when the topology cannot be read."""
+    Returns a description for the bench record (with the previous affinity under "previous_cpus": restore it with os.sched_setaffinity
+    before CPU-heavy work such as the CPU baseline leg); a no-op when the topology cannot be read."""
     node = gpu_numa_node(index)
     if node < 0:
         return {"numa_node": None, "bound": False}
@@ -181,7 +205,8 @@ def bind_to_gpu_numa(index):
         allowed = cpus & set(os.sched_getaffinity(0))
         if not allowed:
             return {"numa_node": node, "bound": False}
+        previous = sorted(os.sched_getaffinity(0))
         os.sched_setaffinity(0, allowed)
-        return {"numa_node": node, "bound": True, "cpus": len(allowed)}
+        return {"numa_node": node, "bound": True, "cpus": len(allowed), "previous_cpus": previous}
     except Exception:
         return {"numa_node": node, "bound": False}

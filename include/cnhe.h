@@ -65,6 +65,13 @@ int cnhe_context_galois_elts(const cnhe_ctx *, uint64_t *out);
  * "trace_noise" (1: record the invariant noise budget after every evaluator-level operation, see cnhe_trace_read) */
 int cnhe_context_set_option(cnhe_ctx *, const char *name, int64_t value);
 int cnhe_context_sync(cnhe_ctx *);
+/* interop with the caller's own GPU work (the NCCL all-gather of the score ciphertexts): the CUDA stream (cudaStream_t as an integer) of a
+ * channel, and the fences of the per-channel streams -- join: stream 0 waits for every channel's tail; fork: every channel waits for
+ * stream 0.  Work the caller enqueues on stream 0 between a join and a fork is ordered after everything queued before the join and
+ * before everything queued after the fork. */
+int cnhe_context_stream(cnhe_ctx *, int channel, uint64_t *stream);
+int cnhe_context_join_streams(cnhe_ctx *);
+int cnhe_context_fork_streams(cnhe_ctx *);
 /* EncryptedSealBfvEnvironment.GenerateEncryptionKeys ("EncryptedSealBfvVector.cs:92-102") -> KeyGenerator, RelinKeys(dbc),
  * GaloisKeys(dbc) ("AtomicSealBfvVector.cs:62-74"), sampled on the device.
  * cnhe_keys_generate_secure: every channel draws a fresh 256-bit ChaCha20 key from the OS (getrandom) -- secret key, key masks and all

@@ -34,6 +34,9 @@ namespace HEWrapper
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int cnhe_context_galois_elts(IntPtr a0, ulong[] @out);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int cnhe_context_set_option(IntPtr a0, string name, long value);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int cnhe_context_sync(IntPtr a0);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int cnhe_context_stream(IntPtr a0, int channel, out ulong stream);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int cnhe_context_join_streams(IntPtr a0);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int cnhe_context_fork_streams(IntPtr a0);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int cnhe_keys_generate_secure(IntPtr a0);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int cnhe_keys_generate(IntPtr a0, ulong seed);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] public static extern int cnhe_keys_export(IntPtr a0, int channel, int what, ulong arg, IntPtr dst, UIntPtr cap_words);
