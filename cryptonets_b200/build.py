@@ -40,7 +40,9 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on " + s)
         if verbose:
             sys.stderr.write(out.decode())
-    subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    tmp = OUT + ".tmp"  # link beside the target and rename: a snapshot of the tree never sees a half-written library
+    subprocess.check_call([NVCC, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    os.replace(tmp, OUT)
     return OUT
 
 

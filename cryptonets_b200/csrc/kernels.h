@@ -21,6 +21,9 @@ struct NttTab {
     double inv_n_w_d;                   // iw[1] * N^-1 mod p, centred: the last inverse stage carries the N^-1 scaling
     int fp_ok;                          // 1 when the FP64 path is exact for this modulus and N
     unsigned fwd_recenter, inv_recenter; // forward: bit i = re-centre at the start of pass i; inverse: bit v = re-centre the sums of stage v
+    // N = 16384 runs as two half-size transforms on a CTA pair (ntt.cu, "split"): wd_hi / iwd_hi then hold the two halves' twiddle
+    // tables ([half][8192], indexed like wd / iwd of an 8192-point transform) and this is the forward schedule of the passes 1+5 | 4 | 4
+    unsigned fwd_recenter_split;
     int fwd_out_rc;                     // lazy forward output must be re-centred (its bound squared would overflow the consumer's product)
     double fwd_out_bound;               // |forward lazy output| <= fwd_out_bound * p
 };
@@ -133,6 +136,9 @@ cudaError_t launch_dyadic_bcast(const u64 *a, const u64 *b, u64 *out, int n, int
                                 const BehzConst *bc, cudaStream_t s);
 // Galois: out[c] = (perm(c0), 0), perm1[c] = perm(c1)   (util::apply_galois)
 cudaError_t launch_galois(const u64 *in, u64 *out_base, u64 *perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *bc, cudaStream_t s);
+// the same with the n input ciphertexts given by a device pointer table
+cudaError_t launch_galois_gather(const u64 *const *in_ptrs, u64 *out_base, u64 *perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *bc,
+                                 cudaStream_t s);
 
 // ---- K4: out[m] = sum_k w[m][k] * in[gather[m][k]] (+ Delta*bias[m] on coefficient 0 of c0)
 struct MacTile {
@@ -179,6 +185,8 @@ cudaError_t launch_mac_dense_imma(const u64 *const *in_ptrs, const void *wfrag, 
 cudaError_t launch_sample(u64 *out, int n, int kind, const RngKey &seed, u64 stream0, u64 stream_step, int k, int logn, const BehzConst *bc, cudaStream_t s);
 // plain[i][index_map[j]] = values[i][j]  (j < count), zero elsewhere
 cudaError_t launch_encode_scatter(const u64 *values, u64 *plain, int n, int count, const u32 *index_map, int logn, cudaStream_t s);
+// plain[i][index_map[first_col + i]] = 1, zero elsewhere (one-hot slot masks, encoded form before the inverse transform)
+cudaError_t launch_onehot_scatter(u64 *plain, int n, int first_col, const u32 *index_map, int logn, cudaStream_t s);
 cudaError_t launch_decode_gather(const u64 *plain_ntt, u64 *values, int n, const u32 *index_map, int logn, cudaStream_t s);
 // ct[i] (already u*pk, coefficient form) += (e0 + Delta*m_i, e1)
 cudaError_t launch_encrypt_finish(u64 *ct, const u64 *plain, size_t plain_stride, int n, int coeffs, const RngKey &seed, u64 nonce0, int k, int logn,

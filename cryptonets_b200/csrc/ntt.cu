@@ -851,6 +851,176 @@ k_ntt_inverse_fp(const u64 *src, const u64 *base_add, int base_group, size_t bas
     }
 }
 
+// ================================================================ N = 16384 on CTA pairs ("split")
+// A 16384-point polynomial is 128 KB of doubles: one CTA per SM, every warp of the SM at the same barrier, loads never overlapping
+// butterflies (0.36 of the HBM roofline against 0.50 at N = 8192).  After the first Cooley-Tukey stage the two halves of the polynomial
+// are independent 8192-point transforms with their own twiddle tables (NttTab::wd_hi holds them), so a cluster of two CTAs takes one
+// polynomial: CTA h computes half h -- x[i] +- w x[i + N/2] on the way in from global memory (the pair reads the same lines at the same
+// time: one trip to HBM, the second read is an L2 hit), then the 5+4+4 passes of the 8192-point kernel in 64 KB of shared memory, 2-3 CTAs
+// per SM.  The inverse runs the 13 in-half stages first and the pair exchanges the halves through distributed shared memory for the last
+// butterfly, which carries N^-1.  src == dst is allowed: the pair meets at a cluster barrier between its loads and its stores.
+constexpr int SPLIT_LOGN = 13, SPLIT_H = 1 << SPLIT_LOGN, SPLIT_THREADS = SPLIT_H / 32;
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned dsmem_base(const void *p, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ double ld_dsmem(unsigned addr) {
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+// first pass of half `upper`: stage 0 of the 16384-point transform folded into the loads, then 5 stages (j = 0: low twiddles only)
+template <bool IN_F>
+__device__ __forceinline__ void fwd_split_first(double *sm, const double *twc, const FwdSrc &src, const NttTab &tb, int vt, double w0, bool upper) {
+    constexpr int R = 5, E = 1 << R, LG = SPLIT_LOGN - R;
+    const double p = tb.pd, pinv = tb.pinv;
+    double x[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int idx = vt + (e << LG);
+        const double a = fwd_load_fp<IN_F>(src, idx, p, pinv), c = fwd_load_fp<IN_F>(src, idx + SPLIT_H, p, pinv);
+        const double t = fmodmul(c, w0, p, pinv);
+        x[e] = upper ? __dsub_rn(a, t) : __dadd_rn(a, t);
+    }
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+        const int h = E >> (u + 1);
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            if (e & h) continue;
+            const double w = twc[(1 << u) + (e >> (R - u))];
+            const double t = fmodmul(x[e + h], w, p, pinv);
+            const double a = x[e];
+            x[e] = __dadd_rn(a, t);
+            x[e + h] = __dsub_rn(a, t);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) sm[swz(vt + (e << LG))] = x[e];
+}
+template <bool IN_F, bool OUT_F>
+__device__ __forceinline__ void fwd_split_body(double *sm, const FwdSrc &src, u64 *dst, NttTab &tb, int half, int tid) {
+    constexpr int TR = SPLIT_THREADS;
+    double *twc = sm + SPLIT_H;
+    const double w0 = __ldg(tb.wd + 1);
+    tb.wd = tb.wd_hi + half * SPLIT_H;
+    tb.fwd_recenter = tb.fwd_recenter_split;
+    load_twiddle_cache(twc, tb.wd, tid, TR);
+    __syncthreads();
+    fwd_split_first<IN_F>(sm, twc, src, tb, tid, w0, half != 0);
+    cluster_arrive(); // this CTA has read everything it needs from the source polynomial
+    __syncthreads();
+    CNHE_VTN(SPLIT_H / 16, (fwd_pass_fp<SPLIT_LOGN, 5, 4, false, 1, false>(sm, twc, src, tb, vt))); __syncthreads();
+    cluster_wait(); // ... and so has its partner: the halves may be written in place
+    CNHE_VTN(SPLIT_H / 16, (fwd_last_fp<SPLIT_LOGN, 2, OUT_F>(sm, dst, tb, vt)));
+}
+template <bool IN_F, bool OUT_F>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SPLIT_THREADS, 2)
+k_ntt_forward_split(const u64 *src, u64 *dst, const NttTab *__restrict__ tabs, int mod_base, int mod_count) {
+    extern __shared__ __align__(16) u64 sm[];
+    const int b = blockIdx.x >> 1, half = blockIdx.x & 1, tid = threadIdx.x;
+    NttTab tb = tabs[mod_base + b % mod_count];
+    FwdSrc fs;
+    fs.src = src + (size_t)b * (2 * SPLIT_H);
+    fs.digit = false; fs.need_reduce = false; fs.shift = 0; fs.mask = 0;
+    fwd_split_body<IN_F, OUT_F>(reinterpret_cast<double *>(sm), fs, dst + (size_t)b * (2 * SPLIT_H) + half * SPLIT_H, tb, half, tid);
+}
+template <bool OUT_F>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SPLIT_THREADS, 2)
+k_ntt_forward_digits_split(const u64 *target, size_t ct_stride, u64 *dst, const NttTab *__restrict__ tabs, int k, DigitMap dm) {
+    extern __shared__ __align__(16) u64 sm[];
+    const int b = blockIdx.x >> 1, half = blockIdx.x & 1, tid = threadIdx.x;
+    const int l = b % k, d = (b / k) % dm.D, c = b / (k * dm.D);
+    NttTab tb = tabs[l];
+    FwdSrc fs;
+    fs.src = target + (size_t)c * ct_stride + (size_t)dm.src[d] * (2 * SPLIT_H);
+    fs.digit = true;
+    fs.shift = dm.shift[d];
+    fs.mask = dm.mask;
+    fs.need_reduce = dm.mask >= tb.mod.p;
+    fwd_split_body<false, OUT_F>(reinterpret_cast<double *>(sm), fs, dst + (((size_t)c * k + l) * dm.D + d) * (2 * SPLIT_H) + half * SPLIT_H, tb, half, tid);
+}
+// last in-half pass (stages 8..12) and the cross-half butterfly: own results go to shared memory for the partner, the partner's come
+// back through DSMEM; half 0 keeps the sums (times N^-1), half 1 the differences (times iw[1] N^-1)
+template <bool OUT_F>
+__device__ __forceinline__ void inv_split_last(double *sm, const double *twc, u64 *dst, const u64 *base_add, const NttTab &tb, int vt, int half) {
+    constexpr int V0 = 8, R = 5, E = 1 << R, N = SPLIT_H;
+    const double p = tb.pd, pinv = tb.pinv;
+    double x[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) x[e] = sm[swz(vt + (e << V0))];
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+        const int h = 1 << u;
+        const bool rc = (tb.inv_recenter >> (V0 + u)) & 1;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            if (e & h) continue;
+            const double w = twc[(N >> (V0 + u + 1)) + (e >> (u + 1))];
+            const double a = x[e], bq = x[e + h];
+            x[e] = __dadd_rn(a, bq);
+            x[e + h] = fmodmul(__dsub_rn(a, bq), w, p, pinv);
+        }
+        if (rc) {
+#pragma unroll
+            for (int e = 0; e < E; e++)
+                if (!(e & h)) x[e] = frecenter(x[e], p, pinv);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) sm[swz(vt + (e << V0))] = x[e];
+    cluster_arrive();
+    cluster_wait(); // both halves are complete and visible across the pair
+    const unsigned peer = dsmem_base(sm, (unsigned)(half ^ 1));
+    const double scale = half ? tb.inv_n_w_d : tb.inv_n_d;
+#pragma unroll
+    for (int e0 = 0; e0 < E; e0 += 8) { // the partner's values in batches of 8: all 32 next to x[] would spill
+        double r[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) r[i] = ld_dsmem(peer + 8u * (unsigned)swz(vt + ((e0 + i) << V0)));
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int idx = vt + ((e0 + i) << V0);
+            const double v = fmodmul(half ? __dsub_rn(r[i], x[e0 + i]) : __dadd_rn(x[e0 + i], r[i]), scale, p, pinv);
+            if constexpr (OUT_F) dst[idx] = lazy_bits(v);
+            else {
+                u64 o = fsmall_u(v, tb.mod.p);
+                if (base_add) o = addmod(o, base_add[idx], tb.mod.p);
+                dst[idx] = o;
+            }
+        }
+    }
+    cluster_arrive(); // done with the partner's memory: either CTA may exit once both have said so
+    cluster_wait();
+}
+template <bool IN_F, bool OUT_F>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SPLIT_THREADS, 2)
+k_ntt_inverse_split(const u64 *src, const u64 *base_add, int base_group, size_t base_stride, u64 *dst, const NttTab *__restrict__ tabs, int mod_base,
+                    int mod_count) {
+    extern __shared__ __align__(16) u64 smraw[];
+    constexpr int TR = SPLIT_THREADS, H = SPLIT_H;
+    const int b = blockIdx.x >> 1, half = blockIdx.x & 1, tid = threadIdx.x;
+    NttTab tb = tabs[mod_base + b % mod_count];
+    tb.iwd = tb.iwd_hi + half * H;
+    double *sm = reinterpret_cast<double *>(smraw);
+    double *twc = sm + H;
+    load_twiddle_cache(twc, tb.iwd, tid, TR);
+    const u64 *s = src + (size_t)b * (2 * H) + half * H;
+    u64 *d = dst + (size_t)b * (2 * H) + half * H;
+    const u64 *ba = base_add ? base_add + (size_t)(b / base_group) * base_stride + (size_t)(b % base_group) * (2 * H) + half * H : nullptr;
+    if (ba) {
+        const char *pb = reinterpret_cast<const char *>(ba);
+        for (int i = tid * 128; i < H * 8; i += TR * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + i));
+    }
+    CNHE_VTN(H / 16, (inv_first_fp<SPLIT_LOGN, IN_F>(sm, s, tb, vt)));
+    __syncthreads();
+    CNHE_VTN(H / 16, (inv_pass_fp<SPLIT_LOGN, 4, 4, false, false>(sm, twc, d, ba, tb, vt))); __syncthreads();
+    inv_split_last<OUT_F>(sm, twc, d, ba, tb, tid, half);
+}
+
 // ================================================================ persistent TMA-staged transforms, N = 4096 / 8192
 // One persistent CTA per SM.  Each CTA is pinned to ONE modulus (CTA c serves the polynomials whose table index is c mod #moduli), so
 // the twiddles it needs never change: the 15N/16 twiddles of the four unit-stride stages -- the ones that used to be fetched from L2 by
@@ -1282,6 +1452,16 @@ static bool ws_flag(const char *name, bool dflt) {
 // in its digit-cutting form), so the forward direction keeps the per-polynomial kernel unless CNHE_NTT_WS_FWD=1 asks for the staged one.
 static bool ws_enabled_fwd() { return ws_flag("CNHE_NTT_WS_FWD", false); } // read per launch: tests flip it inside one process
 static bool ws_enabled_inv() { return ws_flag("CNHE_NTT_WS_INV", true); }
+// N = 16384: CTA pairs unless CNHE_NTT_SPLIT=0 (read per launch, like the flags above)
+static bool split_enabled() {
+    const char *v = getenv("CNHE_NTT_SPLIT");
+    return v ? atoi(v) != 0 : true;
+}
+constexpr int SPLIT_SMEM = SPLIT_H * 8 + TWC * 8;
+template <class K>
+static cudaError_t split_prep(K kern) {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_SMEM);
+}
 static int sm_count() {
     static int n = [] {
         int dev = 0, v = 148;
@@ -1348,6 +1528,18 @@ cudaError_t launch_ntt_forward(const u64 *src, u64 *dst, int n_polys, int logn, 
             return lazy ? ws_launch(k_ntt_forward_ws<12, WS_LAZY, true>, ws_smem_bytes<12>(), map, dst, tabs, a, s)
                         : ws_launch(k_ntt_forward_ws<12, WS_CANON, false>, ws_smem_bytes<12>(), map, dst, tabs, a, s);
         }
+        if (logn == 14 && split_enabled()) {
+            if (lazy) {
+                cudaError_t e = split_prep(k_ntt_forward_split<true, true>);
+                if (e != cudaSuccess) return e;
+                k_ntt_forward_split<true, true><<<2 * n_polys, SPLIT_THREADS, SPLIT_SMEM, s>>>(src, dst, tabs, mod_base, mod_count);
+            } else {
+                cudaError_t e = split_prep(k_ntt_forward_split<false, false>);
+                if (e != cudaSuccess) return e;
+                k_ntt_forward_split<false, false><<<2 * n_polys, SPLIT_THREADS, SPLIT_SMEM, s>>>(src, dst, tabs, mod_base, mod_count);
+            }
+            return cudaGetLastError();
+        }
         CNHE_DISPATCH_LOGN(logn, {
             if (lazy) {
                 cudaError_t e = prep(k_ntt_forward_fp<L, true, true>, L);
@@ -1387,6 +1579,18 @@ cudaError_t launch_ntt_forward_digits(const u64 *target, size_t ct_stride, u64 *
             return of ? ws_launch(k_ntt_forward_ws<12, WS_DIGIT, true>, ws_smem_bytes<12>(), map, dst, tabs, a, s)
                       : ws_launch(k_ntt_forward_ws<12, WS_DIGIT, false>, ws_smem_bytes<12>(), map, dst, tabs, a, s);
         }
+        if (logn == 14 && split_enabled()) {
+            if (fp & NTT_OUT_F) {
+                cudaError_t e = split_prep(k_ntt_forward_digits_split<true>);
+                if (e != cudaSuccess) return e;
+                k_ntt_forward_digits_split<true><<<2 * n_ct * dm.D * k, SPLIT_THREADS, SPLIT_SMEM, s>>>(target, ct_stride, dst, tabs, k, dm);
+            } else {
+                cudaError_t e = split_prep(k_ntt_forward_digits_split<false>);
+                if (e != cudaSuccess) return e;
+                k_ntt_forward_digits_split<false><<<2 * n_ct * dm.D * k, SPLIT_THREADS, SPLIT_SMEM, s>>>(target, ct_stride, dst, tabs, k, dm);
+            }
+            return cudaGetLastError();
+        }
         CNHE_DISPATCH_LOGN(logn, {
             if (fp & NTT_OUT_F) {
                 cudaError_t e = prep(k_ntt_forward_digits_fp<L, true>, L);
@@ -1416,6 +1620,14 @@ static cudaError_t launch_inv_fp(const u64 *src, const u64 *base, int base_group
                                                                                             mod_count);
     return cudaSuccess;
 }
+template <bool IN_F, bool OUT_F>
+static cudaError_t launch_inv_split(const u64 *src, const u64 *base, int base_group, size_t base_stride, u64 *dst, int n_polys, const NttTab *tabs,
+                                    int mod_base, int mod_count, cudaStream_t s) {
+    cudaError_t e = split_prep(k_ntt_inverse_split<IN_F, OUT_F>);
+    if (e != cudaSuccess) return e;
+    k_ntt_inverse_split<IN_F, OUT_F><<<2 * n_polys, SPLIT_THREADS, SPLIT_SMEM, s>>>(src, base, base_group, base_stride, dst, tabs, mod_base, mod_count);
+    return cudaGetLastError();
+}
 static cudaError_t launch_inv(const u64 *src, const u64 *base, int base_group, size_t base_stride, u64 *dst, int n_polys, int logn,
                               const NttTab *tabs, int mod_base, int mod_count, int fp, cudaStream_t s) {
     if (n_polys <= 0) return cudaSuccess;
@@ -1439,6 +1651,10 @@ static cudaError_t launch_inv(const u64 *src, const u64 *base, int base_group, s
                    : in_f ? ws_launch(k_ntt_inverse_ws<12, true, false>, ws_smem_bytes<12>(), map, dst, tabs, a, s)
                           : ws_launch(k_ntt_inverse_ws<12, false, false>, ws_smem_bytes<12>(), map, dst, tabs, a, s);
         }
+        if (logn == 14 && split_enabled())
+            return out_f  ? launch_inv_split<true, true>(src, base, base_group, base_stride, dst, n_polys, tabs, mod_base, mod_count, s)
+                   : in_f ? launch_inv_split<true, false>(src, base, base_group, base_stride, dst, n_polys, tabs, mod_base, mod_count, s)
+                          : launch_inv_split<false, false>(src, base, base_group, base_stride, dst, n_polys, tabs, mod_base, mod_count, s);
         CNHE_DISPATCH_LOGN(logn, {
             cudaError_t e = out_f  ? launch_inv_fp<L, true, true>(src, base, base_group, base_stride, dst, n_polys, tabs, mod_base, mod_count, s)
                             : in_f ? launch_inv_fp<L, true, false>(src, base, base_group, base_stride, dst, n_polys, tabs, mod_base, mod_count, s)

@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(256) k_dyadic_bcast(const u64 *a, const u64 *b
 }
 
 // ---------------------------------------------------------------- Galois permutation (gather form)
-__global__ void __launch_bounds__(256) k_galois(const u64 *__restrict__ in, u64 *__restrict__ out_base, u64 *__restrict__ perm_c1, int n,
-                                               u64 elt_inv, int k, int logn, const BehzConst *__restrict__ bc) {
+__global__ void __launch_bounds__(256) k_galois(const u64 *__restrict__ in, const u64 *const *__restrict__ in_ptrs, u64 *__restrict__ out_base,
+                                               u64 *__restrict__ perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *__restrict__ bc) {
     const int N = 1 << logn;
     const size_t kN = (size_t)k * N;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256) k_galois(const u64 *__restrict__ in, u64 
     const int part = (int)(r / kN), l = (int)((r % kN) >> logn), j = (int)(r & (N - 1));
     const u64 raw = ((u64)j * elt_inv) & (2 * (u64)N - 1);
     const int src = (int)(raw & (N - 1));
-    u64 v = in[c * 2 * kN + (size_t)part * kN + (size_t)l * N + src];
+    const u64 *ct = in_ptrs ? in_ptrs[c] : in + c * 2 * kN; // gathered inputs (batched rotations of scattered ciphertexts) or a packed array
+    u64 v = ct[(size_t)part * kN + (size_t)l * N + src];
     if (raw >> logn) v = negmod(v, bc->q[l].p);
     if (part == 0) {
         out_base[c * 2 * kN + (size_t)l * N + j] = v;
@@ -298,6 +299,15 @@ __global__ void __launch_bounds__(256) k_encode_scatter(const u64 *__restrict__ 
     const size_t c = i >> logn;
     plain[c * N + index_map[j]] = j < count ? values[c * count + j] : 0;
 }
+// plain[i] = BatchEncoder scatter of the one-hot slot vector e_(first_col + i): a single 1 at index_map[first_col + i]
+__global__ void __launch_bounds__(256) k_onehot_scatter(u64 *__restrict__ plain, int n, int first_col, const u32 *__restrict__ index_map, int logn) {
+    const int N = 1 << logn;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n << logn) return;
+    const int x = (int)(i & (N - 1));
+    const size_t row = i >> logn;
+    plain[i] = (u32)x == index_map[first_col + row] ? 1 : 0;
+}
 __global__ void __launch_bounds__(256) k_decode_gather(const u64 *__restrict__ plain_ntt, u64 *__restrict__ values, int n,
                                                       const u32 *__restrict__ index_map, int logn) {
     const int N = 1 << logn;
@@ -388,7 +398,13 @@ cudaError_t launch_dyadic_bcast(const u64 *a, const u64 *b, u64 *out, int n, int
 }
 cudaError_t launch_galois(const u64 *in, u64 *out_base, u64 *perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *bc, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    k_galois<<<blocks_for(((size_t)n * 2 * k) << logn), 256, 0, s>>>(in, out_base, perm_c1, n, elt_inv, k, logn, bc);
+    k_galois<<<blocks_for(((size_t)n * 2 * k) << logn), 256, 0, s>>>(in, nullptr, out_base, perm_c1, n, elt_inv, k, logn, bc);
+    return cudaGetLastError();
+}
+cudaError_t launch_galois_gather(const u64 *const *in_ptrs, u64 *out_base, u64 *perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *bc,
+                                 cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    k_galois<<<blocks_for(((size_t)n * 2 * k) << logn), 256, 0, s>>>(nullptr, in_ptrs, out_base, perm_c1, n, elt_inv, k, logn, bc);
     return cudaGetLastError();
 }
 cudaError_t launch_mac_layer(const u64 *const *in_ptrs, const int *gather, const MacTile *tiles, int n_tiles, const u64 *const *w_ptrs,
@@ -415,6 +431,11 @@ cudaError_t launch_sample(u64 *out, int n, int kind, const RngKey &seed, u64 str
 cudaError_t launch_encode_scatter(const u64 *values, u64 *plain, int n, int count, const u32 *index_map, int logn, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     k_encode_scatter<<<blocks_for((size_t)n << logn), 256, 0, s>>>(values, plain, n, count, index_map, logn);
+    return cudaGetLastError();
+}
+cudaError_t launch_onehot_scatter(u64 *plain, int n, int first_col, const u32 *index_map, int logn, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    k_onehot_scatter<<<blocks_for((size_t)n << logn), 256, 0, s>>>(plain, n, first_col, index_map, logn);
     return cudaGetLastError();
 }
 cudaError_t launch_decode_gather(const u64 *plain_ntt, u64 *values, int n, const u32 *index_map, int logn, cudaStream_t s) {

@@ -189,17 +189,27 @@ void Context::fork_streams() {
 void Context::h2d(void *dst, const void *src, size_t bytes) {
     if (!bytes) return;
     if (!stage_buf) {
-        stage_size = 32u << 20;
+        stage_size = 64u << 20;
         CNHE_CUDA(cudaHostAlloc((void **)&stage_buf, stage_size, cudaHostAllocDefault));
+        stage_ev.resize((size_t)STAGE_PARTS * streams.size());
+        for (cudaEvent_t &e : stage_ev) CNHE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        stage_ev_set.assign(STAGE_PARTS, 0);
     }
-    if (bytes > stage_size / 2) { // large: plain (staged by the driver) copy
+    const size_t part_size = stage_size / STAGE_PARTS;
+    if (bytes > part_size) { // large: plain (staged by the driver) copy
         CNHE_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
         return;
     }
     const size_t need = (bytes + 255) & ~(size_t)255;
-    if (stage_off + need > stage_size) { // wrap: everything queued so far (on any channel stream) must have left the ring
-        sync();
-        stage_off = 0;
+    size_t part = stage_off / part_size;
+    if (stage_off + need > (part + 1) * part_size || stage_off + need > stage_size) { // move on to the next part
+        // what was staged in the part being left is consumed once every channel stream has passed this point
+        for (size_t s = 0; s < streams.size(); s++) CNHE_CUDA(cudaEventRecord(stage_ev[part * streams.size() + s], streams[s]));
+        stage_ev_set[part] = 1;
+        part = (part + 1) % STAGE_PARTS;
+        if (stage_ev_set[part]) // its previous contents: staged STAGE_PARTS - 1 parts ago, long consumed in the steady state
+            for (size_t s = 0; s < streams.size(); s++) CNHE_CUDA(cudaEventSynchronize(stage_ev[part * streams.size() + s]));
+        stage_off = part * part_size;
     }
     memcpy(stage_buf + stage_off, src, bytes);
     CNHE_CUDA(cudaMemcpyAsync(dst, stage_buf + stage_off, bytes, cudaMemcpyHostToDevice, stream));
@@ -258,6 +268,7 @@ Context::~Context() {
     for (auto &r : prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : prof_pool) cudaEventDestroy(e);
     if (stage_buf) cudaFreeHost(stage_buf);
+    for (cudaEvent_t e : stage_ev) cudaEventDestroy(e);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -304,19 +315,33 @@ static void fp_schedule(NttTab &tb, int logN, bool force_int) {
     if (force_int || hm::bit_length(p) > 49) return;
     const double L = 0.9 * 4503599627370496.0 / (double)p;
     auto c = [&](double a) { return 0.5 + 0.75 * a / (L / 0.9) + 1e-6; }; // bound of |a*w mod p| for |a| <= a*p, |w| <= p/2
+    // forward schedule of a pass list; returns false when some pass overflows even after re-centring
+    auto forward = [&](const int *rad, int np, unsigned &mask, double &A) {
+        mask = 0;
+        A = 1.0; // canonical input
+        for (int i = 0; i < np; i++) {
+            for (int attempt = 0; attempt < 2; attempt++) {
+                double a = attempt ? 0.51 : A;
+                bool ok = true;
+                for (int s = 0; s < rad[i]; s++) { ok = ok && a < L; a += c(a); }
+                ok = ok && a < L; // the canonicalisation / next pass consumes it
+                if (ok) { A = a; if (attempt) mask |= 1u << i; break; }
+                if (attempt) return false; // even a re-centred pass overflows
+                if (i == 0) return false;  // the first pass reads straight from global memory: no re-centring slot
+            }
+        }
+        return true;
+    };
     int rad[4];
     const int np = ntt_pass_radices(logN, 0, rad);
-    double A = 1.0; // canonical input
-    for (int i = 0; i < np; i++) {
-        for (int attempt = 0; attempt < 2; attempt++) {
-            double a = attempt ? 0.51 : A;
-            bool ok = true;
-            for (int s = 0; s < rad[i]; s++) { ok = ok && a < L; a += c(a); }
-            ok = ok && a < L; // the canonicalisation / next pass consumes it
-            if (ok) { A = a; if (attempt) tb.fwd_recenter |= 1u << i; break; }
-            if (attempt) return; // even a re-centred pass overflows
-            if (i == 0) return;  // the first pass reads straight from global memory: no re-centring slot
-        }
+    double A;
+    if (!forward(rad, np, tb.fwd_recenter, A)) return;
+    tb.fwd_recenter_split = 0;
+    if (logN == 14) { // CTA-pair form: stage 0 rides on the first pass' loads
+        const int split[3] = {6, 4, 4};
+        double As;
+        if (!forward(split, 3, tb.fwd_recenter_split, As)) return;
+        A = std::max(A, As);
     }
     // lazy forward output (|x| <= A p) feeds products of two such values (tensor) or of one with a canonical key word: both operands
     // of a modular product may be lazy only while A*A*p stays below 2^51
@@ -460,7 +485,16 @@ Context *context_create(const u64 *plain_primes, int P, uint32_t N, const u64 *c
             a = hm::mul(a, psi, p);
             b = hm::mul(b, ipsi, p);
         }
-        { // transposed unit-stride twiddles (see NttTab::wd_hi)
+        if (logN == 14) { // twiddle tables of the two half-size transforms (see NttTab::fwd_recenter_split)
+            const u64 H = N / 2;
+            for (u64 h = 0; h < 2; h++)
+                for (u64 i = 1; i < H; i++) {
+                    u64 m2 = 1;
+                    while (2 * m2 <= i) m2 *= 2; // stage of index i: [m2, 2 m2)
+                    wd_hi[h * H + i] = wd[i + m2 + h * m2];
+                    iwd_hi[h * H + i] = iwd[i + m2 + h * m2];
+                }
+        } else { // transposed unit-stride twiddles (see NttTab::wd_hi)
             const u64 T = N / 16;
             const int S0 = logN - 4;
             for (u64 j = 0; j < T; j++) {
@@ -874,6 +908,73 @@ void op_rotate_rows(Context &c, int ch, const u64 *in, int n, int steps, u64 *ou
 }
 void op_rotate_columns(Context &c, int ch, const u64 *in, int n, u64 *out) { op_apply_galois(c, ch, in, n, 2ULL * c.N - 1, out); }
 
+// apply_galois on n ciphertexts scattered in memory (pointer table) -> packed out[n]
+static void apply_galois_gather(Context &c, int ch, const std::vector<const u64 *> &ins, u64 elt, u64 *out) {
+    auto it = c.ch[ch].glk.find(elt);
+    if (it == c.ch[ch].glk.end()) throw Error(-3, "Galois key not present");
+    const int k = c.k, n = (int)ins.size();
+    const size_t N = c.N;
+    const u64 m2 = 2ULL * N;
+    u64 einv = 0;
+    for (u64 x = 1; x < m2; x += 2)
+        if (((x * elt) & (m2 - 1)) == 1) { einv = x; break; }
+    for (int c0 = 0; c0 < n; c0 += c.chunk) {
+        const int m = std::min(c.chunk, n - c0);
+        std::vector<const u64 *> part(ins.begin() + c0, ins.begin() + c0 + m);
+        u64 *base = c.ws_alloc((size_t)m * 2 * k * N), *p1 = c.ws_alloc((size_t)m * k * N);
+        c.check(launch_galois_gather(upload_ptrs(c, part), base, p1, m, einv, k, c.logN, c.d_bc, c.stream), "galois");
+        op_key_switch(c, p1, (size_t)k * N, m, it->second->p, c.dm_galois, base, (size_t)2 * k * N, out + (size_t)c0 * 2 * k * N);
+    }
+    c.op_count[elt == m2 - 1 ? Context::OP_ROTATE_COLUMNS : Context::OP_ROTATE_ROWS_HOP] += (uint64_t)n;
+    if (c.trace_noise) // one record per ciphertext, as the unbatched path would have written
+        for (int i = 0; i < n; i++) {
+            c.op_count[Context::OP_ROTATE_ROWS_HOP] -= 1; // note() counts it again
+            c.note(Context::OP_ROTATE_ROWS_HOP, ch, 1, out + (size_t)i * 2 * k * N, ins[i]);
+        }
+}
+void op_rotate_rows_multi(Context &c, int ch, const std::vector<RotateJob> &jobs) {
+    const size_t ctw = c.ct_words();
+    struct State { std::vector<int> hops; size_t next; const u64 *cur; };
+    std::vector<State> st(jobs.size());
+    for (size_t j = 0; j < jobs.size(); j++) {
+        const RotateJob &job = jobs[j];
+        st[j].next = 0;
+        st[j].cur = job.src;
+        if (job.steps == 0) continue;
+        const u64 elt = galois_elt_from_step(c, job.steps);
+        if (c.ch[ch].glk.count(elt)) st[j].hops = {job.steps};
+        else {
+            for (int h : naf(job.steps))
+                if ((size_t)std::abs(h) != (c.N >> 1)) st[j].hops.push_back(h); // rotate_internal skips a hop of exactly N/2
+            if (naf(job.steps).size() == 1) throw Error(-3, "Galois key not present");
+        }
+    }
+    for (;;) {
+        // the hop value most jobs are waiting for next
+        std::map<int, std::vector<size_t>> want;
+        for (size_t j = 0; j < jobs.size(); j++)
+            if (st[j].next < st[j].hops.size()) want[st[j].hops[st[j].next]].push_back(j);
+        if (want.empty()) break;
+        auto best = want.begin();
+        for (auto it = want.begin(); it != want.end(); ++it)
+            if (it->second.size() > best->second.size()) best = it;
+        const std::vector<size_t> &js = best->second;
+        std::vector<const u64 *> ins;
+        for (size_t j : js) ins.push_back(st[j].cur);
+        u64 *out = c.ws_alloc(js.size() * ctw);
+        apply_galois_gather(c, ch, ins, galois_elt_from_step(c, best->first), out);
+        for (size_t i = 0; i < js.size(); i++) {
+            st[js[i]].cur = out + i * ctw;
+            st[js[i]].next++;
+        }
+    }
+    for (size_t j = 0; j < jobs.size(); j++)
+        if (st[j].cur != jobs[j].dst) {
+            CNHE_CUDA(cudaMemcpyAsync(jobs[j].dst, st[j].cur, ctw * 8, cudaMemcpyDeviceToDevice, c.stream));
+            c.note_copy(jobs[j].dst, st[j].cur);
+        }
+}
+
 void op_multiply_plain_dense(Context &c, int ch, const u64 *ct, int n, const u64 *plain, bool plain_per_ct, u64 *out) {
     const int k = c.k;
     const size_t N = c.N;
@@ -907,6 +1008,10 @@ void op_multiply_plain_dense_bcast(Context &c, int ch, const u64 *ct, const u64 
 }
 void op_encode(Context &c, int ch, const u64 *values, int n, int count, u64 *plain) {
     c.check(launch_encode_scatter(values, plain, n, count, c.d_index_map, c.logN, c.stream), "encode_scatter");
+    c.check(launch_ntt_inverse(plain, plain, n, c.logN, c.d_tabs, c.ch[ch].mod_id, 1, fp_range(c, c.ch[ch].mod_id, 1), c.stream), "ntt_inverse(t)");
+}
+void op_encode_onehot(Context &c, int ch, int n, int first_col, u64 *plain) {
+    c.check(launch_onehot_scatter(plain, n, first_col, c.d_index_map, c.logN, c.stream), "onehot_scatter");
     c.check(launch_ntt_inverse(plain, plain, n, c.logN, c.d_tabs, c.ch[ch].mod_id, 1, fp_range(c, c.ch[ch].mod_id, 1), c.stream), "ntt_inverse(t)");
 }
 void op_decode(Context &c, int ch, const u64 *plain, int n, u64 *values) {

@@ -139,6 +139,11 @@ struct Context {
     // pinned staging ring for small host->device uploads (pointer tables, weights, tiles): truly asynchronous copies
     unsigned char *stage_buf = nullptr;
     size_t stage_size = 0, stage_off = 0;
+    // the ring is cut into STAGE_PARTS parts; leaving a part records one event per channel stream, entering it waits for the events of
+    // its previous use (several parts ago: already complete in the steady state) -- no device-wide sync when the ring wraps
+    static constexpr int STAGE_PARTS = 8;
+    std::vector<cudaEvent_t> stage_ev; // [part][stream]
+    std::vector<char> stage_ev_set;
     void h2d(void *dst, const void *src, size_t bytes); // async on `stream`; `src` may be freed on return
 
     ~Context();
@@ -195,6 +200,12 @@ void op_key_switch(Context &c, const u64 *target, size_t target_stride, int n, c
 void op_apply_galois(Context &c, int ch, const u64 *in, int n, u64 elt, u64 *out);
 void op_rotate_rows(Context &c, int ch, const u64 *in, int n, int steps, u64 *out); // steps == 0 copies
 void op_rotate_columns(Context &c, int ch, const u64 *in, int n, u64 *out);
+// Many independent single-ciphertext row rotations with DIFFERENT step counts (Interleave / Stack / Duplicate rotate every vector by its
+// own offset): each job walks the hop sequence rotate_rows would take for it (exact key or NAF hops), and hops with the same Galois
+// element are batched across jobs into one key-switch wave.  Per ciphertext the operations and their order are exactly those of
+// op_rotate_rows, so the outputs are bit-identical.
+struct RotateJob { const u64 *src; int steps; u64 *dst; };
+void op_rotate_rows_multi(Context &c, int ch, const std::vector<RotateJob> &jobs);
 u64 galois_elt_from_step(const Context &c, int steps);
 // dense plaintext (coefficient form mod t, [n or 1][N]) times ciphertexts [n][2kN]
 void op_multiply_plain_dense(Context &c, int ch, const u64 *ct, int n, const u64 *plain, bool plain_per_ct, u64 *out);
@@ -202,6 +213,8 @@ void op_multiply_plain_dense_bcast(Context &c, int ch, const u64 *ct, const u64 
 // values [n][count] (mod t, device) -> plain [n][N] coefficient form
 void op_encode(Context &c, int ch, const u64 *values, int n, int count, u64 *plain);
 void op_decode(Context &c, int ch, const u64 *plain, int n, u64 *values);
+// plain[i] = BatchEncoder.Encode(e_(first_col + i)) for i < n, built on the device (the one-hot masks of ForceOutputInColumn)
+void op_encode_onehot(Context &c, int ch, int n, int first_col, u64 *plain);
 // plain [n][plain_stride] (first `coeffs` coefficients used) -> ct [n][2kN]; nonces nonce0..nonce0+n-1
 // reserve n consecutive encryption nonces of a channel (a secure channel re-keys from the OS before the 32-bit counter wraps)
 u64 take_nonces(Context &c, int ch, u64 n);

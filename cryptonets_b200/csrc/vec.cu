@@ -282,7 +282,10 @@ extern "C" int cnhe_raw_behz_floor(cnhe_ctx *h, int channel, uint64_t d, int n, 
 }
 extern "C" int cnhe_dev_copy(cnhe_ctx *h, uint64_t dst, uint64_t src, size_t words) {
     API_BEGIN(h)
-    CNHE_CUDA(cudaMemcpyAsync((void *)dst, (const void *)src, words * 8, cudaMemcpyDeviceToDevice, c.stream));
+    // the pointers may belong to any channel: order the copy after every channel's queued work and before anything queued later
+    c.join_streams();
+    CNHE_CUDA(cudaMemcpyAsync((void *)dst, (const void *)src, words * 8, cudaMemcpyDeviceToDevice, c.streams[0]));
+    c.fork_streams();
     API_END
 }
 extern "C" int cnhe_prof_enable(cnhe_ctx *h, int on) {
@@ -968,10 +971,14 @@ extern "C" int cnhe_vec_duplicate(cnhe_ctx *h, const cnhe_vec *a, uint64_t count
     alloc_channels(o);
     for (int ch = 0; ch < c.P; ch++) {
         c.set_channel(ch);
-        u64 *res = o->ptr(ch), *rotator = c.ws_alloc(ctw), *tmp = c.ws_alloc(ctw);
+        u64 *res = o->ptr(ch), *rotator = c.ws_alloc(ctw);
         CNHE_CUDA(cudaMemcpyAsync(res, a->ptr(ch), ctw * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(res, a->ptr(ch));
         const u64 *rot_src = a->ptr(ch);
         bool column_rotated = false;
+        // the count-1 rotations of the original (or of its column-rotated copy) are independent: queue them, execute them together
+        // (hops with the same Galois element share a key-switch wave), then add them in the reference's order (":1385-1402")
+        std::vector<RotateJob> jobs;
+        std::vector<u64 *> pieces;
         for (uint64_t i = 1; i < count; i++) {
             long long target = (long long)(i * shift);
             if (target * 2 >= (long long)N) {
@@ -982,9 +989,12 @@ extern "C" int cnhe_vec_duplicate(cnhe_ctx *h, const cnhe_vec *a, uint64_t count
                 }
                 target -= (long long)N / 2;
             }
-            op_rotate_rows(c, ch, rot_src, 1, -(int)target, tmp); // RotateRowsAndAdd(rotator, target, ...)
-            do_add(c, ch, res, tmp, res, ctw, 0);
+            u64 *tmp = c.ws_alloc(ctw);
+            jobs.push_back({rot_src, -(int)target, tmp}); // RotateRowsAndAdd(rotator, target, ...)
+            pieces.push_back(tmp);
         }
+        op_rotate_rows_multi(c, ch, jobs);
+        for (u64 *tmp : pieces) do_add(c, ch, res, tmp, res, ctw, 0);
     }
     *out = guard.release();
     API_END
@@ -1062,6 +1072,12 @@ static void interleave_channel(Context &c, int ch, const std::vector<const cnhe_
         c.sync();
         return pl;
     };
+    // phase 1: every vector's rotation (RotateRowsInplace of its own offset, ":625-660") -- independent of each other, so they are
+    // queued and executed together: hops with the same Galois element share one key-switch wave (same per-ciphertext operations
+    // and order as one rotate_rows call per vector, hence the same ciphertexts)
+    struct Placed { int kind, start_block, end_block, in_block; u64 *v; }; // kind 0 lower, 1 upper, 2 straddles into the next block, 3 straddles lower/upper
+    std::vector<Placed> placed(vecs.size());
+    std::vector<RotateJob> jobs;
     for (size_t kk = 0; kk < vecs.size(); kk++) {
         long long this_shift = (long long)shift * (long long)kk;
         if (this_shift < 0) this_shift = half + this_shift;
@@ -1069,28 +1085,42 @@ static void interleave_channel(Context &c, int ch, const std::vector<const cnhe_
         const int start_block = (int)(this_shift / block_size), end_block = (int)((this_shift + abs_shift) / block_size);
         u64 *v = c.ws_alloc(ctw);
         const u64 *src = vecs[kk]->block(ch, 0);
+        Placed &pl = placed[kk];
+        pl.start_block = start_block; pl.end_block = end_block; pl.in_block = in_block; pl.v = v;
         if (in_block == 0) {
             CNHE_CUDA(cudaMemcpyAsync(v, src, ctw * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(v, src);
-            lower[start_block].push_back(v);
+            pl.kind = 0;
         } else if (in_block + abs_shift < half) {
-            op_rotate_rows(c, ch, src, 1, -(int)this_shift, v);
-            lower[start_block].push_back(v);
+            jobs.push_back({src, -(int)this_shift, v});
+            pl.kind = 0;
         } else if (in_block >= half) {
-            op_rotate_rows(c, ch, src, 1, -(in_block - half), v);
-            if (start_block == end_block) {
-                upper[start_block].push_back(v);
-            } else { // straddles the upper half of this block and the lower half of the next
-                const int upper_part = (in_block + abs_shift) - block_size;
-                u64 *v2 = c.ws_alloc(ctw);
-                CNHE_CUDA(cudaMemcpyAsync(v2, v, ctw * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(v2, v);
-                op_multiply_plain_dense(c, ch, v, 1, ones_plain(upper_part), false, v);
-                do_add(c, ch, v2, v, v2, ctw, 1);
-                upper[start_block].push_back(v2);
-                if (end_block >= out_blocks) fail("not enough room for interleaving");
-                lower[end_block].push_back(v);
-            }
+            jobs.push_back({src, -(in_block - half), v});
+            pl.kind = start_block == end_block ? 1 : 2;
+        } else {
+            jobs.push_back({src, -in_block, v});
+            pl.kind = 3;
+        }
+    }
+    op_rotate_rows_multi(c, ch, jobs);
+    // phase 2: split the vectors that straddle a half / block boundary with a one-hot-prefix mask (":640-672") and file every piece
+    for (size_t kk = 0; kk < vecs.size(); kk++) {
+        const Placed &pl = placed[kk];
+        u64 *v = pl.v;
+        const int start_block = pl.start_block, end_block = pl.end_block, in_block = pl.in_block;
+        if (pl.kind == 0) {
+            lower[start_block].push_back(v);
+        } else if (pl.kind == 1) {
+            upper[start_block].push_back(v);
+        } else if (pl.kind == 2) { // straddles the upper half of this block and the lower half of the next
+            const int upper_part = (in_block + abs_shift) - block_size;
+            u64 *v2 = c.ws_alloc(ctw);
+            CNHE_CUDA(cudaMemcpyAsync(v2, v, ctw * 8, cudaMemcpyDeviceToDevice, c.stream)); c.note_copy(v2, v);
+            op_multiply_plain_dense(c, ch, v, 1, ones_plain(upper_part), false, v);
+            do_add(c, ch, v2, v, v2, ctw, 1);
+            upper[start_block].push_back(v2);
+            if (end_block >= out_blocks) fail("not enough room for interleaving");
+            lower[end_block].push_back(v);
         } else { // straddles lower and upper half of the same block
-            op_rotate_rows(c, ch, src, 1, -in_block, v);
             const int upper_part = (in_block + abs_shift) - half;
             if (upper_part > 0) {
                 u64 *v2 = c.ws_alloc(ctw);
@@ -1466,11 +1496,8 @@ extern "C" int cnhe_mat_mul_rowmajor_shard(cnhe_ctx *h, const cnhe_vec *const *r
             sum_slots_batched(c, ch, prod, m, CNHE_ALL_SLOTS);
             if (force_dense) {
                 // one-hot masks for columns r0..r0+m (EncryptedSealBfvMatrix.cs:96, AtomicSealBfvVector.cs:936-945)
-                std::vector<u64> onehot((size_t)m * N, 0);
-                for (int i = 0; i < m; i++) onehot[(size_t)i * N + (first_row + r0 + i)] = 1;
-                u64 *dv = c.ws_alloc((size_t)m * N), *masks = c.ws_alloc((size_t)m * N);
-                CNHE_CUDA(cudaMemcpyAsync(dv, onehot.data(), onehot.size() * 8, cudaMemcpyHostToDevice, c.stream));
-                op_encode(c, ch, dv, m, (int)N, masks);
+                u64 *masks = c.ws_alloc((size_t)m * N);
+                op_encode_onehot(c, ch, m, first_row + r0, masks); // built on the device (was a 134 MB pageable upload per 1024-row wave)
                 op_multiply_plain_dense(c, ch, prod, m, masks, true, prod);
                 std::vector<const u64 *> terms;
                 if (!first) terms.push_back(o->ptr(ch));

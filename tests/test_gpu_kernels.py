@@ -342,3 +342,43 @@ def test_persistent_and_per_polynomial_transforms_agree(pair, fwd, inv, monkeypa
     assert np.array_equal(eng.dev_download(o2, m * 2 * k * N).reshape(m, -1), want)
     eng.dev_free(a)
     eng.dev_free(o2)
+
+
+@pytest.mark.parametrize("split", ["1", "0"])
+def test_cta_pair_and_whole_polynomial_transforms_agree(pair, split, monkeypatch):
+    """N = 16384 runs on CTA pairs by default (two 8192-point halves, the cross-half stage on the way in / through distributed shared
+    memory on the way out); CNHE_NTT_SPLIT=0 keeps the one-CTA-per-polynomial kernels.  Both must give the oracle's words: plain
+    transforms out of place and IN PLACE (the pair reads both halves before either writes), the digit-cutting forward and the lazy
+    variants inside multiply + relinearise."""
+    eng, orc, name = pair
+    if eng.N != 16384:
+        pytest.skip("CTA pairs serve N = 16384 only")
+    monkeypatch.setenv("CNHE_NTT_SPLIT", split)
+    rng = np.random.default_rng(12)
+    N, k, kt = eng.N, eng.k, eng.k + eng.kb
+    tab = _mod_table(eng, orc)
+    n = 40 * kt + 5
+    polys = np.stack([rng.integers(0, tab[b % kt][0], N, dtype=np.uint64) for b in range(n)])
+    polys[0, :] = tab[0][0] - 1  # largest canonical input everywhere: the worst case of the magnitude schedule
+    d, out = eng.dev_from(polys), eng.dev_alloc(polys.size)
+    eng.raw_ntt(d, out, n, 0, kt, False)
+    got = eng.dev_download(out, polys.size).reshape(polys.shape)
+    for b in [0] + list(range(1, n, 41)) + [n - 1]:
+        p, o, oid = tab[b % kt]
+        assert np.array_equal(got[b], o.ntt(oid, polys[b])), b
+    eng.raw_ntt(d, d, n, 0, kt, False)  # in place
+    assert np.array_equal(eng.dev_download(d, polys.size).reshape(polys.shape), got)
+    eng.raw_ntt(d, d, n, 0, kt, True)
+    assert np.array_equal(eng.dev_download(d, polys.size).reshape(polys.shape), polys)
+    eng.raw_ntt(out, d, n, 0, kt, True)  # out of place
+    assert np.array_equal(eng.dev_download(d, polys.size).reshape(polys.shape), polys)
+    eng.dev_free(d)
+    eng.dev_free(out)
+    m = 3
+    _, cts = _fresh_cts(orc, m, 22)
+    a, o2 = eng.dev_from(cts), eng.dev_alloc(m * 2 * k * N)
+    eng.raw_multiply_relin(0, a, a, m, o2)
+    want = np.stack([orc.relinearize(orc.multiply(cts[i], cts[i])) for i in range(m)])
+    assert np.array_equal(eng.dev_download(o2, m * 2 * k * N).reshape(m, -1), want)
+    eng.dev_free(a)
+    eng.dev_free(o2)
