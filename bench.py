@@ -15,6 +15,7 @@ public API with host (pinned) ciphertext buffers; `roofline` is the NTT kernel f
 the library's stream."""
 import argparse
 import ctypes
+import gc
 import json
 import os
 import subprocess
@@ -238,6 +239,17 @@ def run_reference(args):
     }))
 
 
+
+def quiesce_python_gc():
+    """The cyclic collector's generation-2 pass walks the whole heap that torch, numpy and the network leave behind: 30-35 ms on the GPU
+    box, about once every nine CryptoNets batches -- longer than a batch of device time, so the GPU ran dry behind it
+    (profiles/r02_e2e_gc.txt).  Everything allocated during set-up is parked in the permanent generation; what the steps allocate is
+    still collected (young generations), a full pass now has almost nothing to walk."""
+    gc.collect()
+    gc.freeze()
+    return "gc.freeze() after set-up"
+
+
 # --------------------------------------------------------------------------------------------------------- B200 arm
 def build_network(factory):
     """The CryptoNets-MNIST layer chain without its reader/encrypt layers (those sit before the timer)."""
@@ -321,6 +333,7 @@ def run_b200(args):
         gatherer.gather([v.vec for v in out_.vectors])
         return out_
 
+    host_gc = quiesce_python_gc()
     for _ in range(args.warmup):
         step_resident().Dispose()
     barrier()
@@ -375,26 +388,29 @@ def run_b200(args):
         vecs = eng.import_raw_many(host_in.data_ptr(), 784, 1, BATCH, 16.0)  # asynchronous: runs on the library's upload stream
         return B200BfvMatrix(f, [B200BfvVector(f, v) for v in vecs], EMatrixFormat.ColumnMajor, CopyVectors=False)
 
-    host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
+    depth = max(1, int(os.environ.get("CNHE_E2E_DEPTH", "2")))  # batches queued ahead of the one whose scores the host waits for
+    host_outs = [host_out] + [torch.empty_like(host_out).pin_memory() for _ in range(depth)]
 
     def e2e_run(steps):
-        """`steps` batches: host ciphertexts in, score ciphertexts back on the host, pipelined one batch deep the way a serving loop
-        is: batch i+1 is uploaded and queued while batch i computes; the host only ever waits for batch i-1's scores."""
+        """`steps` batches: host ciphertexts in, score ciphertexts back on the host, pipelined the way a serving loop is: batch i+1 is
+        uploaded and queued while batch i computes, and the host waits for the scores of batch i-depth, so that a host-side hiccup shorter
+        than `depth` batches of device time never starves the GPU.  Every batch's scores are on the host before the timed region ends."""
         nxt = e2e_import()
-        pending = None
+        pending = []
         for s_ in range(steps):
             cur = nxt
             out = forward(layers, cur)
             cur.Dispose()
             gatherer.gather([v.vec for v in out.vectors])  # NVLink all-gather of this batch's scores, queued behind its kernels
-            ticket = eng.export_raw_many_async([v.vec for v in out.vectors], host_outs[s_ & 1].data_ptr())
+            ticket = eng.export_raw_many_async([v.vec for v in out.vectors], host_outs[s_ % (depth + 1)].data_ptr())
             out.Dispose()  # stream-ordered: released after the copies above
             if s_ + 1 < steps:
                 nxt = e2e_import()
-            if pending is not None:
-                eng.export_wait(pending)
-            pending = ticket
-        eng.export_wait(pending)
+            pending.append(ticket)
+            if len(pending) > depth:
+                eng.export_wait(pending.pop(0))
+        for ticket in pending:
+            eng.export_wait(ticket)
         gatherer.finish()
 
     eng.set_option("multi_stream", int(os.environ.get("CNHE_E2E_MULTI_STREAM", "1")))
@@ -439,7 +455,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic MNIST-shaped uint8 images (80% zeros), shipped CryptoNets weights, device-generated keys",
             "config": cpu_line_config(len(primes), world),
-            "clocks": clocks, "gpu_launches": int(launches), "numa": {k_: v for k_, v in numa.items() if k_ != "previous_cpus"},
+            "clocks": clocks, "gpu_launches": int(launches), "numa": {k_: v for k_, v in numa.items() if k_ != "previous_cpus"}, "host_gc": host_gc,
             "collective": {"op": "all_gather_into_tensor (NCCL) of the score ciphertexts, every step, inside both timed regions",
                            "bytes_per_rank_per_step": int(eng.P * 10 * eng.ct_words * 8)},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(host_in.numel() * 8), "d2h_bytes_per_step": int(host_out.numel() * 8)},
@@ -524,6 +540,7 @@ def run_lola(args):
         torch.cuda.synchronize()
 
     eng.set_option("multi_stream", 0)
+    quiesce_python_gc()
     for _ in range(args.warmup):
         forward(xm).Dispose()
     barrier()

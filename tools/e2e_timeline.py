@@ -1,5 +1,5 @@
 """Host-side breakdown of the pipelined end-to-end loop of bench.py (import / forward issue / export issue / wait), per step."""
-import json, os, sys, time
+import gc, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
@@ -30,6 +30,21 @@ def imp():
 
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+# GC=off disables the cyclic collector in the loop, GC=freeze parks everything allocated so far in the permanent generation; every
+# collection is timed (a full collection over the heap that torch and the network leave behind costs tens of milliseconds)
+_gc_t0 = [0.0]
+gc_log = []
+def _gc_cb(phase, info):
+    if phase == "start":
+        _gc_t0[0] = time.perf_counter()
+    else:
+        gc_log.append((info["generation"], round((time.perf_counter() - _gc_t0[0]) * 1e3, 2)))
+gc.callbacks.append(_gc_cb)
+if os.environ.get("GC") == "off":
+    gc.disable()
+elif os.environ.get("GC") == "freeze":
+    gc.collect()
+    gc.freeze()
 rows = []
 t_start = time.perf_counter()
 nxt = imp()
@@ -54,4 +69,5 @@ for s in range(steps):
     rows.append([round((b - a) * 1e3, 1) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, t4))])
 eng.export_wait(pending)
 total = (time.perf_counter() - t_start) * 1e3
+print("gc (generation, ms):", [g for g in gc_log if g[1] > 1.0], "collections:", len(gc_log), file=sys.stderr)
 print(json.dumps({"steps": steps, "ms_per_step": round(total / steps, 2), "forward_export_import_wait_ms": rows}))
