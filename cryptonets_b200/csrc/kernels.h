@@ -182,6 +182,13 @@ enum SampleKind { SAMPLE_TERNARY = 0, SAMPLE_NOISE = 1, SAMPLE_UNIFORM = 2 };
 // limbs = ceil(bits(q)/8); needs K*254*255 < 2^31
 cudaError_t launch_mac_dense_imma(const u64 *const *in_ptrs, const void *wfrag, const void *wfrag2, const u64 *bias, int K, int M, int limbs,
                                   u64 *const *out_ptrs, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
+// the same layer on tcgen05 (mac_umma.cu): M <= 128 outputs, |w| <= 127, the packed weight matrix resident in shared memory.
+// wpack = mac_dense_umma_weight_bytes(K) bytes in A-operand order (mac_dense_umma_pack, host side)
+bool mac_dense_umma_fits(int K, int M, int limbs);
+size_t mac_dense_umma_weight_bytes(int K);
+void mac_dense_umma_pack(const signed char *w, int M, int K, unsigned char *out);
+cudaError_t launch_mac_dense_umma(const u64 *const *in_ptrs, const void *wpack, const u64 *bias, int K, int M, int limbs, u64 *const *out_ptrs, int k,
+                                  int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
 cudaError_t launch_sample(u64 *out, int n, int kind, const RngKey &seed, u64 stream0, u64 stream_step, int k, int logn, const BehzConst *bc, cudaStream_t s);
 // plain[i][index_map[j]] = values[i][j]  (j < count), zero elsewhere
 cudaError_t launch_encode_scatter(const u64 *values, u64 *plain, int n, int count, const u32 *index_map, int logn, cudaStream_t s);

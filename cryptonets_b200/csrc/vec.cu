@@ -1287,8 +1287,20 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
         const int limbs = (maxbits + 7) / 8;
         const bool imma = order_rows == 1 && wmax <= 254.0 && K >= 32 && M >= 8 && limbs >= 5 && limbs <= 7 && (double)K * 254.0 * 255.0 < 2147483648.0 &&
                           !getenv("CNHE_MAC_NO_IMMA") && !getenv("CNHE_MAC_INT");
-        const void *d_wfrag = nullptr, *d_wfrag2 = nullptr;
-        if (imma) {
+        // ... on tcgen05 when the layer fits its shape (mac_umma.cu): weights within one signed byte, at most 128 outputs
+        const bool umma = imma && wmax <= 127.0 && mac_dense_umma_fits(K, M, limbs) && !getenv("CNHE_MAC_NO_UMMA");
+        const void *d_wfrag = nullptr, *d_wfrag2 = nullptr, *d_wpack = nullptr;
+        if (umma) {
+            std::vector<signed char> w8((size_t)M * K, 0);
+            for (int m = 0; m < M; m++)
+                for (int kk = 0; kk < K; kk++)
+                    if (grows[kk] >= 0) w8[(size_t)m * K + kk] = (signed char)(int)wdh[(size_t)m * K + kk];
+            std::vector<unsigned char> packed(mac_dense_umma_weight_bytes(K));
+            mac_dense_umma_pack(w8.data(), M, K, packed.data());
+            u64 *buf = c.ws_alloc((packed.size() + 7) / 8);
+            c.h2d(buf, packed.data(), packed.size());
+            d_wpack = buf;
+        } else if (imma) {
             const int mtiles = (M + 15) / 16, chunks = (K + 31) / 32;
             const size_t fwords = (size_t)mtiles * chunks * 32 * 4;
             std::vector<uint32_t> frag(2 * fwords, 0); // W1 = clamp(W, +-127) then the residual W2 = W - W1
@@ -1338,7 +1350,12 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
             double used = 0;
             for (auto &t : tiles) { int kk = 0; for (int j = 0; j < K; j++) kk += grows[(size_t)t.gather_row * K + j] >= 0; used += kk + t.n_out; }
             c.prof_begin(4, used * 8.0 * c.ct_words());
-            if (imma) {
+            if (umma) {
+                std::vector<const u64 *> ipg(K);
+                for (int kk = 0; kk < K; kk++) ipg[kk] = ip[grows[kk] < 0 ? 0 : grows[kk]]; // padded taps carry weight 0
+                c.check(launch_mac_dense_umma(upload_ptrs(c, ipg), d_wpack, d_bias, K, M, limbs, upload_ptrs_mut(c, op), c.k, c.logN, c.d_bc, c.ch[ch].pc, c.stream),
+                        "mac_dense_umma");
+            } else if (imma) {
                 std::vector<const u64 *> ipg(K);
                 for (int kk = 0; kk < K; kk++) ipg[kk] = ip[grows[kk] < 0 ? 0 : grows[kk]]; // padded taps carry weight 0
                 c.check(launch_mac_dense_imma(upload_ptrs(c, ipg), d_wfrag, d_wfrag2, d_bias, K, M, limbs, upload_ptrs_mut(c, op), c.k, c.logN, c.d_bc, c.ch[ch].pc,

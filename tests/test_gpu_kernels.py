@@ -264,17 +264,23 @@ def test_mac_layer_and_square_layer(pair):
         assert sq[i].scale == 32.0 * 32.0
 
 
-def test_dense_layer_on_tensor_cores(pair):
-    """Dense layer (all outputs read the same K inputs, |w| <= 254): the exact 8-bit-limb integer GEMM of mac_imma.cu must give
-    the same ciphertext words as the oracle's 128-bit multiply-accumulate -- odd M and K (padding inside the m16/k32 tiles), a padded
-    tap, zero weights, extreme weights +-127 and maximal residues, bias on coefficient 0 of c0; and the same layer with the tensor-core
-    path disabled."""
+@pytest.mark.parametrize("shape", ["wide-21x43", "byte-21x43", "byte-100x70", "byte-128x33"])
+def test_dense_layer_on_tensor_cores(pair, shape):
+    """Dense layer (all outputs read the same K inputs): the exact 8-bit-limb integer GEMM must give the same ciphertext words as the
+    oracle's 128-bit multiply-accumulate -- odd M and K (padding inside the tiles), a padded tap, zero weights, extreme weights and
+    maximal residues, bias on coefficient 0 of c0.  "wide" weights (|w| <= 254) take mma.sync (mac_imma.cu: W = W1 + W2); weights
+    within a signed byte take tcgen05.mma with TMEM accumulators (mac_umma.cu), up to 128 outputs and several 32-tap chunks.  Every
+    case is repeated with the tcgen05 path off (mma.sync) and with both off (FP64 scalar MAC)."""
     import os
     from cryptonets_b200.engine import DENSE, SPARSE
     eng, orc, name = pair
     N = eng.N
     rng = np.random.default_rng(23)
-    n_in, M, K = 45, 21, 43
+    wide = shape.startswith("wide")
+    M, K = [int(x) for x in shape.split("-")[1].split("x")]
+    if M > 21 and name != "default4096":
+        pytest.skip("the larger shapes run on the smallest ring (oracle time)")
+    n_in = K + 2
     vals, cts = _fresh_cts(orc, n_in, 12, nonce0=900)
     q = np.array(orc.q, dtype=np.uint64)
     cts = np.array(cts, dtype=np.uint64).reshape(n_in, 2, len(q), N)
@@ -288,7 +294,8 @@ def test_dense_layer_on_tensor_cores(pair):
     w = rng.integers(-127, 128, (M, K)).astype(np.float64)
     w[:, 0] = 127
     w[:, 1] = -127
-    w[5, 3], w[6, 40], w[20, 42] = 254, -254, 165  # beyond 8 bits: carried by the residual fragment
+    if wide:
+        w[5, 3], w[6, 40], w[20, 42] = 254, -254, 165  # beyond 8 bits: carried by the residual fragment
     w[3, :] = 0
     w[3, 2] = 1
     bias = rng.integers(-1000, 1000, M).astype(np.float64)
@@ -301,13 +308,14 @@ def test_dense_layer_on_tensor_cores(pair):
     outs = eng.layer_conv_dense(ins, gather, wv, bv, M, K)
     for m in range(M):
         assert np.array_equal(outs[m].export_raw(0, 0), want[m]), m
-    os.environ["CNHE_MAC_NO_IMMA"] = "1"
-    try:
-        outs2 = eng.layer_conv_dense(ins, gather, wv, bv, M, K)
-    finally:
-        del os.environ["CNHE_MAC_NO_IMMA"]
-    for m in range(M):
-        assert np.array_equal(outs2[m].export_raw(0, 0), want[m]), m
+    for off in ("CNHE_MAC_NO_UMMA", "CNHE_MAC_NO_IMMA"):
+        os.environ[off] = "1"
+        try:
+            outs2 = eng.layer_conv_dense(ins, gather, wv, bv, M, K)
+        finally:
+            del os.environ[off]
+        for m in range(M):
+            assert np.array_equal(outs2[m].export_raw(0, 0), want[m]), (off, m)
 
 
 @pytest.mark.parametrize("fwd,inv", [("1", "1"), ("0", "0"), ("1", "0"), ("0", "1")])
