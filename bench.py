@@ -388,13 +388,14 @@ def run_b200(args):
         vecs = eng.import_raw_many(host_in.data_ptr(), 784, 1, BATCH, 16.0)  # asynchronous: runs on the library's upload stream
         return B200BfvMatrix(f, [B200BfvVector(f, v) for v in vecs], EMatrixFormat.ColumnMajor, CopyVectors=False)
 
-    depth = max(1, int(os.environ.get("CNHE_E2E_DEPTH", "2")))  # batches queued ahead of the one whose scores the host waits for
+    depth = max(1, int(os.environ.get("CNHE_E2E_DEPTH", "1")))  # batches queued ahead of the one whose scores the host waits for (2 measured slower: the
+    # upload of batch i+1 then has to wait for a slot of batch i-2 and no longer hides under batch i-1: tools/e2e_timeline.py, DEPTH=1|2)
     host_outs = [host_out] + [torch.empty_like(host_out).pin_memory() for _ in range(depth)]
 
     def e2e_run(steps):
         """`steps` batches: host ciphertexts in, score ciphertexts back on the host, pipelined the way a serving loop is: batch i+1 is
-        uploaded and queued while batch i computes, and the host waits for the scores of batch i-depth, so that a host-side hiccup shorter
-        than `depth` batches of device time never starves the GPU.  Every batch's scores are on the host before the timed region ends."""
+        uploaded and queued while batch i computes, and the host waits for the scores of batch i-depth.  Every batch's scores are on the
+        host before the timed region ends."""
         nxt = e2e_import()
         pending = []
         for s_ in range(steps):

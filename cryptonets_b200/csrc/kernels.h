@@ -184,11 +184,15 @@ cudaError_t launch_mac_dense_imma(const u64 *const *in_ptrs, const void *wfrag, 
                                   u64 *const *out_ptrs, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
 // the same layer on tcgen05 (mac_umma.cu): M <= 128 outputs, |w| <= 127, the packed weight matrix resident in shared memory.
 // wpack = mac_dense_umma_weight_bytes(K) bytes in A-operand order (mac_dense_umma_pack, host side)
+// in_ptrs: K + n_extra source polynomials.  The first K must be evenly spaced in memory (in_ptrs[i] = in_ptrs[0] + i * stride: the outputs
+// of the previous layer's slab) -- they are fetched through one 2-D tensor map, 32 taps x 32 words per request; the n_extra taps behind
+// them (the W2 columns) may point anywhere and are fetched one bulk copy each.  Their weights start at column ceil32(K) of wpack.
 bool mac_dense_umma_fits(int K, int M, int limbs);
+cudaError_t make_word_map_2d(void *map, const u64 *base, size_t inner_words, size_t rows, size_t row_stride, unsigned box_words, unsigned box_rows);
 size_t mac_dense_umma_weight_bytes(int K);
 void mac_dense_umma_pack(const signed char *w, int M, int K, unsigned char *out);
-cudaError_t launch_mac_dense_umma(const u64 *const *in_ptrs, const void *wpack, const u64 *bias, int K, int M, int limbs, u64 *const *out_ptrs, int k,
-                                  int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
+cudaError_t launch_mac_dense_umma(const u64 *const *in_ptrs, const u64 *affine_base, size_t affine_stride_words, int K, int n_extra, const void *wpack,
+                                  const u64 *bias, int M, int limbs, u64 *const *out_ptrs, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
 cudaError_t launch_sample(u64 *out, int n, int kind, const RngKey &seed, u64 stream0, u64 stream_step, int k, int logn, const BehzConst *bc, cudaStream_t s);
 // plain[i][index_map[j]] = values[i][j]  (j < count), zero elsewhere
 cudaError_t launch_encode_scatter(const u64 *values, u64 *plain, int n, int count, const u32 *index_map, int logn, cudaStream_t s);

@@ -1287,16 +1287,40 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
         const int limbs = (maxbits + 7) / 8;
         const bool imma = order_rows == 1 && wmax <= 254.0 && K >= 32 && M >= 8 && limbs >= 5 && limbs <= 7 && (double)K * 254.0 * 255.0 < 2147483648.0 &&
                           !getenv("CNHE_MAC_NO_IMMA") && !getenv("CNHE_MAC_INT");
-        // ... on tcgen05 when the layer fits its shape (mac_umma.cu): weights within one signed byte, at most 128 outputs
-        const bool umma = imma && wmax <= 127.0 && mac_dense_umma_fits(K, M, limbs) && !getenv("CNHE_MAC_NO_UMMA");
+        // ... on tcgen05 when the layer fits its shape (mac_umma.cu): at most 128 outputs, one signed byte per weight.  Weights beyond
+        // +-127 (up to +-254) are split W = W1 + W2 as above, but W2 is sparse (CryptoNets' 845 -> 100 layer: 48 of 84 500 weights, in 31
+        // columns), so it rides on extra taps: every column that holds such a weight is appended once more with W2 as its weights
+        std::vector<int> extra_taps;
+        for (int kk = 0; kk < K && imma; kk++) {
+            bool big = false;
+            for (int m = 0; m < M; m++) big = big || std::fabs(wdh[(size_t)m * K + kk]) > 127.0;
+            if (big && grows[kk] >= 0) extra_taps.push_back(kk);
+        }
+        // weight columns: taps 0..K-1, zero padding to the next multiple of 32 (the extra taps start a fresh MMA chunk), then the W2 columns
+        const int K_pad = (K + 31) & ~31, n_extra = (int)extra_taps.size(), K_ext = K_pad + n_extra;
+        // the K taps must be evenly spaced in memory (one 2-D tensor map fetches 32 of them per request): true when the layer reads the
+        // previous layer's output slab in order, which is how the dense layers are fed
+        bool affine = imma && bl == 1 && K >= 2;
+        long long tap_stride = 0;
+        if (affine) {
+            auto tap_ptr = [&](int kk) { return in[grows[kk] < 0 ? 0 : grows[kk]]->block(ch, 0); };
+            tap_stride = tap_ptr(1) - tap_ptr(0);
+            for (int kk = 0; kk < K && affine; kk++) affine = grows[kk] >= 0 && tap_ptr(kk) == tap_ptr(0) + (long long)kk * tap_stride;
+            affine = affine && tap_stride > 0 && tap_stride % 2 == 0;
+        }
+        const bool umma = affine && mac_dense_umma_fits(K_ext, M, limbs) && (double)K_ext * 127.0 * 255.0 < 2147483648.0 && !getenv("CNHE_MAC_NO_UMMA");
         const void *d_wfrag = nullptr, *d_wfrag2 = nullptr, *d_wpack = nullptr;
         if (umma) {
-            std::vector<signed char> w8((size_t)M * K, 0);
-            for (int m = 0; m < M; m++)
-                for (int kk = 0; kk < K; kk++)
-                    if (grows[kk] >= 0) w8[(size_t)m * K + kk] = (signed char)(int)wdh[(size_t)m * K + kk];
-            std::vector<unsigned char> packed(mac_dense_umma_weight_bytes(K));
-            mac_dense_umma_pack(w8.data(), M, K, packed.data());
+            std::vector<signed char> w8((size_t)M * K_ext, 0);
+            for (int m = 0; m < M; m++) {
+                for (int kk = 0; kk < K; kk++) w8[(size_t)m * K_ext + kk] = (signed char)std::max(-127, std::min(127, (int)wdh[(size_t)m * K + kk]));
+                for (int j = 0; j < n_extra; j++) {
+                    const int w = (int)wdh[(size_t)m * K + extra_taps[j]];
+                    w8[(size_t)m * K_ext + K_pad + j] = (signed char)(w - std::max(-127, std::min(127, w)));
+                }
+            }
+            std::vector<unsigned char> packed(mac_dense_umma_weight_bytes(K_ext));
+            mac_dense_umma_pack(w8.data(), M, K_ext, packed.data());
             u64 *buf = c.ws_alloc((packed.size() + 7) / 8);
             c.h2d(buf, packed.data(), packed.size());
             d_wpack = buf;
@@ -1351,9 +1375,11 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
             for (auto &t : tiles) { int kk = 0; for (int j = 0; j < K; j++) kk += grows[(size_t)t.gather_row * K + j] >= 0; used += kk + t.n_out; }
             c.prof_begin(4, used * 8.0 * c.ct_words());
             if (umma) {
-                std::vector<const u64 *> ipg(K);
-                for (int kk = 0; kk < K; kk++) ipg[kk] = ip[grows[kk] < 0 ? 0 : grows[kk]]; // padded taps carry weight 0
-                c.check(launch_mac_dense_umma(upload_ptrs(c, ipg), d_wpack, d_bias, K, M, limbs, upload_ptrs_mut(c, op), c.k, c.logN, c.d_bc, c.ch[ch].pc, c.stream),
+                std::vector<const u64 *> ipg(K + n_extra);
+                for (int kk = 0; kk < K; kk++) ipg[kk] = ip[grows[kk]];
+                for (int j = 0; j < n_extra; j++) ipg[K + j] = ip[grows[extra_taps[j]]];
+                c.check(launch_mac_dense_umma(upload_ptrs(c, ipg), ipg[0], (size_t)tap_stride, K, n_extra, d_wpack, d_bias, M, limbs, upload_ptrs_mut(c, op), c.k,
+                                              c.logN, c.d_bc, c.ch[ch].pc, c.stream),
                         "mac_dense_umma");
             } else if (imma) {
                 std::vector<const u64 *> ipg(K);

@@ -264,20 +264,22 @@ def test_mac_layer_and_square_layer(pair):
         assert sq[i].scale == 32.0 * 32.0
 
 
-@pytest.mark.parametrize("shape", ["wide-21x43", "byte-21x43", "byte-100x70", "byte-128x33"])
-def test_dense_layer_on_tensor_cores(pair, shape):
+@pytest.mark.parametrize("shape", ["gather-wide-21x43", "slab-wide-21x43", "slab-byte-21x43", "slab-byte-100x70", "slab-byte-128x33"])
+def test_dense_layer_on_tensor_cores(pair, shape, capfd):
     """Dense layer (all outputs read the same K inputs): the exact 8-bit-limb integer GEMM must give the same ciphertext words as the
-    oracle's 128-bit multiply-accumulate -- odd M and K (padding inside the tiles), a padded tap, zero weights, extreme weights and
-    maximal residues, bias on coefficient 0 of c0.  "wide" weights (|w| <= 254) take mma.sync (mac_imma.cu: W = W1 + W2); weights
-    within a signed byte take tcgen05.mma with TMEM accumulators (mac_umma.cu), up to 128 outputs and several 32-tap chunks.  Every
-    case is repeated with the tcgen05 path off (mma.sync) and with both off (FP64 scalar MAC)."""
+    oracle's 128-bit multiply-accumulate -- odd M and K (padding inside the tiles), zero weights, extreme weights and maximal residues,
+    bias on coefficient 0 of c0.  "gather": inputs scattered in memory, permuted, one padded tap -> mma.sync (mac_imma.cu).  "slab": the
+    inputs are consecutive ciphertexts of one allocation read in order, as a dense layer is fed by the layer before it -> tcgen05.mma with
+    TMEM accumulators and TMA loads (mac_umma.cu), up to 128 outputs, several 32-tap chunks, and ("wide", |w| <= 254) the W2 columns as
+    extra taps.  Every case is repeated with the tcgen05 path off and with both tensor-core paths off (FP64 scalar MAC)."""
     import os
     from cryptonets_b200.engine import DENSE, SPARSE
     eng, orc, name = pair
     N = eng.N
     rng = np.random.default_rng(23)
-    wide = shape.startswith("wide")
-    M, K = [int(x) for x in shape.split("-")[1].split("x")]
+    feed, kind, dims = shape.split("-")
+    wide = kind == "wide"
+    M, K = [int(x) for x in dims.split("x")]
     if M > 21 and name != "default4096":
         pytest.skip("the larger shapes run on the smallest ring (oracle time)")
     n_in = K + 2
@@ -287,9 +289,13 @@ def test_dense_layer_on_tensor_cores(pair, shape):
     cts[0] = (q - 1)[None, :, None]                       # every word of input 0 at its maximum
     cts[1, :, :, ::2] = (q - 1)[None, :, None]
     cts = cts.reshape(n_in, -1)
-    ins = [eng.import_raw(cts[i], 1, N, 4.0) for i in range(n_in)]
-    row = rng.permutation(n_in)[:K].astype(np.int32)
-    row[7] = -1                                           # one padded tap
+    if feed == "slab":
+        ins = eng.import_raw_many(cts, n_in, 1, N, 4.0)   # one allocation, evenly spaced
+        row = np.arange(K, dtype=np.int32)                # taps 0..K-1 in order (input 0: maximal words)
+    else:
+        ins = [eng.import_raw(cts[i], 1, N, 4.0) for i in range(n_in)]
+        row = rng.permutation(n_in)[:K].astype(np.int32)
+        row[7] = -1                                       # one padded tap
     gather = np.tile(row, (M, 1)).astype(np.int32)
     w = rng.integers(-127, 128, (M, K)).astype(np.float64)
     w[:, 0] = 127
@@ -305,7 +311,15 @@ def test_dense_layer_on_tensor_cores(pair, shape):
     wres = np.where(w < 0, w + t, w).astype(np.uint64)
     bres = np.where(bias * 4 < 0, bias * 4 + t, bias * 4).astype(np.uint64)
     want = orc.mac_layer(cts, gather, wres, bres, M, K, threads=4).reshape(M, -1)
-    outs = eng.layer_conv_dense(ins, gather, wv, bv, M, K)
+    os.environ["CNHE_UMMA_PROF"] = "1"  # the tcgen05 launcher then reports itself on stderr
+    capfd.readouterr()
+    try:
+        outs = eng.layer_conv_dense(ins, gather, wv, bv, M, K)
+        eng.sync()
+    finally:
+        del os.environ["CNHE_UMMA_PROF"]
+    served = "[umma K=" in capfd.readouterr().err
+    assert served == (feed == "slab"), "wrong kernel served the layer"
     for m in range(M):
         assert np.array_equal(outs[m].export_raw(0, 0), want[m]), m
     for off in ("CNHE_MAC_NO_UMMA", "CNHE_MAC_NO_IMMA"):

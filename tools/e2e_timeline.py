@@ -18,7 +18,8 @@ eng.set_option("multi_stream", int(os.environ.get("MS", "1")))
 if os.environ.get("CHUNK"):
     eng.set_option("chunk", int(os.environ["CHUNK"]))
 host_in = torch.empty(eng.P * 784 * eng.ct_words, dtype=torch.int64).pin_memory()
-host_outs = [torch.empty(eng.P * 10 * eng.ct_words, dtype=torch.int64).pin_memory() for _ in range(2)]
+DEPTH = int(os.environ.get("DEPTH", "1"))  # batches queued ahead of the one the host waits for
+host_outs = [torch.empty(eng.P * 10 * eng.ct_words, dtype=torch.int64).pin_memory() for _ in range(DEPTH + 1)]
 eng.export_raw_many([v.vec for v in xm.vectors], host_in.data_ptr())
 
 
@@ -48,7 +49,7 @@ elif os.environ.get("GC") == "freeze":
 rows = []
 t_start = time.perf_counter()
 nxt = imp()
-pending = None
+pending = []
 for s in range(steps):
     t0 = time.perf_counter()
     cur = nxt
@@ -56,18 +57,19 @@ for s in range(steps):
     if cur is not None:
         cur.Dispose()
     t1 = time.perf_counter()
-    ticket = eng.export_raw_many_async([v.vec for v in out.vectors], host_outs[s & 1].data_ptr())
+    ticket = eng.export_raw_many_async([v.vec for v in out.vectors], host_outs[s % (DEPTH + 1)].data_ptr())
     out.Dispose()
     t2 = time.perf_counter()
     if s + 1 < steps:
         nxt = imp()
     t3 = time.perf_counter()
-    if pending is not None:
-        eng.export_wait(pending)
+    pending.append(ticket)
+    if len(pending) > DEPTH:
+        eng.export_wait(pending.pop(0))
     t4 = time.perf_counter()
-    pending = ticket
     rows.append([round((b - a) * 1e3, 1) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, t4))])
-eng.export_wait(pending)
+for ticket in pending:
+    eng.export_wait(ticket)
 total = (time.perf_counter() - t_start) * 1e3
 print("gc (generation, ms):", [g for g in gc_log if g[1] > 1.0], "collections:", len(gc_log), file=sys.stderr)
 print(json.dumps({"steps": steps, "ms_per_step": round(total / steps, 2), "forward_export_import_wait_ms": rows}))
