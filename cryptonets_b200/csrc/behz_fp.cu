@@ -228,43 +228,63 @@ __device__ __forceinline__ ulonglong2 ldcs2(const u64 *p) { // streaming (evict-
     asm volatile("ld.global.cs.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
     return v;
 }
-template <bool LAZY, int UNR>
+// CT ciphertexts per thread: the two key words of a (digit, residue, coefficient pair) are fetched from L2 once and used for all of
+// them.  With one ciphertext per thread the kernel moved 48 bytes through L2 for every 16 bytes of the digit stream and sat on the L2
+// bandwidth (3.9 TB/s of HBM reads = 11.7 TB/s out of L2); with four it is 24 bytes.
+template <bool LAZY, int UNR, int CT>
 __global__ void __launch_bounds__(256) k_ks_mac_fp(const u64 *__restrict__ digits, const u64 *__restrict__ key, u64 *__restrict__ acc, int n, int D,
                                                   int logn, const __grid_constant__ BehzConstF F) {
     const int N = 1 << logn, k = F.k;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= ((size_t)n * k) << (logn - 1)) return;
+    const int n_groups = (n + CT - 1) / CT;
+    if (gid >= ((size_t)n_groups * k) << (logn - 1)) return;
     const int x = (int)(gid & (N / 2 - 1)) * 2;
-    const int l = (int)((gid >> (logn - 1)) % k), c = (int)((gid >> (logn - 1)) / k);
+    const int l = (int)((gid >> (logn - 1)) % k), c0 = (int)((gid >> (logn - 1)) / k) * CT;
     const double p = F.qd[l], pinv = F.qinv[l];
-    const size_t kpoly = (size_t)k * N, kstride = (size_t)2 * k * N;
-    const u64 *dg = digits + ((size_t)c * k + l) * D * N + x;
+    const size_t kpoly = (size_t)k * N, kstride = (size_t)2 * k * N, cstride = (size_t)k * D * N;
+    const u64 *dg = digits + ((size_t)c0 * k + l) * D * N + x;
     const u64 *k0 = key + (size_t)l * N + x;
-    double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0; // a<key poly><coefficient>
+    double a[CT][4]; // [ciphertext][key poly * 2 + coefficient]
+#pragma unroll
+    for (int ci = 0; ci < CT; ci++) a[ci][0] = a[ci][1] = a[ci][2] = a[ci][3] = 0.0;
 #pragma unroll UNR
     for (int dd = 0; dd < D; dd++) {
-        const ulonglong2 vu = ldcs2(dg + (size_t)dd * N);
+        ulonglong2 vu[CT];
+#pragma unroll
+        for (int ci = 0; ci < CT; ci++)
+            vu[ci] = c0 + ci < n ? ldcs2(dg + (size_t)ci * cstride + (size_t)dd * N) : make_ulonglong2(0, 0);
         const ulonglong2 w0u = __ldg(reinterpret_cast<const ulonglong2 *>(k0 + (size_t)dd * kstride));
         const ulonglong2 w1u = __ldg(reinterpret_cast<const ulonglong2 *>(k0 + (size_t)dd * kstride + kpoly));
-        const double v0 = LAZY ? __longlong_as_double((long long)vu.x) : u2d(vu.x), v1 = LAZY ? __longlong_as_double((long long)vu.y) : u2d(vu.y);
-        a00 = __dadd_rn(a00, fmodmul(v0, u2d(w0u.x), p, pinv));
-        a01 = __dadd_rn(a01, fmodmul(v1, u2d(w0u.y), p, pinv));
-        a10 = __dadd_rn(a10, fmodmul(v0, u2d(w1u.x), p, pinv));
-        a11 = __dadd_rn(a11, fmodmul(v1, u2d(w1u.y), p, pinv));
+        const double w00 = u2d(w0u.x), w01 = u2d(w0u.y), w10 = u2d(w1u.x), w11 = u2d(w1u.y);
+#pragma unroll
+        for (int ci = 0; ci < CT; ci++) {
+            const double v0 = LAZY ? __longlong_as_double((long long)vu[ci].x) : u2d(vu[ci].x);
+            const double v1 = LAZY ? __longlong_as_double((long long)vu[ci].y) : u2d(vu[ci].y);
+            a[ci][0] = __dadd_rn(a[ci][0], fmodmul(v0, w00, p, pinv));
+            a[ci][1] = __dadd_rn(a[ci][1], fmodmul(v1, w01, p, pinv));
+            a[ci][2] = __dadd_rn(a[ci][2], fmodmul(v0, w10, p, pinv));
+            a[ci][3] = __dadd_rn(a[ci][3], fmodmul(v1, w11, p, pinv));
+        }
         if ((dd & 7) == 7) { // sums of 8 fresh products stay below 4.1 p; re-centre before they could leave the exact range
-            a00 = frecenter(a00, p, pinv); a01 = frecenter(a01, p, pinv);
-            a10 = frecenter(a10, p, pinv); a11 = frecenter(a11, p, pinv);
+#pragma unroll
+            for (int ci = 0; ci < CT; ci++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) a[ci][j] = frecenter(a[ci][j], p, pinv);
         }
     }
-    a00 = frecenter(a00, p, pinv); a01 = frecenter(a01, p, pinv);
-    a10 = frecenter(a10, p, pinv); a11 = frecenter(a11, p, pinv);
-    const size_t o = ((size_t)(c * 2) * k + l) * N + x;
-    if (LAZY) {
-        *reinterpret_cast<ulonglong2 *>(acc + o) = make_ulonglong2(lazy_bits(a00), lazy_bits(a01));
-        *reinterpret_cast<ulonglong2 *>(acc + o + kpoly) = make_ulonglong2(lazy_bits(a10), lazy_bits(a11));
-    } else {
-        *reinterpret_cast<ulonglong2 *>(acc + o) = make_ulonglong2(fsmall_u(a00, F.q_u[l]), fsmall_u(a01, F.q_u[l]));
-        *reinterpret_cast<ulonglong2 *>(acc + o + kpoly) = make_ulonglong2(fsmall_u(a10, F.q_u[l]), fsmall_u(a11, F.q_u[l]));
+#pragma unroll
+    for (int ci = 0; ci < CT; ci++) {
+        if (c0 + ci >= n) break;
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[ci][j] = frecenter(a[ci][j], p, pinv);
+        const size_t o = ((size_t)((c0 + ci) * 2) * k + l) * N + x;
+        if (LAZY) {
+            *reinterpret_cast<ulonglong2 *>(acc + o) = make_ulonglong2(lazy_bits(a[ci][0]), lazy_bits(a[ci][1]));
+            *reinterpret_cast<ulonglong2 *>(acc + o + kpoly) = make_ulonglong2(lazy_bits(a[ci][2]), lazy_bits(a[ci][3]));
+        } else {
+            *reinterpret_cast<ulonglong2 *>(acc + o) = make_ulonglong2(fsmall_u(a[ci][0], F.q_u[l]), fsmall_u(a[ci][1], F.q_u[l]));
+            *reinterpret_cast<ulonglong2 *>(acc + o + kpoly) = make_ulonglong2(fsmall_u(a[ci][2], F.q_u[l]), fsmall_u(a[ci][3], F.q_u[l]));
+        }
     }
 }
 
@@ -298,13 +318,24 @@ cudaError_t launch_behz_floor_fold_fp(const u64 *d, u64 *out3, int n, int logn, 
 cudaError_t launch_ks_mac_fp(const u64 *digits, const u64 *key, u64 *acc, int n, int D, int k, int logn, const BehzConstF *f, int lazy,
                              cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    static const int unr = getenv("CNHE_KSMAC") ? atoi(getenv("CNHE_KSMAC")) : 1; // tuning knob: digits in flight per thread
-    const unsigned blocks = blocks_for(((size_t)n * k) << (logn - 1));
-    if (!lazy) k_ks_mac_fp<false, 4><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
-    else if (unr == 1) k_ks_mac_fp<true, 1><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
-    else if (unr == 2) k_ks_mac_fp<true, 2><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
-    else if (unr == 8) k_ks_mac_fp<true, 8><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
-    else k_ks_mac_fp<true, 4><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+    static const int unr = getenv("CNHE_KSMAC") ? atoi(getenv("CNHE_KSMAC")) : 1;       // tuning knob: digits in flight per thread
+    static const int cts = getenv("CNHE_KSMAC_CT") ? atoi(getenv("CNHE_KSMAC_CT")) : 4; // ciphertexts per thread (key reuse)
+    const int ct = n < 4 ? 1 : (cts == 1 || cts == 2 ? cts : 4);
+    const unsigned blocks = blocks_for(((size_t)((n + ct - 1) / ct) * k) << (logn - 1));
+    if (!lazy) {
+        if (ct == 4) k_ks_mac_fp<false, 1, 4><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+        else if (ct == 2) k_ks_mac_fp<false, 2, 2><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+        else k_ks_mac_fp<false, 4, 1><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+    } else if (ct == 4) {
+        if (unr == 2) k_ks_mac_fp<true, 2, 4><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+        else k_ks_mac_fp<true, 1, 4><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+    } else if (ct == 2) {
+        if (unr == 2) k_ks_mac_fp<true, 2, 2><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+        else k_ks_mac_fp<true, 1, 2><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+    } else if (unr == 1) k_ks_mac_fp<true, 1, 1><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+    else if (unr == 2) k_ks_mac_fp<true, 2, 1><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+    else if (unr == 8) k_ks_mac_fp<true, 8, 1><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+    else k_ks_mac_fp<true, 4, 1><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
     return cudaGetLastError();
 }
 

@@ -182,17 +182,38 @@ enum SampleKind { SAMPLE_TERNARY = 0, SAMPLE_NOISE = 1, SAMPLE_UNIFORM = 2 };
 // limbs = ceil(bits(q)/8); needs K*254*255 < 2^31
 cudaError_t launch_mac_dense_imma(const u64 *const *in_ptrs, const void *wfrag, const void *wfrag2, const u64 *bias, int K, int M, int limbs,
                                   u64 *const *out_ptrs, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
-// the same layer on tcgen05 (mac_umma.cu): M <= 128 outputs, |w| <= 127, the packed weight matrix resident in shared memory.
-// wpack = mac_dense_umma_weight_bytes(K) bytes in A-operand order (mac_dense_umma_pack, host side)
-// in_ptrs: K + n_extra source polynomials.  The first K must be evenly spaced in memory (in_ptrs[i] = in_ptrs[0] + i * stride: the outputs
-// of the previous layer's slab) -- they are fetched through one 2-D tensor map, 32 taps x 32 words per request; the n_extra taps behind
-// them (the W2 columns) may point anywhere and are fetched one bulk copy each.  Their weights start at column ceil32(K) of wpack.
-bool mac_dense_umma_fits(int K, int M, int limbs);
-cudaError_t make_word_map_2d(void *map, const u64 *base, size_t inner_words, size_t rows, size_t row_stride, unsigned box_words, unsigned box_rows);
-size_t mac_dense_umma_weight_bytes(int K);
-void mac_dense_umma_pack(const signed char *w, int M, int K, unsigned char *out);
-cudaError_t launch_mac_dense_umma(const u64 *const *in_ptrs, const u64 *affine_base, size_t affine_stride_words, int K, int n_extra, const void *wpack,
-                                  const u64 *bias, int M, int limbs, u64 *const *out_ptrs, int k, int logn, const BehzConst *bc, PlainConst pc, cudaStream_t s);
+// Scalar-MAC layers on tcgen05 (mac_umma.cu).  The layer's inputs are rows of one slab (input i at slab + i * slab_stride_words); a
+// BUNDLE is up to 128 outputs whose taps lie in a window of consecutive inputs: chunk j of the bundle multiplies the 32 inputs that start
+// at row chunk_rows[chunk0 + j] (bit 30 set: a row of the scratch slab that holds the W2 taps) with the 128 x 32 weight block at
+// wpack + a_off + j * 4096.  Outputs and constant biases are listed in bundle order (out0 = first entry of the bundle).
+struct UmBundle {
+    int chunk0, n_chunks, a_off, n_out, out0;
+};
+struct UmmaLaunch {
+    const u64 *slab;            // input 0
+    size_t slab_stride_words;   // distance between consecutive inputs
+    size_t slab_rows;           // number of inputs
+    const u64 *scratch;         // W2 taps gathered side by side (ct_words apart), or null
+    size_t scratch_rows;
+    const UmBundle *bundles;    // device
+    int n_bundles;
+    const int *chunk_rows;      // device
+    int total_chunks;           // chunks per tile (sum over the bundles)
+    const unsigned char *wpack; // device: a_bytes of weight blocks (identical matrices stored once)
+    int a_bytes;
+    u64 *const *out_ptrs;       // device, bundle order
+    const u64 *bias;            // device, bundle order; null = no constant bias
+    int n_out_total;
+    int limbs, k, logn;
+    const BehzConst *bc;
+    PlainConst pc;
+};
+bool mac_umma_fits(int a_bytes, int total_chunks, int n_out_total, int n_bundles, int limbs);
+void mac_umma_pack(const signed char *w, int rows, int cols, unsigned char *out); // cols a multiple of 32; out: cols / 32 * 4096 bytes
+cudaError_t launch_mac_umma(const UmmaLaunch &a, cudaStream_t s);
+// 2-D tensor map over 64-bit words (ntt.cu): rows of inner_words words, row_stride bytes apart; swizzle128: rows of the box are 128 bytes
+cudaError_t make_word_map_2d(void *map, const u64 *base, size_t inner_words, size_t rows, size_t row_stride, unsigned box_words, unsigned box_rows,
+                             int swizzle128);
 cudaError_t launch_sample(u64 *out, int n, int kind, const RngKey &seed, u64 stream0, u64 stream_step, int k, int logn, const BehzConst *bc, cudaStream_t s);
 // plain[i][index_map[j]] = values[i][j]  (j < count), zero elsewhere
 cudaError_t launch_encode_scatter(const u64 *values, u64 *plain, int n, int count, const u32 *index_map, int logn, cudaStream_t s);

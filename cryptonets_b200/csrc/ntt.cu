@@ -1482,16 +1482,18 @@ static cudaError_t make_row_map(CUtensorMap *m, const u64 *base, size_t words) {
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 // General 2-D map over 64-bit words for other kernels (mac_umma.cu): `rows` rows of `inner_words` words, `row_stride` bytes apart, box of
-// box_words x box_rows, no swizzle, out-of-bounds rows read as zero.  `map` points at a CUtensorMap (128 bytes, 64-byte aligned).
-cudaError_t make_word_map_2d(void *map, const u64 *base, size_t inner_words, size_t rows, size_t row_stride, unsigned box_words, unsigned box_rows) {
+// box_words x box_rows, optionally SWIZZLE_128B (box rows of 128 bytes), out-of-bounds rows read as zero.  `map` points at a CUtensorMap (128 bytes, 64-byte aligned).
+cudaError_t make_word_map_2d(void *map, const u64 *base, size_t inner_words, size_t rows, size_t row_stride, unsigned box_words, unsigned box_rows,
+                             int swizzle128) {
     if (encode_tiled() == nullptr) return cudaErrorNotSupported;
     const cuuint64_t dims[2] = {(cuuint64_t)inner_words, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)row_stride};
     const cuuint32_t box[2] = {box_words, box_rows}, estr[2] = {1, 1};
-    if ((row_stride & 15) || (reinterpret_cast<uintptr_t>(base) & 15) || box_words * 8 > 256 * 8 || box_rows > 256) return cudaErrorInvalidValue;
+    if ((row_stride & 15) || (reinterpret_cast<uintptr_t>(base) & 15) || box_words > 256 || box_rows > 256 || (swizzle128 && box_words != 16))
+        return cudaErrorInvalidValue;
     const CUresult r = encode_tiled()(reinterpret_cast<CUtensorMap *>(map), CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<u64 *>(base), dims, strides, box, estr,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 static unsigned ws_stagger_ns() {

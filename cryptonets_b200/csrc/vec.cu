@@ -6,6 +6,7 @@
 // class method by method (cited inline); the arithmetic itself is in the CUDA kernels.
 #include <cmath>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 #include <unordered_map>
 
@@ -1184,6 +1185,128 @@ struct RowHash {
         return hsh;
     }
 };
+// ---- plan of a scalar-MAC layer for the tcgen05 kernel (mac_umma.cu): bundles of consecutive distinct gather rows
+struct UmmaPlan {
+    bool ok = false;
+    std::vector<UmBundle> bundles;
+    std::vector<int> chunk_rows;
+    std::vector<unsigned char> wpack;
+    std::vector<int> out_order;  // output index per (bundle, row)
+    std::vector<int> extra_taps; // input index of every scratch-slab row (taps whose weights need the W2 part)
+    int total_chunks = 0;
+    // device copies (owned by the cache entry)
+    UmBundle *d_bundles = nullptr;
+    int *d_rows = nullptr;
+    unsigned char *d_wpack = nullptr;
+    ~UmmaPlan() {
+        if (d_bundles) cudaFree(d_bundles);
+        if (d_rows) cudaFree(d_rows);
+        if (d_wpack) cudaFree(d_wpack);
+    }
+};
+// bundles of `g` consecutive distinct rows; returns false when a bundle exceeds 128 outputs or a weight exceeds +-254
+static bool umma_try(UmmaPlan &pl, int g, const std::vector<int> &grows, const std::vector<std::vector<int>> &row_outs, const std::vector<double> &wdh, int K) {
+    const int R = (int)row_outs.size();
+    std::unordered_map<std::string, int> seen;
+    for (int start = 0; start < R; start += g) {
+        const int end = std::min(R, start + g);
+        std::vector<int> outs, out_row;
+        int tmin = INT_MAX, tmax = -1;
+        for (int r = start; r < end; r++) {
+            for (int m : row_outs[r]) { outs.push_back(m); out_row.push_back(r); }
+            for (int kk = 0; kk < K; kk++) {
+                const int t = grows[(size_t)r * K + kk];
+                if (t >= 0) { tmin = std::min(tmin, t); tmax = std::max(tmax, t); }
+            }
+        }
+        if (outs.empty() || outs.size() > 128 || tmax < 0) return false;
+        const int cols_main = ((tmax - tmin + 1) + 31) / 32 * 32;
+        std::vector<int> wfull(outs.size() * (size_t)cols_main, 0);
+        for (size_t i = 0; i < outs.size(); i++)
+            for (int kk = 0; kk < K; kk++) {
+                const int t = grows[(size_t)out_row[i] * K + kk];
+                if (t >= 0) wfull[i * cols_main + (t - tmin)] += (int)wdh[(size_t)outs[i] * K + kk];
+            }
+        std::vector<int> extras; // columns that hold a weight beyond one signed byte
+        for (int col = 0; col < cols_main; col++) {
+            bool big = false;
+            for (size_t i = 0; i < outs.size(); i++) {
+                const int w = wfull[i * cols_main + col];
+                if (w > 254 || w < -254) return false;
+                big = big || w > 127 || w < -127;
+            }
+            if (big) extras.push_back(col);
+        }
+        const int cols = cols_main + ((int)extras.size() + 31) / 32 * 32;
+        std::vector<signed char> w8(outs.size() * (size_t)cols, 0);
+        for (size_t i = 0; i < outs.size(); i++) {
+            for (int col = 0; col < cols_main; col++) w8[i * cols + col] = (signed char)std::max(-127, std::min(127, wfull[i * cols_main + col]));
+            for (size_t j = 0; j < extras.size(); j++) {
+                const int w = wfull[i * cols_main + extras[j]];
+                w8[i * cols + cols_main + j] = (signed char)(w - std::max(-127, std::min(127, w)));
+            }
+        }
+        std::string blob((size_t)cols / 32 * 4096, '\0');
+        mac_umma_pack(w8.data(), (int)outs.size(), cols, reinterpret_cast<unsigned char *>(&blob[0]));
+        UmBundle b;
+        auto it = seen.find(blob);
+        if (it == seen.end()) { // interior rows of a convolution share one matrix: the window slides with the bundle
+            b.a_off = (int)pl.wpack.size();
+            seen.emplace(blob, b.a_off);
+            pl.wpack.insert(pl.wpack.end(), blob.begin(), blob.end());
+        } else
+            b.a_off = it->second;
+        b.chunk0 = (int)pl.chunk_rows.size();
+        b.n_chunks = cols / 32;
+        b.n_out = (int)outs.size();
+        b.out0 = (int)pl.out_order.size();
+        for (int cch = 0; cch < cols_main / 32; cch++) pl.chunk_rows.push_back(tmin + 32 * cch);
+        for (int cch = 0; cch < (cols - cols_main) / 32; cch++) pl.chunk_rows.push_back((1 << 30) | ((int)pl.extra_taps.size() + 32 * cch));
+        for (int col : extras) pl.extra_taps.push_back(tmin + col);
+        pl.out_order.insert(pl.out_order.end(), outs.begin(), outs.end());
+        pl.bundles.push_back(b);
+        pl.total_chunks += b.n_chunks;
+    }
+    return true;
+}
+// fewest chunks per tile over the bundle sizes that fit in shared memory; cached per layer (keyed by a hash of its gather table and weights)
+static std::shared_ptr<UmmaPlan> umma_plan(Context &c, int ch, const std::vector<int> &grows, const std::vector<std::vector<int>> &row_outs,
+                                           const std::vector<double> &wdh, int M, int K, int limbs) {
+    u64 key = 0xcbf29ce484222325ULL ^ (u64)ch * 0x9e3779b97f4a7c15ULL ^ ((u64)M << 32) ^ (u64)K;
+    auto mix = [&](const void *p, size_t bytes) {
+        const u64 *w = reinterpret_cast<const u64 *>(p);
+        for (size_t i = 0; i < bytes / 8; i++) { key ^= w[i]; key *= 0x100000001b3ULL; key ^= key >> 29; }
+    };
+    mix(wdh.data(), wdh.size() * 8);
+    mix(grows.data(), grows.size() / 2 * 8);
+    auto hit = c.umma_plans.find(key);
+    if (hit != c.umma_plans.end()) return std::static_pointer_cast<UmmaPlan>(hit->second);
+    std::shared_ptr<UmmaPlan> best;
+    const int R = (int)row_outs.size();
+    for (int g = 1; g <= R; g++) {
+        auto pl = std::make_shared<UmmaPlan>();
+        if (!umma_try(*pl, g, grows, row_outs, wdh, K)) {
+            if (g > 1 && (size_t)g * row_outs[0].size() > 128) break; // larger groups only grow
+            continue;
+        }
+        if (!mac_umma_fits((int)pl->wpack.size(), pl->total_chunks, M, (int)pl->bundles.size(), limbs)) continue;
+        if (!best || pl->total_chunks < best->total_chunks) best = pl;
+        if (g > 64) break;
+    }
+    if (!best) best = std::make_shared<UmmaPlan>();
+    else {
+        best->ok = true;
+        CNHE_CUDA(cudaMalloc((void **)&best->d_bundles, best->bundles.size() * sizeof(UmBundle)));
+        CNHE_CUDA(cudaMalloc((void **)&best->d_rows, best->chunk_rows.size() * sizeof(int)));
+        CNHE_CUDA(cudaMalloc((void **)&best->d_wpack, best->wpack.size()));
+        CNHE_CUDA(cudaMemcpy(best->d_bundles, best->bundles.data(), best->bundles.size() * sizeof(UmBundle), cudaMemcpyHostToDevice));
+        CNHE_CUDA(cudaMemcpy(best->d_rows, best->chunk_rows.data(), best->chunk_rows.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CNHE_CUDA(cudaMemcpy(best->d_wpack, best->wpack.data(), best->wpack.size(), cudaMemcpyHostToDevice));
+    }
+    if (c.umma_plans.size() > 64) c.umma_plans.clear();
+    c.umma_plans[key] = best;
+    return best;
+}
 // Shared body of DenseMatrixBySparseVectorMultiply (ciphertext columns x plain constants) and of the fused PoolLayer.
 // in[n_in] encrypted dense vectors (same block count), weights[m] plain sparse of dim K, bias[m] plain dense or null.
 static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int32_t *gather, const cnhe_vec *const *weights, const cnhe_vec *const *bias,
@@ -1216,6 +1339,7 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
     // tiles: outputs that share a gather row, 8 at a time
     std::vector<int> grows;
     std::vector<MacTile> tiles;
+    std::vector<std::vector<int>> row_outs; // outputs of every distinct gather row, in the order of `grows`
     {
         std::unordered_map<std::vector<int>, std::vector<int>, RowHash> groups;
         std::vector<std::vector<int>> order;
@@ -1244,6 +1368,7 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
             const int row_index = (int)(grows.size() / K);
             grows.insert(grows.end(), row.begin(), row.end());
             const std::vector<int> &ms = groups[row];
+            row_outs.push_back(ms);
             for (size_t s = 0; s < ms.size(); s += 8) {
                 MacTile t;
                 memset(&t, 0, sizeof(t));
@@ -1287,44 +1412,23 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
         const int limbs = (maxbits + 7) / 8;
         const bool imma = order_rows == 1 && wmax <= 254.0 && K >= 32 && M >= 8 && limbs >= 5 && limbs <= 7 && (double)K * 254.0 * 255.0 < 2147483648.0 &&
                           !getenv("CNHE_MAC_NO_IMMA") && !getenv("CNHE_MAC_INT");
-        // ... on tcgen05 when the layer fits its shape (mac_umma.cu): at most 128 outputs, one signed byte per weight.  Weights beyond
-        // +-127 (up to +-254) are split W = W1 + W2 as above, but W2 is sparse (CryptoNets' 845 -> 100 layer: 48 of 84 500 weights, in 31
-        // columns), so it rides on extra taps: every column that holds such a weight is appended once more with W2 as its weights
-        std::vector<int> extra_taps;
-        for (int kk = 0; kk < K && imma; kk++) {
-            bool big = false;
-            for (int m = 0; m < M; m++) big = big || std::fabs(wdh[(size_t)m * K + kk]) > 127.0;
-            if (big && grows[kk] >= 0) extra_taps.push_back(kk);
-        }
-        // weight columns: taps 0..K-1, zero padding to the next multiple of 32 (the extra taps start a fresh MMA chunk), then the W2 columns
-        const int K_pad = (K + 31) & ~31, n_extra = (int)extra_taps.size(), K_ext = K_pad + n_extra;
-        // the K taps must be evenly spaced in memory (one 2-D tensor map fetches 32 of them per request): true when the layer reads the
-        // previous layer's output slab in order, which is how the dense layers are fed
-        bool affine = imma && bl == 1 && K >= 2;
+        // ... or, for any layer whose inputs are evenly spaced rows of one slab (the previous layer's output, an imported batch) and whose
+        // weights stay within +-254: tcgen05 (mac_umma.cu), dense and convolution alike
+        std::shared_ptr<UmmaPlan> plan;
         long long tap_stride = 0;
-        if (affine) {
-            auto tap_ptr = [&](int kk) { return in[grows[kk] < 0 ? 0 : grows[kk]]->block(ch, 0); };
-            tap_stride = tap_ptr(1) - tap_ptr(0);
-            for (int kk = 0; kk < K && affine; kk++) affine = grows[kk] >= 0 && tap_ptr(kk) == tap_ptr(0) + (long long)kk * tap_stride;
-            affine = affine && tap_stride > 0 && tap_stride % 2 == 0;
-        }
-        const bool umma = affine && mac_dense_umma_fits(K_ext, M, limbs) && (double)K_ext * 127.0 * 255.0 < 2147483648.0 && !getenv("CNHE_MAC_NO_UMMA");
-        const void *d_wfrag = nullptr, *d_wfrag2 = nullptr, *d_wpack = nullptr;
-        if (umma) {
-            std::vector<signed char> w8((size_t)M * K_ext, 0);
-            for (int m = 0; m < M; m++) {
-                for (int kk = 0; kk < K; kk++) w8[(size_t)m * K_ext + kk] = (signed char)std::max(-127, std::min(127, (int)wdh[(size_t)m * K + kk]));
-                for (int j = 0; j < n_extra; j++) {
-                    const int w = (int)wdh[(size_t)m * K + extra_taps[j]];
-                    w8[(size_t)m * K_ext + K_pad + j] = (signed char)(w - std::max(-127, std::min(127, w)));
-                }
+        {
+            bool slab = bl == 1 && n_in >= 2 && limbs >= 5 && limbs <= 7 && wmax <= 254.0 && !getenv("CNHE_MAC_NO_UMMA") && !getenv("CNHE_MAC_NO_IMMA") &&
+                        !getenv("CNHE_MAC_INT");
+            if (slab) {
+                tap_stride = in[1]->block(ch, 0) - in[0]->block(ch, 0);
+                slab = tap_stride >= (long long)c.ct_words() && tap_stride % 2 == 0;
+                for (int i = 0; i < n_in && slab; i++) slab = in[i]->block(ch, 0) == in[0]->block(ch, 0) + (long long)i * tap_stride;
             }
-            std::vector<unsigned char> packed(mac_dense_umma_weight_bytes(K_ext));
-            mac_dense_umma_pack(w8.data(), M, K_ext, packed.data());
-            u64 *buf = c.ws_alloc((packed.size() + 7) / 8);
-            c.h2d(buf, packed.data(), packed.size());
-            d_wpack = buf;
-        } else if (imma) {
+            if (slab) plan = umma_plan(c, ch, grows, row_outs, wdh, M, K, limbs);
+        }
+        const bool umma = plan && plan->ok && (double)plan->total_chunks * 32.0 * 127.0 * 255.0 < 2147483648.0;
+        const void *d_wfrag = nullptr, *d_wfrag2 = nullptr;
+        if (!umma && imma) {
             const int mtiles = (M + 15) / 16, chunks = (K + 31) / 32;
             const size_t fwords = (size_t)mtiles * chunks * 32 * 4;
             std::vector<uint32_t> frag(2 * fwords, 0); // W1 = clamp(W, +-127) then the residual W2 = W - W1
@@ -1375,12 +1479,34 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
             for (auto &t : tiles) { int kk = 0; for (int j = 0; j < K; j++) kk += grows[(size_t)t.gather_row * K + j] >= 0; used += kk + t.n_out; }
             c.prof_begin(4, used * 8.0 * c.ct_words());
             if (umma) {
-                std::vector<const u64 *> ipg(K + n_extra);
-                for (int kk = 0; kk < K; kk++) ipg[kk] = ip[grows[kk]];
-                for (int j = 0; j < n_extra; j++) ipg[K + j] = ip[grows[extra_taps[j]]];
-                c.check(launch_mac_dense_umma(upload_ptrs(c, ipg), ipg[0], (size_t)tap_stride, K, n_extra, d_wpack, d_bias, M, limbs, upload_ptrs_mut(c, op), c.k,
-                                              c.logN, c.d_bc, c.ch[ch].pc, c.stream),
-                        "mac_dense_umma");
+                UmmaLaunch a;
+                memset(&a, 0, sizeof(a));
+                a.slab = in[0]->block(ch, 0);
+                a.slab_stride_words = (size_t)tap_stride;
+                a.slab_rows = (size_t)n_in;
+                if (!plan->extra_taps.empty()) { // the taps that need the W2 part, side by side
+                    u64 *scratch = c.ws_alloc(plan->extra_taps.size() * c.ct_words());
+                    for (size_t j = 0; j < plan->extra_taps.size(); j++)
+                        CNHE_CUDA(cudaMemcpyAsync(scratch + j * c.ct_words(), ip[plan->extra_taps[j]], c.ct_words() * 8, cudaMemcpyDeviceToDevice, c.stream));
+                    a.scratch = scratch;
+                    a.scratch_rows = plan->extra_taps.size();
+                }
+                std::vector<u64 *> opo(M);
+                for (int i = 0; i < M; i++) opo[i] = op[plan->out_order[i]];
+                const u64 *d_bias_o = nullptr;
+                if (d_bias) {
+                    std::vector<u64> bo(M);
+                    for (int i = 0; i < M; i++) bo[i] = bias[plan->out_order[i]]->const_val[ch];
+                    u64 *db = c.ws_alloc(M);
+                    c.h2d(db, bo.data(), (size_t)M * 8);
+                    d_bias_o = db;
+                }
+                a.bundles = plan->d_bundles; a.n_bundles = (int)plan->bundles.size();
+                a.chunk_rows = plan->d_rows; a.total_chunks = plan->total_chunks;
+                a.wpack = plan->d_wpack; a.a_bytes = (int)plan->wpack.size();
+                a.out_ptrs = upload_ptrs_mut(c, opo); a.bias = d_bias_o; a.n_out_total = M;
+                a.limbs = limbs; a.k = c.k; a.logn = c.logN; a.bc = c.d_bc; a.pc = c.ch[ch].pc;
+                c.check(launch_mac_umma(a, c.stream), "mac_umma");
             } else if (imma) {
                 std::vector<const u64 *> ipg(K);
                 for (int kk = 0; kk < K; kk++) ipg[kk] = ip[grows[kk] < 0 ? 0 : grows[kk]]; // padded taps carry weight 0

@@ -318,7 +318,7 @@ def test_dense_layer_on_tensor_cores(pair, shape, capfd):
         eng.sync()
     finally:
         del os.environ["CNHE_UMMA_PROF"]
-    served = "[umma K=" in capfd.readouterr().err
+    served = "[umma " in capfd.readouterr().err
     assert served == (feed == "slab"), "wrong kernel served the layer"
     for m in range(M):
         assert np.array_equal(outs[m].export_raw(0, 0), want[m]), m
@@ -404,3 +404,66 @@ def test_cta_pair_and_whole_polynomial_transforms_agree(pair, split, monkeypatch
     assert np.array_equal(eng.dev_download(o2, m * 2 * k * N).reshape(m, -1), want)
     eng.dev_free(a)
     eng.dev_free(o2)
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_convolution_on_tensor_cores(pair, wide, capfd):
+    """A strided, padded convolution over a slab of per-pixel ciphertexts (PoolLayer.cs:68-80, 196-227) on the tcgen05 path: the host
+    plan bundles the outputs of one output row (their taps lie in a window of consecutive inputs), interior rows share one weight matrix,
+    padded taps carry no weight, and weights beyond a signed byte ("wide") ride on extra taps gathered into a scratch slab.  Same words as
+    the oracle's 128-bit multiply-accumulate, and as the FP64 scalar-MAC kernel."""
+    import os
+    from cryptonets_b200.engine import DENSE, SPARSE
+    eng, orc, name = pair
+    N = eng.N
+    rng = np.random.default_rng(31)
+    side, ker, stride, pad, maps = (17 if name == "default4096" else 9), 3, 2, 1, 4  # 256 outputs = two bundles on the smallest ring
+    osz = (side + pad - ker) // stride + 1  # upper padding only, as the reference's Upperpadding
+    n_in, K = side * side, ker * ker
+    M = maps * osz * osz
+    vals, cts = _fresh_cts(orc, n_in, 12, nonce0=1500)
+    cts = np.array(cts, dtype=np.uint64)
+    cts[0, :] = np.tile(np.array(orc.q, dtype=np.uint64) - 1, 2).repeat(N)  # maximal words in the first pixel
+    ins = eng.import_raw_many(cts, n_in, 1, N, 4.0)
+    gather = np.full((M, K), -1, dtype=np.int32)
+    w = np.zeros((M, K))
+    kern = rng.integers(-127, 128, (maps, K)).astype(np.float64)
+    kern[:, 0] = [127, -127, 1, 0]
+    if wide:
+        kern[1, 4], kern[2, 8] = 201, -254
+    m = 0
+    for y in range(osz):          # position-major, maps innermost: outputs of one window are adjacent (PoolLayer's order)
+        for x in range(osz):
+            for f in range(maps):
+                for dy in range(ker):
+                    for dx in range(ker):
+                        iy, ix = y * stride + dy - pad, x * stride + dx - pad
+                        if 0 <= iy < side and 0 <= ix < side:
+                            gather[m, dy * ker + dx] = iy * side + ix
+                w[m] = kern[f]
+                m += 1
+    bias = rng.integers(-1000, 1000, M).astype(np.float64)
+    wv = [eng.plain(w[i], 1.0, SPARSE) for i in range(M)]
+    bv = [eng.plain(np.full(N, bias[i]), 4.0, DENSE) for i in range(M)]
+    t = orc.t
+    wres = np.where(w < 0, w + t, w).astype(np.uint64)
+    bres = np.where(bias * 4 < 0, bias * 4 + t, bias * 4).astype(np.uint64)
+    want = orc.mac_layer(cts, gather, wres, bres, M, K, threads=4).reshape(M, -1)
+    os.environ["CNHE_UMMA_PROF"] = "1"
+    capfd.readouterr()
+    try:
+        outs = eng.layer_conv_dense(ins, gather, wv, bv, M, K)
+        eng.sync()
+    finally:
+        del os.environ["CNHE_UMMA_PROF"]
+    err = capfd.readouterr().err
+    assert "[umma bundles=" in err, "the tcgen05 kernel did not serve the convolution"
+    for i in range(M):
+        assert np.array_equal(outs[i].export_raw(0, 0), want[i]), i
+    os.environ["CNHE_MAC_NO_UMMA"] = "1"
+    try:
+        outs2 = eng.layer_conv_dense(ins, gather, wv, bv, M, K)
+    finally:
+        del os.environ["CNHE_MAC_NO_UMMA"]
+    for i in range(M):
+        assert np.array_equal(outs2[i].export_raw(0, 0), want[i]), i
