@@ -320,12 +320,14 @@ cudaError_t launch_ks_mac_fp(const u64 *digits, const u64 *key, u64 *acc, int n,
     if (n <= 0) return cudaSuccess;
     static const int unr = getenv("CNHE_KSMAC") ? atoi(getenv("CNHE_KSMAC")) : 1;       // tuning knob: digits in flight per thread
     static const int cts = getenv("CNHE_KSMAC_CT") ? atoi(getenv("CNHE_KSMAC_CT")) : 4; // ciphertexts per thread (key reuse)
-    const int ct = n < 4 ? 1 : (cts == 1 || cts == 2 ? cts : 4);
+    const int ct = n < 4 ? 1 : (cts == 1 || cts == 2 || (cts == 8 && lazy) ? cts : 4);
     const unsigned blocks = blocks_for(((size_t)((n + ct - 1) / ct) * k) << (logn - 1));
     if (!lazy) {
         if (ct == 4) k_ks_mac_fp<false, 1, 4><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
         else if (ct == 2) k_ks_mac_fp<false, 2, 2><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
         else k_ks_mac_fp<false, 4, 1><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
+    } else if (ct == 8) {
+        k_ks_mac_fp<true, 1, 8><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
     } else if (ct == 4) {
         if (unr == 2) k_ks_mac_fp<true, 2, 4><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);
         else k_ks_mac_fp<true, 1, 4><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);

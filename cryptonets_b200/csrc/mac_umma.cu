@@ -56,16 +56,18 @@ __device__ __forceinline__ void mb_expect_tx(unsigned long long *bar, unsigned b
 __device__ __forceinline__ void mb_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sptr(bar)) : "memory");
 }
-// bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the GPU
+// bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the GPU.  The try_wait carries a suspend-time
+// hint, so a waiting warp sleeps in hardware instead of spinning: in the first version the spin loops (TRYWAIT / ISETP / BRA / YIELD)
+// were 40 % of all executed instructions and took issue slots from the working warps of the same scheduler (ncu source view)
 __device__ __forceinline__ void mb_wait(unsigned long long *bar, unsigned parity) {
     const unsigned a = sptr(bar);
     unsigned done = 0;
     for (unsigned spin = 0; !done; spin++) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done)
-                     : "r"(a), "r"(parity)
+                     : "r"(a), "r"(parity), "r"(20000u)
                      : "memory");
-        if (!done && spin > (1u << 26)) __trap();
+        if (!done && spin > (1u << 22)) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
@@ -99,6 +101,10 @@ __device__ __forceinline__ void tmem_ld8(unsigned taddr, int (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr));
 }
+// the registers of a TMEM load are valid only after tcgen05.wait::ld; this empty volatile asm (ordered after the wait) "rewrites" them, so
+// no use of them can be scheduled above the wait
+template <int W>
+__device__ __forceinline__ void tmem_regs_ready(int (&v)[W], int o) { asm volatile("" : "+r"(v[o]), "+r"(v[o + 1]), "+r"(v[o + 2]), "+r"(v[o + 3])); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // exact double of a signed integer |x| < 2^51: one integer add, one FP64 add (inverse of d2i)
 __device__ __forceinline__ double i2d(long long x) { return __dsub_rn(__longlong_as_double(x + 0x4338000000000000LL), FP_MAGIC); }
@@ -312,12 +318,17 @@ k_mac_umma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
                 const unsigned tbase = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + as * UM_ACC_COLS;
                 if ((warp & 3) * 32 < bn.n_out) { // warps whose 32 rows are all padding skip the arithmetic (uniform per warp)
                     u64 *orow = m < bn.n_out ? sdst[bn.out0 + m] + col0 : nullptr;
+                    // eight words per step: the epilogue is a latency chain (TMEM load -> integer combine -> FP64 modular product -> canonical
+                    // word -> store) at ~0.25 instructions per cycle and warp, so what counts is independent words in flight.  (Four words
+                    // with the next four prefetched from TMEM measured 14 % slower: the TMEM load is not what the chain waits for.)
 #pragma unroll
                     for (int n0 = 0; n0 < UM_TN; n0 += 8) {
                         int acc[LIMBS][8];
 #pragma unroll
                         for (int a = 0; a < LIMBS; a++) tmem_ld8(tbase + a * UM_TN + n0, acc[a]);
                         tmem_ld_wait();
+#pragma unroll
+                        for (int a = 0; a < LIMBS; a++) { tmem_regs_ready(acc[a], 0); tmem_regs_ready(acc[a], 4); }
                         u64 res[8];
 #pragma unroll
                         for (int e = 0; e < 8; e++) {

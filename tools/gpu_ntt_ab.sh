@@ -1,7 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "== kernel parity (ws on)"; timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_wrapper.py -x -q 2>&1 | tail -4
-echo "== ntt_bench WS"; timeout 120 python tools/ntt_bench.py 8192 5 16384; timeout 120 python tools/ntt_bench.py 4096 3 32768
-echo "== square_bench ws both"; timeout 120 python tools/square_bench.py 845 4
-echo "== square_bench ws inv only"; CNHE_NTT_WS_FWD=0 timeout 120 python tools/square_bench.py 845 4
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ntt_forward_ws -s 2 -c 1 -o gpurun_out/r02_ws5_fwd python tools/ntt_bench.py 8192 5 16384 > /dev/null 2>&1
+echo "== kernel parity (persistent/per-polynomial combos)"; timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k "persistent_and_per_polynomial" 2>&1 | tail -3
+echo "== ntt_bench 8192: inverse persistent (default), forward per-polynomial"; timeout 120 python tools/ntt_bench.py 8192 5 16384
+echo "== ntt_bench 8192: both persistent"; CNHE_NTT_WS_FWD=1 timeout 120 python tools/ntt_bench.py 8192 5 16384
+echo "== ntt_bench 8192: none persistent"; CNHE_NTT_WS=0 timeout 120 python tools/ntt_bench.py 8192 5 16384
+echo "== ntt_bench 4096"; timeout 120 python tools/ntt_bench.py 4096 3 32768
+run() { python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | python -c "
+import json,sys;d=json.loads(sys.stdin.read());print({k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['value_two_streams']['value'], d['roofline']['frac']); print(d['roofline']['families_ms_per_step'])"; }
+echo "== bench default"; run
+echo "== bench forward persistent too"; CNHE_NTT_WS_FWD=1 run
