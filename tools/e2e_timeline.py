@@ -23,7 +23,17 @@ host_outs = [torch.empty(eng.P * 10 * eng.ct_words, dtype=torch.int64).pin_memor
 eng.export_raw_many([v.vec for v in xm.vectors], host_in.data_ptr())
 
 
+_dummy = None
+_side = None
 def imp():
+    global _dummy, _side
+    if os.environ.get("DUMMYCOPY"):  # the same bytes cross PCIe every step on a side stream, but nothing depends on them:
+        if _dummy is None:           # separates hardware interference (DMA vs kernels) from scheduling / dependencies
+            _dummy = torch.empty(host_in.numel(), dtype=torch.int64, device="cuda")
+            _side = torch.cuda.Stream()
+        with torch.cuda.stream(_side):
+            _dummy.copy_(host_in, non_blocking=True)
+        return None
     if os.environ.get("NOIMPORT"):  # isolate the upload: every step reuses the resident batch
         return None
     vecs = eng.import_raw_many(host_in.data_ptr(), 784, 1, bench.BATCH, 16.0)
