@@ -438,11 +438,11 @@ def run_b200(args):
         roof = {"bound": "fp64-issue (reported against hbm)", "kernel": "k_ntt_forward_fp / k_ntt_forward_digits_fp (N=8192), 16*N algorithmic bytes per transform", "achieved": achieved,
                 "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)",
-                # ncu (profiles/r01_square_path_v2_ncu.txt): one k_ntt_forward_digits_fp launch of 16000 transforms moved 42.3 MB + 995.9 MB of
+                # ncu (profiles/r02_top_kernels_ncu.txt, same figures as round 1's capture): one k_ntt_forward_digits_fp launch of 16000 transforms moved 42.4 MB + 994.7 MB of
                 # DRAM traffic against 2097.2 MB algorithmic (16N per transform; the digit source is shared by 125 transforms through
                 # L2) -- ratio 0.495, applied to this run's mean launch (waves are larger than the captured one)
                 "traffic": 0.495 * fam["bytes"] / max(1, fam["launches"]),
-                "traffic_source": "ncu dram bytes / algorithmic bytes = 0.495 for k_ntt_forward_digits_fp<13,1> (profiles/r01_square_path_v2_ncu.txt), scaled to this run's mean launch",
+                "traffic_source": "ncu dram bytes / algorithmic bytes = 0.495 for k_ntt_forward_digits_fp<13,1> (profiles/r02_top_kernels_ncu.txt), scaled to this run's mean launch",
                 "launches_timed": fam["launches"], "algorithmic_bytes_per_launch": fam["bytes"] / max(1, fam["launches"]),
                 "avg_launch_ms": fam["ms"] / max(1, fam["launches"]), "share_of_step": fam["ms"] / ms if ms else None,
                 "families_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}

@@ -320,7 +320,8 @@ cudaError_t launch_ks_mac_fp(const u64 *digits, const u64 *key, u64 *acc, int n,
     if (n <= 0) return cudaSuccess;
     static const int unr = getenv("CNHE_KSMAC") ? atoi(getenv("CNHE_KSMAC")) : 1;       // tuning knob: digits in flight per thread
     static const int cts = getenv("CNHE_KSMAC_CT") ? atoi(getenv("CNHE_KSMAC_CT")) : 4; // ciphertexts per thread (key reuse)
-    const int ct = n < 4 ? 1 : (cts == 1 || cts == 2 || (cts == 8 && lazy) ? cts : 4);
+    // key reuse pays once the launch fills the GPU anyway: with few ciphertexts (LoLa: 1-32 per call) four per thread leaves SMs idle
+    const int ct = n < 64 ? 1 : (cts == 1 || cts == 2 || (cts == 8 && lazy) ? cts : 4);
     const unsigned blocks = blocks_for(((size_t)((n + ct - 1) / ct) * k) << (logn - 1));
     if (!lazy) {
         if (ct == 4) k_ks_mac_fp<false, 1, 4><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);

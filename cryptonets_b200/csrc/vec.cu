@@ -1417,7 +1417,9 @@ static void mac_layer(Context &c, const cnhe_vec *const *in, int n_in, const int
         std::shared_ptr<UmmaPlan> plan;
         long long tap_stride = 0;
         {
-            bool slab = bl == 1 && n_in >= 2 && limbs >= 5 && limbs <= 7 && wmax <= 254.0 && !getenv("CNHE_MAC_NO_UMMA") && !getenv("CNHE_MAC_NO_IMMA") &&
+            // (M >= 8: LoLa's per-map products come one output at a time -- a 128-row MMA per tile would be 99 % padding and the kernel's
+            // per-tile latency more than the whole scalar-MAC launch)
+            bool slab = bl == 1 && n_in >= 2 && M >= 8 && limbs >= 5 && limbs <= 7 && wmax <= 254.0 && !getenv("CNHE_MAC_NO_UMMA") && !getenv("CNHE_MAC_NO_IMMA") &&
                         !getenv("CNHE_MAC_INT");
             if (slab) {
                 tap_stride = in[1]->block(ch, 0) - in[0]->block(ch, 0);
