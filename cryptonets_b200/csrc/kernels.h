@@ -135,7 +135,8 @@ cudaError_t launch_plain_lift(const u64 *plain, u64 *lifted, int n, int coeffs, 
 cudaError_t launch_dyadic_bcast(const u64 *a, const u64 *b, u64 *out, int n, int size, int a_per_ct, int b_per_ct, int k, int logn,
                                 const BehzConst *bc, cudaStream_t s);
 // Galois: out[c] = (perm(c0), 0), perm1[c] = perm(c1)   (util::apply_galois)
-cudaError_t launch_galois(const u64 *in, u64 *out_base, u64 *perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *bc, cudaStream_t s);
+cudaError_t launch_galois(const u64 *in, u64 *out_base, u64 *perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *bc, cudaStream_t s,
+                          int add_back = 0); // add_back: base = (c0 + perm(c0), c1) -> key switch + base = x + rotate(x)
 // the same with the n input ciphertexts given by a device pointer table
 cudaError_t launch_galois_gather(const u64 *const *in_ptrs, u64 *out_base, u64 *perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *bc,
                                  cudaStream_t s);

@@ -98,8 +98,11 @@ __global__ void __launch_bounds__(256) k_dyadic_bcast(const u64 *a, const u64 *b
 }
 
 // ---------------------------------------------------------------- Galois permutation (gather form)
+// add_back: the base of the key switch also carries the UNROTATED ciphertext (c0 + perm(c0), c1), so that key switch + base == x + rotate(x):
+// one step of the rotate-and-sum ladder (SumAllSlots) without a separate addition pass
 __global__ void __launch_bounds__(256) k_galois(const u64 *__restrict__ in, const u64 *const *__restrict__ in_ptrs, u64 *__restrict__ out_base,
-                                               u64 *__restrict__ perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *__restrict__ bc) {
+                                               u64 *__restrict__ perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *__restrict__ bc,
+                                               int add_back) {
     const int N = 1 << logn;
     const size_t kN = (size_t)k * N;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,8 +115,13 @@ __global__ void __launch_bounds__(256) k_galois(const u64 *__restrict__ in, cons
     u64 v = ct[(size_t)part * kN + (size_t)l * N + src];
     if (raw >> logn) v = negmod(v, bc->q[l].p);
     if (part == 0) {
-        out_base[c * 2 * kN + (size_t)l * N + j] = v;
-        out_base[c * 2 * kN + kN + (size_t)l * N + j] = 0;
+        if (add_back) {
+            out_base[c * 2 * kN + (size_t)l * N + j] = addmod(v, ct[(size_t)l * N + j], bc->q[l].p);
+            out_base[c * 2 * kN + kN + (size_t)l * N + j] = ct[kN + (size_t)l * N + j];
+        } else {
+            out_base[c * 2 * kN + (size_t)l * N + j] = v;
+            out_base[c * 2 * kN + kN + (size_t)l * N + j] = 0;
+        }
     } else {
         perm_c1[c * kN + (size_t)l * N + j] = v;
     }
@@ -396,15 +404,16 @@ cudaError_t launch_dyadic_bcast(const u64 *a, const u64 *b, u64 *out, int n, int
     k_dyadic_bcast<<<blocks_for(((size_t)n * size * k) << logn), 256, 0, s>>>(a, b, out, n, size, a_per_ct, b_per_ct, k, logn, bc);
     return cudaGetLastError();
 }
-cudaError_t launch_galois(const u64 *in, u64 *out_base, u64 *perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *bc, cudaStream_t s) {
+cudaError_t launch_galois(const u64 *in, u64 *out_base, u64 *perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *bc, cudaStream_t s,
+                          int add_back) {
     if (n <= 0) return cudaSuccess;
-    k_galois<<<blocks_for(((size_t)n * 2 * k) << logn), 256, 0, s>>>(in, nullptr, out_base, perm_c1, n, elt_inv, k, logn, bc);
+    k_galois<<<blocks_for(((size_t)n * 2 * k) << logn), 256, 0, s>>>(in, nullptr, out_base, perm_c1, n, elt_inv, k, logn, bc, add_back);
     return cudaGetLastError();
 }
 cudaError_t launch_galois_gather(const u64 *const *in_ptrs, u64 *out_base, u64 *perm_c1, int n, u64 elt_inv, int k, int logn, const BehzConst *bc,
                                  cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    k_galois<<<blocks_for(((size_t)n * 2 * k) << logn), 256, 0, s>>>(nullptr, in_ptrs, out_base, perm_c1, n, elt_inv, k, logn, bc);
+    k_galois<<<blocks_for(((size_t)n * 2 * k) << logn), 256, 0, s>>>(nullptr, in_ptrs, out_base, perm_c1, n, elt_inv, k, logn, bc, 0);
     return cudaGetLastError();
 }
 cudaError_t launch_mac_layer(const u64 *const *in_ptrs, const int *gather, const MacTile *tiles, int n_tiles, const u64 *const *w_ptrs,

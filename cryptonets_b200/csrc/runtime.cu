@@ -859,7 +859,7 @@ u64 galois_elt_from_step(const Context &c, int steps) { // Evaluator::galois_elt
     for (u64 i = 0; i < s; i++) e = (e * 3) & (m - 1);
     return e;
 }
-void op_apply_galois(Context &c, int ch, const u64 *in, int n, u64 elt, u64 *out) {
+void op_apply_galois(Context &c, int ch, const u64 *in, int n, u64 elt, u64 *out, bool add_back) {
     auto it = c.ch[ch].glk.find(elt);
     if (it == c.ch[ch].glk.end()) throw Error(-3, "Galois key not present");
     const int k = c.k;
@@ -871,10 +871,20 @@ void op_apply_galois(Context &c, int ch, const u64 *in, int n, u64 elt, u64 *out
     for (int c0 = 0; c0 < n; c0 += c.chunk) {
         const int m = std::min(c.chunk, n - c0);
         u64 *base = c.ws_alloc((size_t)m * 2 * k * N), *p1 = c.ws_alloc((size_t)m * k * N);
-        c.check(launch_galois(in + (size_t)c0 * 2 * k * N, base, p1, m, einv, k, c.logN, c.d_bc, c.stream), "galois");
+        c.check(launch_galois(in + (size_t)c0 * 2 * k * N, base, p1, m, einv, k, c.logN, c.d_bc, c.stream, add_back ? 1 : 0), "galois");
         op_key_switch(c, p1, (size_t)k * N, m, it->second->p, c.dm_galois, base, (size_t)2 * k * N, out + (size_t)c0 * 2 * k * N);
     }
     c.note(elt == m2 - 1 ? Context::OP_ROTATE_COLUMNS : Context::OP_ROTATE_ROWS_HOP, ch, n, out, in);
+    if (add_back) c.note(Context::OP_ADD, ch, n, out, in, out); // the reference issues Rotate + Add: both are counted
+}
+// x + rotate(x) in one pass (in == out allowed): the permutation kernel folds the unrotated ciphertext into the key switch's base.  Returns
+// false when the step has no key of its own (multi-hop rotation) or per-operation noise tracing wants the rotated ciphertext on its own.
+bool op_rotate_add(Context &c, int ch, const u64 *in, int n, int steps, bool columns, u64 *out) {
+    if (c.trace_noise) return false;
+    const u64 elt = columns ? 2ULL * c.N - 1 : galois_elt_from_step(c, steps);
+    if (!c.ch[ch].glk.count(elt)) return false;
+    op_apply_galois(c, ch, in, n, elt, out, true);
+    return true;
 }
 static std::vector<int> naf(int value) { // non-adjacent form, least significant term first (SEAL util::naf)
     std::vector<int> res;

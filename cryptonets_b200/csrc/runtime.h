@@ -199,7 +199,8 @@ void op_relinearize(Context &c, int ch, const u64 *in3, int n, u64 *out2);
 void op_multiply_relin(Context &c, int ch, const std::vector<const u64 *> &a, const std::vector<const u64 *> &b, u64 *out2);
 void op_key_switch(Context &c, const u64 *target, size_t target_stride, int n, const u64 *key, const DigitMap &dm, const u64 *base,
                    size_t base_stride, u64 *out);
-void op_apply_galois(Context &c, int ch, const u64 *in, int n, u64 elt, u64 *out);
+void op_apply_galois(Context &c, int ch, const u64 *in, int n, u64 elt, u64 *out, bool add_back = false);
+bool op_rotate_add(Context &c, int ch, const u64 *in, int n, int steps, bool columns, u64 *out); // out = in + rotate(in) in one pass, if possible
 void op_rotate_rows(Context &c, int ch, const u64 *in, int n, int steps, u64 *out); // steps == 0 copies
 void op_rotate_columns(Context &c, int ch, const u64 *in, int n, u64 *out);
 // Many independent single-ciphertext row rotations with DIFFERENT step counts (Interleave / Stack / Duplicate rotate every vector by its

@@ -904,11 +904,14 @@ static cnhe_vec *sum_all_slots(Context &c, const cnhe_vec *a, uint64_t length, i
         }
         u64 *tmp = c.ws_alloc(ctw);
         if (len >= N / 2) {
-            op_rotate_columns(c, ch, sum, 1, tmp);
-            do_add(c, ch, sum, tmp, sum, ctw, 0);
+            if (!op_rotate_add(c, ch, sum, 1, 0, true, sum)) { // x += rotate(x) in one pass when the step has its own key
+                op_rotate_columns(c, ch, sum, 1, tmp);
+                do_add(c, ch, sum, tmp, sum, ctw, 0);
+            }
             len = N / 2;
         }
         for (uint64_t steps = 1; steps < len; steps *= 2) { // RotateRowsAndAdd(sum, steps): RotateRows(c, -steps)
+            if (op_rotate_add(c, ch, sum, 1, -(int)steps, false, sum)) continue;
             op_rotate_rows(c, ch, sum, 1, -(int)steps, tmp);
             do_add(c, ch, sum, tmp, sum, ctw, 0);
         }
@@ -1609,12 +1612,17 @@ static uint64_t sum_slots_batched(Context &c, int ch, u64 *cts, int n, uint64_t 
     const size_t N = c.N, words = (size_t)n * c.ct_words();
     uint64_t len = length;
     u64 *tmp = c.ws_alloc(words);
+    // every step is x += rotate(x): fused into the rotation (the permutation kernel folds x into the key switch's base) when the step
+    // has its own Galois key -- it does for the powers of two the ladder walks -- else rotate, then add
     if (len >= N / 2) {
-        op_rotate_columns(c, ch, cts, n, tmp);
-        do_add(c, ch, cts, tmp, cts, words, 0);
+        if (!op_rotate_add(c, ch, cts, n, 0, true, cts)) {
+            op_rotate_columns(c, ch, cts, n, tmp);
+            do_add(c, ch, cts, tmp, cts, words, 0);
+        }
         len = N / 2;
     }
     for (uint64_t steps = 1; steps < len; steps *= 2) {
+        if (op_rotate_add(c, ch, cts, n, -(int)steps, false, cts)) continue;
         op_rotate_rows(c, ch, cts, n, -(int)steps, tmp);
         do_add(c, ch, cts, tmp, cts, words, 0);
     }

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== pytest -m gpu"; (timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3)
+echo "== bench lola_small"; timeout 600 python bench.py --workload lola_small --steps 20 --warmup 3 2>>gpurun_out/r02_bench.err | tail -1 > gpurun_out/r02_bench_lola_small.json; python -c "
+import json;d=json.load(open('gpurun_out/r02_bench_lola_small.json'));print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['families_ms_per_step'])"
+echo "== bench lola_cifar"; timeout 900 python bench.py --workload lola_cifar --steps 3 --warmup 1 2>>gpurun_out/r02_bench.err | tail -1 > gpurun_out/r02_bench_lola_cifar.json; python -c "
+import json;d=json.load(open('gpurun_out/r02_bench_lola_cifar.json'));print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['families_ms_per_step'])"
