@@ -467,3 +467,17 @@ def test_convolution_on_tensor_cores(pair, wide, capfd):
         del os.environ["CNHE_MAC_NO_UMMA"]
     for i in range(M):
         assert np.array_equal(outs2[i].export_raw(0, 0), want[i]), i
+
+
+def test_tensor_core_layers_randomised():
+    """Random dense shapes and random strided / padded convolutions (weights up to +-254, random biases, maximal words) through the
+    tcgen05 kernel and through the FP64 scalar-MAC kernel: two independent GPU implementations, bit-identical outputs
+    (tools/umma_stress.py; the oracle-checked cases are test_dense_layer_on_tensor_cores / test_convolution_on_tensor_cores)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("umma_stress", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "umma_stress.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lines = []
+    assert mod.run(16, 3, log=lines.append) == 0, "\n".join(lines)
+    assert len(lines) >= 12
