@@ -592,8 +592,10 @@ __device__ __forceinline__ void fwd_body_fp(double *sm, const FwdSrc &src, u64 *
         CNHE_VTN(N / 16, (fwd_last_fp<13, 2, OUT_F>(sm, dst, tb, vt)));
     }
 }
-template <int LOGN, bool IN_F, bool OUT_F>
-__global__ void __launch_bounds__(fp_threads(LOGN), fp_min_blocks(LOGN))
+// MINB: resident CTAs per SM the register allocation aims for (0 = fp_min_blocks).  N = 8192 with three (80 registers, 6 doubles spilled)
+// instead of two: a third CTA's memory phases fill the FP64 pipe's idle slots
+template <int LOGN, bool IN_F, bool OUT_F, int MINB = 0>
+__global__ void __launch_bounds__(fp_threads(LOGN), MINB ? MINB : fp_min_blocks(LOGN))
 k_ntt_forward_fp(const u64 *src, u64 *dst, const NttTab *__restrict__ tabs, int mod_base, int mod_count) {
     extern __shared__ __align__(16) u64 sm[];
     constexpr int N = 1 << LOGN;
@@ -606,8 +608,8 @@ k_ntt_forward_fp(const u64 *src, u64 *dst, const NttTab *__restrict__ tabs, int 
     fwd_body_fp<LOGN, IN_F, OUT_F>(reinterpret_cast<double *>(sm), fs, dst + (size_t)b * N, tb, tid);
 }
 // target: ciphertext c's polynomial with `k` residues starts at target + c * ct_stride (words)
-template <int LOGN, bool OUT_F>
-__global__ void __launch_bounds__(fp_threads(LOGN), fp_min_blocks(LOGN))
+template <int LOGN, bool OUT_F, int MINB = 0>
+__global__ void __launch_bounds__(fp_threads(LOGN), MINB ? MINB : fp_min_blocks(LOGN))
 k_ntt_forward_digits_fp(const u64 *target, size_t ct_stride, u64 *dst, const NttTab *__restrict__ tabs, int k, DigitMap dm) {
     extern __shared__ __align__(16) u64 sm[];
     constexpr int N = 1 << LOGN;
@@ -1454,6 +1456,11 @@ static bool ws_flag(const char *name, bool dflt) {
 // in its digit-cutting form), so the forward direction keeps the per-polynomial kernel unless CNHE_NTT_WS_FWD=1 asks for the staged one.
 static bool ws_enabled_fwd() { return ws_flag("CNHE_NTT_WS_FWD", false); } // read per launch: tests flip it inside one process
 static bool ws_enabled_inv() { return ws_flag("CNHE_NTT_WS_INV", true); }
+// N = 8192 forward transforms with three CTAs per SM (CNHE_NTT_FWD_BLOCKS=3) or two (=2); read per launch
+static bool fwd_three_blocks() {
+    const char *v = getenv("CNHE_NTT_FWD_BLOCKS");
+    return v ? atoi(v) == 3 : false;
+}
 // N = 16384: CTA pairs unless CNHE_NTT_SPLIT=0 (read per launch, like the flags above)
 static bool split_enabled() {
     const char *v = getenv("CNHE_NTT_SPLIT");
@@ -1557,6 +1564,18 @@ cudaError_t launch_ntt_forward(const u64 *src, u64 *dst, int n_polys, int logn, 
             }
             return cudaGetLastError();
         }
+        if (logn == 13 && fwd_three_blocks()) {
+            if (lazy) {
+                cudaError_t e = prep(k_ntt_forward_fp<13, true, true, 3>, 13);
+                if (e != cudaSuccess) return e;
+                k_ntt_forward_fp<13, true, true, 3><<<n_polys, fp_threads(13), ntt_kernel_smem_bytes(13), s>>>(src, dst, tabs, mod_base, mod_count);
+            } else {
+                cudaError_t e = prep(k_ntt_forward_fp<13, false, false, 3>, 13);
+                if (e != cudaSuccess) return e;
+                k_ntt_forward_fp<13, false, false, 3><<<n_polys, fp_threads(13), ntt_kernel_smem_bytes(13), s>>>(src, dst, tabs, mod_base, mod_count);
+            }
+            return cudaGetLastError();
+        }
         CNHE_DISPATCH_LOGN(logn, {
             if (lazy) {
                 cudaError_t e = prep(k_ntt_forward_fp<L, true, true>, L);
@@ -1605,6 +1624,18 @@ cudaError_t launch_ntt_forward_digits(const u64 *target, size_t ct_stride, u64 *
                 cudaError_t e = split_prep(k_ntt_forward_digits_split<false>);
                 if (e != cudaSuccess) return e;
                 k_ntt_forward_digits_split<false><<<2 * n_ct * dm.D * k, SPLIT_THREADS, SPLIT_SMEM, s>>>(target, ct_stride, dst, tabs, k, dm);
+            }
+            return cudaGetLastError();
+        }
+        if (logn == 13 && fwd_three_blocks()) {
+            if (fp & NTT_OUT_F) {
+                cudaError_t e = prep(k_ntt_forward_digits_fp<13, true, 3>, 13);
+                if (e != cudaSuccess) return e;
+                k_ntt_forward_digits_fp<13, true, 3><<<n_ct * dm.D * k, fp_threads(13), ntt_kernel_smem_bytes(13), s>>>(target, ct_stride, dst, tabs, k, dm);
+            } else {
+                cudaError_t e = prep(k_ntt_forward_digits_fp<13, false, 3>, 13);
+                if (e != cudaSuccess) return e;
+                k_ntt_forward_digits_fp<13, false, 3><<<n_ct * dm.D * k, fp_threads(13), ntt_kernel_smem_bytes(13), s>>>(target, ct_stride, dst, tabs, k, dm);
             }
             return cudaGetLastError();
         }
