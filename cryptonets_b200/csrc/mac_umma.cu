@@ -15,15 +15,16 @@
 //     as many bytes in flight as HBM latency needs.  (Issuing one 256-byte cp.async.bulk per tap cost ~60 cycles each: 94 % of the
 //     first version's time.)  The few taps whose weights exceed a signed byte (W = W1 + W2) are gathered into a scratch slab by the
 //     host call and appear a second time, as extra chunks with W2 as their weights, through a second map;
-//   * four "cutter" warps turn a raw stage into the B operand -- limb a of word n is row a*32 + n of a K-major, unswizzled
-//     UMMA tile (8-row x 16-byte core matrices) -- with conflict-free 32-bit stores;
+//   * eight "cutter" warps turn a raw stage into the B operand -- limb a of word n is row a*32 + n of a K-major, unswizzled
+//     UMMA tile (8-row x 16-byte core matrices) -- three byte permutes per limb, conflict-free 32-bit stores;
 //   * one thread issues ONE tcgen05.mma (M = 128 outputs, N = 32 * limbs, K = 32 taps) per stage against the weight chunk that
 //     has been resident in shared memory since the CTA started (A operand, packed by the host in core-matrix order), and
 //     tcgen05.commit hands the B stage back;
 //   * persistent CTAs (one per SM) walk the 32-word tiles of the ciphertext, and inside a tile the bundles of the layer.
 // Warp roles: 0-3 and 8-11 epilogue (TMEM lanes 32 (w % 4).. = output rows; each thread writes its row's 32 words straight to HBM, 64
 // bytes at a time; one group per accumulator buffer), 4 TMA producer, 5 MMA issuer, 6-7 and 12-17 cutters.
-// Output words are bit-identical to k_mac_dense_imma / k_mac_layer_fp (tests/test_gpu_kernels.py::test_mac_layer_*).
+// Output words are bit-identical to k_mac_dense_imma / k_mac_layer_fp and to the oracle (tests/test_gpu_kernels.py:
+// test_dense_layer_on_tensor_cores, test_convolution_on_tensor_cores, test_tensor_core_layers_randomised).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
