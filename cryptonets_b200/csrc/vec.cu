@@ -1281,7 +1281,13 @@ static std::shared_ptr<UmmaPlan> umma_plan(Context &c, int ch, const std::vector
         for (size_t i = 0; i < bytes / 8; i++) { key ^= w[i]; key *= 0x100000001b3ULL; key ^= key >> 29; }
     };
     mix(wdh.data(), wdh.size() * 8);
-    mix(grows.data(), grows.size() / 2 * 8);
+    {
+        std::vector<int> shape(grows); // the distinct gather rows, then which row every output reads
+        shape.resize(grows.size() + (size_t)M + 1, -2);
+        for (size_t r = 0; r < row_outs.size(); r++)
+            for (int m : row_outs[r]) shape[grows.size() + (size_t)m] = (int)r;
+        mix(shape.data(), shape.size() / 2 * 8);
+    }
     auto hit = c.umma_plans.find(key);
     if (hit != c.umma_plans.end()) return std::static_pointer_cast<UmmaPlan>(hit->second);
     std::shared_ptr<UmmaPlan> best;
