@@ -288,6 +288,106 @@ __global__ void __launch_bounds__(256) k_ks_mac_fp(const u64 *__restrict__ digit
     }
 }
 
+// ---- the same inner product with the operands staged by the copy engine (cp.async.bulk -> shared memory ring, mbarriers): the register
+// version above is bound by load latency (ncu: long_scoreboard 10 stall cycles per issue, 49 % of DRAM bandwidth) -- it can keep only as
+// many bytes in flight as it has registers for.  Here one producer thread streams, per digit, the tile's slice of CT digit polynomials
+// (HBM) and of the two key polynomials (L2) into a four-stage ring; 256 consumer threads (2 coefficients each) run the identical
+// arithmetic in the identical order out of shared memory.  CTA = (group of CT ciphertexts, residue l, 512 coefficients).
+constexpr int KT_X = 512, KT_STAGES = 4, KT_CONSUMERS = 256, KT_THREADS = KT_CONSUMERS + 32;
+__device__ __forceinline__ unsigned kt_sptr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void kt_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = kt_sptr(bar);
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; spin++) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done && spin > (1u << 28)) __trap(); // a protocol error fails the launch instead of hanging the GPU
+    }
+}
+template <int CT>
+__global__ void __launch_bounds__(KT_THREADS, 2) k_ks_mac_tma(const u64 *__restrict__ digits, const u64 *__restrict__ key, u64 *__restrict__ acc, int n, int D,
+                                                             int logn, const __grid_constant__ BehzConstF F) {
+    extern __shared__ __align__(128) unsigned char kt_smem[];
+    constexpr int STAGE_BYTES = (CT + 2) * KT_X * 8;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(kt_smem + KT_STAGES * STAGE_BYTES);
+    unsigned long long *full = bars, *empty = bars + KT_STAGES;
+    const int N = 1 << logn, k = F.k, tid = threadIdx.x;
+    const int tiles = N / KT_X;
+    const int tile = blockIdx.x % tiles, l = (blockIdx.x / tiles) % k, c0 = (blockIdx.x / (tiles * k)) * CT;
+    const int x0 = tile * KT_X;
+    const size_t kpoly = (size_t)k * N, kstride = (size_t)2 * k * N, cstride = (size_t)k * D * N;
+    const int n_here = min(CT, n - c0);
+    if (tid == 0) {
+        for (int i = 0; i < KT_STAGES; i++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kt_sptr(full + i)), "r"(1u));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kt_sptr(empty + i)), "r"((unsigned)KT_CONSUMERS));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid >= KT_CONSUMERS) {
+        if (tid == KT_CONSUMERS) { // producer
+            const u64 *dg = digits + ((size_t)c0 * k + l) * D * N + x0;
+            const u64 *k0 = key + (size_t)l * N + x0;
+            for (int dd = 0; dd < D; dd++) {
+                const int s = dd % KT_STAGES;
+                kt_wait(empty + s, (((unsigned)dd / KT_STAGES) & 1) ^ 1);
+                unsigned char *st = kt_smem + s * STAGE_BYTES;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(kt_sptr(full + s)), "r"((unsigned)((n_here + 2) * KT_X * 8)) : "memory");
+                for (int ci = 0; ci < n_here; ci++)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(kt_sptr(st + ci * KT_X * 8)),
+                                 "l"(dg + (size_t)ci * cstride + (size_t)dd * N), "r"((unsigned)(KT_X * 8)), "r"(kt_sptr(full + s))
+                                 : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(kt_sptr(st + CT * KT_X * 8)),
+                             "l"(k0 + (size_t)dd * kstride), "r"((unsigned)(KT_X * 8)), "r"(kt_sptr(full + s))
+                             : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(kt_sptr(st + (CT + 1) * KT_X * 8)),
+                             "l"(k0 + (size_t)dd * kstride + kpoly), "r"((unsigned)(KT_X * 8)), "r"(kt_sptr(full + s))
+                             : "memory");
+            }
+        }
+        return;
+    }
+    const double p = F.qd[l], pinv = F.qinv[l];
+    double a[CT][4]; // [ciphertext][key poly * 2 + coefficient]
+#pragma unroll
+    for (int ci = 0; ci < CT; ci++) a[ci][0] = a[ci][1] = a[ci][2] = a[ci][3] = 0.0;
+    for (int dd = 0; dd < D; dd++) {
+        const int s = dd % KT_STAGES;
+        kt_wait(full + s, ((unsigned)dd / KT_STAGES) & 1);
+        const ulonglong2 *st = reinterpret_cast<const ulonglong2 *>(kt_smem + s * STAGE_BYTES);
+        const ulonglong2 w0u = st[CT * (KT_X / 2) + tid], w1u = st[(CT + 1) * (KT_X / 2) + tid];
+        const double w00 = u2d(w0u.x), w01 = u2d(w0u.y), w10 = u2d(w1u.x), w11 = u2d(w1u.y);
+#pragma unroll
+        for (int ci = 0; ci < CT; ci++) {
+            if (ci < n_here) {
+                const ulonglong2 vu = st[ci * (KT_X / 2) + tid];
+                const double v0 = __longlong_as_double((long long)vu.x), v1 = __longlong_as_double((long long)vu.y);
+                a[ci][0] = __dadd_rn(a[ci][0], fmodmul(v0, w00, p, pinv));
+                a[ci][1] = __dadd_rn(a[ci][1], fmodmul(v1, w01, p, pinv));
+                a[ci][2] = __dadd_rn(a[ci][2], fmodmul(v0, w10, p, pinv));
+                a[ci][3] = __dadd_rn(a[ci][3], fmodmul(v1, w11, p, pinv));
+            }
+        }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(kt_sptr(empty + s)) : "memory"); // this thread is done with the stage
+        if ((dd & 7) == 7) { // sums of 8 fresh products stay below 4.1 p; re-centre before they could leave the exact range
+#pragma unroll
+            for (int ci = 0; ci < CT; ci++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) a[ci][j] = frecenter(a[ci][j], p, pinv);
+        }
+    }
+    const int x = x0 + 2 * tid;
+#pragma unroll
+    for (int ci = 0; ci < CT; ci++) {
+        if (ci >= n_here) break;
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[ci][j] = frecenter(a[ci][j], p, pinv);
+        const size_t o = ((size_t)((c0 + ci) * 2) * k + l) * N + x;
+        *reinterpret_cast<ulonglong2 *>(acc + o) = make_ulonglong2(lazy_bits(a[ci][0]), lazy_bits(a[ci][1]));
+        *reinterpret_cast<ulonglong2 *>(acc + o + kpoly) = make_ulonglong2(lazy_bits(a[ci][2]), lazy_bits(a[ci][3]));
+    }
+}
+
 static inline unsigned blocks_for(size_t threads) { return (unsigned)((threads + 255) / 256); }
 
 // `f` is the HOST copy of the constants (passed by value into the kernel's parameter space)
@@ -322,6 +422,16 @@ cudaError_t launch_ks_mac_fp(const u64 *digits, const u64 *key, u64 *acc, int n,
     static const int cts = getenv("CNHE_KSMAC_CT") ? atoi(getenv("CNHE_KSMAC_CT")) : 4; // ciphertexts per thread (key reuse)
     // key reuse pays once the launch fills the GPU anyway: with few ciphertexts (LoLa: 1-32 per call) four per thread leaves SMs idle
     const int ct = n < 64 ? 1 : (cts == 1 || cts == 2 || (cts == 8 && lazy) ? cts : 4);
+    // full waves of lazy digits: the copy-engine-staged kernel (CNHE_KSMAC_TMA=0 keeps the register version)
+    const bool tma = getenv("CNHE_KSMAC_TMA") ? atoi(getenv("CNHE_KSMAC_TMA")) != 0 : true; // read per launch (tests compare both)
+    if (lazy && tma && ct == 4 && (1 << logn) % KT_X == 0) {
+        constexpr int smem = KT_STAGES * (4 + 2) * KT_X * 8 + 2 * KT_STAGES * 8;
+        cudaError_t e = cudaFuncSetAttribute(k_ks_mac_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        const unsigned grid = (unsigned)(((1 << logn) / KT_X) * k * ((n + 3) / 4));
+        k_ks_mac_tma<4><<<grid, KT_THREADS, smem, s>>>(digits, key, acc, n, D, logn, *f);
+        return cudaGetLastError();
+    }
     const unsigned blocks = blocks_for(((size_t)((n + ct - 1) / ct) * k) << (logn - 1));
     if (!lazy) {
         if (ct == 4) k_ks_mac_fp<false, 1, 4><<<blocks, 256, 0, s>>>(digits, key, acc, n, D, logn, *f);

@@ -481,3 +481,27 @@ def test_tensor_core_layers_randomised():
     lines = []
     assert mod.run(16, 3, log=lines.append) == 0, "\n".join(lines)
     assert len(lines) >= 12
+
+
+def test_key_switch_mac_full_waves(pair, monkeypatch):
+    """Waves of 64 or more ciphertexts take the key-switch inner product through the copy-engine-staged kernel (cp.async.bulk ring, four
+    ciphertexts per CTA share the key words); smaller calls and CNHE_KSMAC_TMA=0 use the register kernels.  70 ciphertexts (a ragged last
+    group of two): multiply + relinearise must match the oracle on sampled ciphertexts and the register kernel on all of them."""
+    eng, orc, name = pair
+    if eng.N > 8192:
+        pytest.skip("oracle time")
+    N, k = eng.N, eng.k
+    m = 70
+    _, few = _fresh_cts(orc, 6, 21, nonce0=3000)
+    cts = np.stack([few[i % 6] for i in range(m)])
+    cts[1::2] = np.roll(cts[1::2], 1, axis=0)  # not all groups alike
+    a, o1, o2 = eng.dev_from(cts), eng.dev_alloc(m * 2 * k * N), eng.dev_alloc(m * 2 * k * N)
+    eng.raw_multiply_relin(0, a, a, m, o1)
+    got = eng.dev_download(o1, m * 2 * k * N).reshape(m, -1)
+    for i in (0, 3, 33, 67, 68, 69):
+        assert np.array_equal(got[i], orc.relinearize(orc.multiply(cts[i], cts[i]))), i
+    monkeypatch.setenv("CNHE_KSMAC_TMA", "0")
+    eng.raw_multiply_relin(0, a, a, m, o2)
+    assert np.array_equal(eng.dev_download(o2, m * 2 * k * N).reshape(m, -1), got)
+    for d in (a, o1, o2):
+        eng.dev_free(d)
