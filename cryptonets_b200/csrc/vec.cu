@@ -1272,6 +1272,45 @@ static bool umma_try(UmmaPlan &pl, int g, const std::vector<int> &grows, const s
     }
     return true;
 }
+// the search itself (host only): every bundle size g = 1, 2, ... rows; the plan with the fewest chunks per tile that fits in shared memory
+static std::shared_ptr<UmmaPlan> umma_search(const std::vector<int> &grows, const std::vector<std::vector<int>> &row_outs, const std::vector<double> &wdh,
+                                             int M, int K, int limbs) {
+    std::shared_ptr<UmmaPlan> best;
+    const int R = (int)row_outs.size();
+    for (int g = 1; g <= R; g++) {
+        auto pl = std::make_shared<UmmaPlan>();
+        if (!umma_try(*pl, g, grows, row_outs, wdh, K)) {
+            if (g > 1 && (size_t)g * row_outs[0].size() > 128) break; // larger groups only grow
+            continue;
+        }
+        if (!mac_umma_fits((int)pl->wpack.size(), pl->total_chunks, M, (int)pl->bundles.size(), limbs)) continue;
+        if (!best || pl->total_chunks < best->total_chunks) best = pl;
+        if (g > 64) break;
+    }
+    return best;
+}
+// Planner probe for the CPU test suite (not part of include/cnhe.h, needs no GPU): gather[M][K] (-1 = padded tap), signed integer weights
+// w[M][K]; out = {bundles, chunks per tile, weight bytes after de-duplication, extra (W2) taps}; returns 0 when no plan fits.
+extern "C" int cnhe_debug_mac_plan(const int32_t *gather, const double *w, int M, int K, int limbs, int *out) {
+    std::unordered_map<std::vector<int>, int, RowHash> index;
+    std::vector<int> grows;
+    std::vector<std::vector<int>> row_outs;
+    for (int m = 0; m < M; m++) {
+        std::vector<int> row(gather + (size_t)m * K, gather + (size_t)(m + 1) * K);
+        auto it = index.find(row);
+        if (it == index.end()) {
+            index.emplace(row, (int)row_outs.size());
+            grows.insert(grows.end(), row.begin(), row.end());
+            row_outs.push_back({m});
+        } else
+            row_outs[it->second].push_back(m);
+    }
+    std::vector<double> wdh(w, w + (size_t)M * K);
+    std::shared_ptr<UmmaPlan> pl = umma_search(grows, row_outs, wdh, M, K, limbs);
+    if (!pl) return 0;
+    out[0] = (int)pl->bundles.size(); out[1] = pl->total_chunks; out[2] = (int)pl->wpack.size(); out[3] = (int)pl->extra_taps.size();
+    return 1;
+}
 // fewest chunks per tile over the bundle sizes that fit in shared memory; cached per layer (keyed by a hash of its gather table and weights)
 static std::shared_ptr<UmmaPlan> umma_plan(Context &c, int ch, const std::vector<int> &grows, const std::vector<std::vector<int>> &row_outs,
                                            const std::vector<double> &wdh, int M, int K, int limbs) {
@@ -1290,18 +1329,7 @@ static std::shared_ptr<UmmaPlan> umma_plan(Context &c, int ch, const std::vector
     }
     auto hit = c.umma_plans.find(key);
     if (hit != c.umma_plans.end()) return std::static_pointer_cast<UmmaPlan>(hit->second);
-    std::shared_ptr<UmmaPlan> best;
-    const int R = (int)row_outs.size();
-    for (int g = 1; g <= R; g++) {
-        auto pl = std::make_shared<UmmaPlan>();
-        if (!umma_try(*pl, g, grows, row_outs, wdh, K)) {
-            if (g > 1 && (size_t)g * row_outs[0].size() > 128) break; // larger groups only grow
-            continue;
-        }
-        if (!mac_umma_fits((int)pl->wpack.size(), pl->total_chunks, M, (int)pl->bundles.size(), limbs)) continue;
-        if (!best || pl->total_chunks < best->total_chunks) best = pl;
-        if (g > 64) break;
-    }
+    std::shared_ptr<UmmaPlan> best = umma_search(grows, row_outs, wdh, M, K, limbs);
     if (!best) best = std::make_shared<UmmaPlan>();
     else {
         best->ok = true;
