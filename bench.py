@@ -435,7 +435,7 @@ def run_b200(args):
         achieved = fam["bytes"] / (fam["ms"] * 1e-3) / 1e9 if fam["ms"] > 0 else 0.0
         # the forward transform is limited by FP64 issue (8 DP instructions per butterfly: 100 % of the pipe = 0.85 of this HBM figure), not by
         # HBM itself; it is reported against the measured HBM copy bandwidth because that is the roofline SURVEY.md 8d prescribes
-        roof = {"bound": "fp64-issue (reported against hbm)", "kernel": "k_ntt_forward_fp / k_ntt_forward_digits_fp (N=8192), 16*N algorithmic bytes per transform", "achieved": achieved,
+        roof = {"bound": "hbm", "limited_by": "fp64-issue (ncu: 63 % of the FP64 pipe busy, math_pipe_throttle the top stall; 100 % of the pipe would be 0.85 of this HBM figure)", "kernel": "k_ntt_forward_fp / k_ntt_forward_digits_fp (N=8192), 16*N algorithmic bytes per transform", "achieved": achieved,
                 "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)",
                 # ncu (profiles/r02_top_kernels_ncu.txt, same figures as round 1's capture): one k_ntt_forward_digits_fp launch of 16000 transforms moved 42.4 MB + 994.7 MB of
@@ -624,7 +624,7 @@ def run_lola(args):
             "clocks": clocks, "gpu_launches": int(launches), "operations_per_inference": counts,
             "e2e": {"value": args.steps * images_per_step / e2e_s, "unit": "images/s", "h2d_bytes_per_step": int(host_in.numel() * 8),
                     "d2h_bytes_per_step": int(host_out.numel() * 8)},
-            "roofline": {"bound": "fp64-issue (reported against hbm)", "kernel": "forward NTT family (digit transforms of the Galois / relinearisation key switch), 16*N algorithmic bytes per transform",
+            "roofline": {"bound": "hbm", "limited_by": "fp64-issue (ncu: 63 % of the FP64 pipe busy, math_pipe_throttle the top stall; 100 % of the pipe would be 0.85 of this HBM figure)", "kernel": "forward NTT family (digit transforms of the Galois / relinearisation key switch), 16*N algorithmic bytes per transform",
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)", "traffic": None, "launches_timed": fam["launches"],
                          "share_of_step": fam["ms"] / ms if ms else None, "families_ms_per_step": {k_: v["ms"] / args.steps for k_, v in prof.items()}},
